@@ -1,0 +1,174 @@
+/*
+ * wbem.h -- C ABI of the B200-native collocation-BEM hot path (libwbem.so).
+ *
+ * Drop-in boundary for WaveBEM's BEMProblem<3> (reference include/bem_problem.h:87-180,
+ * source/bem_problem.cc).  Every entry point is extern "C", takes plain pointers and sizes,
+ * returns an int status: 0 = ok, <0 = fatal (CUDA / NCCL / allocation / bad argument),
+ * >0 = solver did not converge (the adapter rethrows it as SolverControl::NoConvergence).
+ * wbem_last_error() gives the message.  All host arrays are caller-owned, contiguous,
+ * fp64 / uint32 / uint8; the library owns all device memory inside the opaque context.
+ * One calling host thread per context (the reference is single-threaded, main.cc:26).
+ *
+ * There is NO CPU fallback: every compute entry point fails (<0) when no sm_100 device is
+ * usable.
+ *
+ * Multi-GPU: one process (context) per GPU.  Context `rank` of `world_size` owns the
+ * contiguous block of matrix rows [rank*ceil(N/P), min(N,(rank+1)*ceil(N/P))); vectors,
+ * geometry, masks and constraints are replicated.  Matrix-vector products all-gather the
+ * row blocks over NCCL (wbem_comm_init).
+ */
+#ifndef WBEM_H
+#define WBEM_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct wbem_ctx wbem_ctx;
+
+/* Replaces the prm keys the path reads: "Quadrature rules/{Quadrature order, Singular
+ * quadrature order}" (source/computational_domain.cc:84-91,123-131), "Solver/{Tolerance,
+ * Max steps}" (source/bem_problem.cc:83-85,95-97), the GMRES AdditionalData(100)
+ * (source/bem_problem.cc:826-827) and preconditioner_band = 100 (:68). */
+typedef struct wbem_params
+{
+  int quad_order;          /* Gauss n x n, default 4 */
+  int sing_order;          /* QGaussOneOverR n -> 2 n^2 points, default 5 */
+  double gmres_tol;        /* absolute, on the preconditioned residual; default 1e-16 */
+  int gmres_max_steps;     /* default 200 */
+  int gmres_n_tmp_vectors; /* default 100 (Krylov basis 98) */
+  int preconditioner_band; /* default 100; 0 disables the band preconditioner */
+  int device;              /* CUDA device ordinal */
+  int rank;                /* this context's row block */
+  int world_size;          /* number of row blocks (GPUs) */
+  int assemble_variant;    /* 0 = default (tiled, deterministic), 1 = simple atomic kernel */
+  int precond_on_host;     /* 1 = band LU + solves on the host (debug), 0 = on the device */
+  int reserved[5];
+} wbem_params;
+
+typedef struct wbem_timings
+{ /* device milliseconds measured with CUDA events on the library's stream (last call) */
+  double geometry_ms;      /* cell quadrature data */
+  double assemble_regular_ms;
+  double assemble_singular_ms;
+  double alpha_ms;
+  double assemble_total_ms;
+  double rhs_ms;
+  double precond_setup_ms;
+  double gmres_ms;         /* whole GMRES loop */
+  double gemv_ms_sum;      /* sum over operator applications in the last solve */
+  double precond_apply_ms_sum;
+  double allgather_ms_sum;
+  double solve_system_total_ms;
+  int gemv_calls;
+  int gmres_iters;
+  long long kernel_launches; /* kernels of this library launched since create/reset */
+  double gemv_bytes_last;  /* matrix bytes the last operator application had to stream */
+  double reserved[6];
+} wbem_timings;
+
+void wbem_default_params(wbem_params *p);
+int wbem_create(const wbem_params *p, wbem_ctx **out);
+int wbem_destroy(wbem_ctx *ctx);
+const char *wbem_last_error(const wbem_ctx *ctx); /* ctx may be NULL: last create error */
+int wbem_version(void);
+
+/* BEMProblem<3>::reinit (source/bem_problem.cc:55-71) + the once-per-mesh flattening of
+ * comp_dom.dh / comp_dom.double_nodes_set (source/bem_problem.cc:192-196, 223-230).
+ * cell_dofs[C][4]: deal.II lexicographic vertex order; cell_dir_flag[C]:
+ * cell->direction_flag(); dn_ptr[N+1], dn_idx[]: CSR of double_nodes_set (set i holds i). */
+int wbem_set_topology(wbem_ctx *ctx, uint32_t n_dofs, uint32_t n_cells,
+                      const uint32_t *cell_dofs, const uint8_t *cell_dir_flag,
+                      const uint32_t *dn_ptr, const uint32_t *dn_idx);
+
+/* Per assembly: support_points[N][3] = DoFTools::map_dofs_to_support_points
+ * (source/bem_problem.cc:168-169).  The Q1 mapping's quadrature points, normals and JxW
+ * (the FEValues of :133-137, 192-196, 495-501) are recomputed on the device from them. */
+int wbem_set_geometry(wbem_ctx *ctx, const double *support_points);
+int wbem_set_geometry_dev(wbem_ctx *ctx, const double *d_support_points);
+
+/* BEMProblem<3>::assemble_system (source/bem_problem.cc:106-590): both matrices for this
+ * context's rows, plus alpha (compute_alpha, :594-618) fused behind it. */
+int wbem_assemble(wbem_ctx *ctx);
+/* BEMProblem<3>::compute_alpha alone (:594-618). */
+int wbem_compute_alpha(wbem_ctx *ctx);
+int wbem_get_alpha(wbem_ctx *ctx, double *alpha /* [N] */);
+
+/* Test/preconditioner access to matrix entries (the reference exposes neumann_matrix and
+ * dirichlet_matrix as public members, include/bem_problem.h:153-154).  which: 0 = Neumann
+ * (double layer), 1 = Dirichlet (single layer).  Rows [r0,r1) must lie inside this
+ * context's row block; out is (r1-r0) x N row-major in global dof numbering. */
+int wbem_get_rows(wbem_ctx *ctx, int which, uint32_t r0, uint32_t r1, double *out);
+int wbem_row_block(const wbem_ctx *ctx, uint32_t *row0, uint32_t *row1);
+
+/* comp_dom.surface_nodes / other_nodes (source/numerical_towing_tank.cc:1799-1807); callers
+ * mutate them between solves (source/free_surface.cc:642-675, 6048-6049). */
+int wbem_set_masks(wbem_ctx *ctx, const double *surface_nodes, const double *other_nodes);
+
+/* ConstraintMatrix built by compute_constraints (source/bem_problem.cc:990-1105), flattened:
+ * line k constrains dof lines[k] = sum_j val[j] x[col[j]] (j in ptr[k]..ptr[k+1]) + inhom[k]. */
+int wbem_set_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t *lines,
+                         const uint32_t *ptr, const uint32_t *col, const double *val,
+                         const double *inhom);
+
+/* BEMProblem<3>::vmult (source/bem_problem.cc:620-670). */
+int wbem_vmult(wbem_ctx *ctx, double *dst, const double *src);
+/* ConstrainedOperator::vmult / distribute_rhs (include/constrained_matrix.h:73-94). */
+int wbem_constrained_vmult(wbem_ctx *ctx, double *dst, const double *src);
+int wbem_distribute_rhs(wbem_ctx *ctx, double *rhs);
+/* BEMProblem<3>::compute_rhs (source/bem_problem.cc:673-707). */
+int wbem_compute_rhs(wbem_ctx *ctx, double *dst, const double *src);
+/* BEMProblem<3>::assemble_preconditioner (source/bem_problem.cc:1107-1149). */
+int wbem_assemble_preconditioner(wbem_ctx *ctx);
+int wbem_precond_vmult(wbem_ctx *ctx, double *dst, const double *src);
+/* the band_system entries of this context's rows: out[(r-row0)*band + (i-(r-band/2+1))] */
+int wbem_get_band(wbem_ctx *ctx, double *out);
+
+/* BEMProblem<3>::solve_system (source/bem_problem.cc:821-895).  phi / dphi_dn are in-out:
+ * only the unknown half is overwritten (:869-879).  iters / last_res may be NULL.
+ * Returns 1 when GMRES hits max_steps (SolverControl::NoConvergence). */
+int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double *tmp_rhs,
+                      int *iters, double *last_res);
+/* BEMProblem<3>::solve (source/bem_problem.cc:969-987) = assemble_system + solve_system,
+ * with the geometry upload in front (the caller moved the mesh,
+ * source/free_surface.cc:5306-5307). */
+int wbem_solve(wbem_ctx *ctx, const double *support_points, double *phi, double *dphi_dn,
+               const double *tmp_rhs, int *iters, double *last_res);
+/* Same with every array already in device memory (bench `value` leg). */
+int wbem_solve_dev(wbem_ctx *ctx, const double *d_support_points, double *d_phi,
+                   double *d_dphi_dn, const double *d_tmp_rhs, int *iters, double *last_res);
+int wbem_solve_system_dev(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn,
+                          const double *d_tmp_rhs, int *iters, double *last_res);
+/* BEMProblem<3>::residual (source/bem_problem.cc:903-961). */
+int wbem_residual(wbem_ctx *ctx, double *res, const double *phi, const double *dphi_dn);
+
+/* system_rhs / sol of the last solve_system (public members, include/bem_problem.h:155-158) */
+int wbem_get_system_rhs(wbem_ctx *ctx, double *out);
+int wbem_get_sol(wbem_ctx *ctx, double *out);
+
+int wbem_get_timings(wbem_ctx *ctx, wbem_timings *out);
+int wbem_reset_counters(wbem_ctx *ctx);
+
+/* Row-sharded runs: rank 0 makes an id (128 bytes), the launcher (torch.distributed, MPI,
+ * ...) broadcasts it, every rank calls wbem_comm_init. */
+int wbem_comm_unique_id(void *id128);
+int wbem_comm_init(wbem_ctx *ctx, const void *id128);
+
+/* Diagnostics used by bench.py: measured FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s)
+ * of this device; one operator application timed alone. */
+int wbem_measure_fp64_peak(wbem_ctx *ctx, double *tflops);
+int wbem_measure_copy_bw(wbem_ctx *ctx, double *gbs);
+int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, double *bytes);
+int wbem_time_assemble(wbem_ctx *ctx, int reps, double *ms_avg);
+/* device self test of the fast 1/sqrt used by the regular-pair kernel: out[i] = rsqrt(in[i]) */
+int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out, int n);
+/* host-only check of the assembly tiling plan (no GPU): 0 = all invariants hold */
+int wbem_plan_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *cell_dofs, uint32_t w_max,
+                    uint32_t max_cells, double *stats8);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* WBEM_H */

@@ -1,0 +1,52 @@
+import os
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+if ROOT not in sys.path:
+    sys.path.insert(0, ROOT)
+
+
+def pytest_configure(config):
+    config.addinivalue_line("markers", "gpu: needs a B200 (run with -m gpu on the GPU box)")
+
+
+@pytest.fixture(scope="session")
+def orc():
+    """The CPU oracle (oracle/wbem_oracle.c) -- the checker, never the product."""
+    from oracle import oracle
+    oracle.build()
+    return oracle
+
+
+@pytest.fixture(scope="session")
+def wb():
+    import wavebem_b200
+    if not os.path.exists(wavebem_b200.LIB_PATH):
+        from wavebem_b200 import build
+        build.build()
+    return wavebem_b200
+
+
+def rel_err_rowscaled(a, b):
+    """Parity metric of SURVEY 7/8c: |a-b| <= tol * max(|a|,|b|,row_scale), row_scale = max_j |b_ij|.
+    Returns max over entries of |a-b| / that scale (double-layer entries between coplanar
+    panels are analytically 0, so a purely relative error is meaningless there)."""
+    a = np.asarray(a)
+    b = np.asarray(b)
+    scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), np.abs(b).max(axis=-1, keepdims=True))
+    scale = np.where(scale == 0, 1.0, scale)
+    return float((np.abs(a - b) / scale).max())
+
+
+def make_problem(mesh, orc_mod=None, bc=None):
+    """Boundary data + constraint lines for a mesh (host logic shared by oracle and GPU)."""
+    from wavebem_b200 import meshgen
+    from wavebem_b200.constraints import compute_constraints
+    if bc is None:
+        bc = meshgen.towing_tank_bc(mesh)
+    nn = meshgen.cell_normals_at_nodes(mesh)
+    cl = compute_constraints(mesh.dn_ptr, mesh.dn_idx, mesh.surface_nodes, bc, nodes_normals=nn)
+    return bc, nn, cl

@@ -1,0 +1,273 @@
+"""Known-answer tests that pin the CPU oracle from first principles.
+
+The reference (mathLab/WaveBEM) has no test for this path and cannot be built here, so these
+KATs are what anchors the oracle: quadrature identities, flat-panel integrals, solid angles of
+closed surfaces, manufactured harmonic fields, and linear-algebra cross checks with numpy.
+"""
+import numpy as np
+import pytest
+
+from wavebem_b200 import meshgen
+from wavebem_b200.constraints import compute_constraints
+
+
+def test_gauss_legendre_exactness(orc):
+    for n in (1, 2, 4, 5, 8):
+        x, w = orc.gauss01(n)
+        assert abs(w.sum() - 1.0) < 1e-15
+        for k in range(2 * n):  # exact for degree <= 2n-1
+            assert abs((w * x ** k).sum() - 1.0 / (k + 1)) < 2e-15
+    # published 4-point nodes on [-1,1]
+    x, w = orc.gauss01(4)
+    ref = np.array([-0.8611363115940526, -0.3399810435848563, 0.3399810435848563, 0.8611363115940526])
+    assert np.abs((2 * x - 1) - ref).max() < 1e-15
+    assert np.abs(2 * w - np.array([0.3478548451374538, 0.6521451548625461, 0.6521451548625461, 0.3478548451374538])).max() < 1e-15
+
+
+def test_qgauss2_order_x_fastest(orc):
+    uv, w = orc.qgauss2(4)
+    x, w1 = orc.gauss01(4)
+    assert np.allclose(uv[:4, 0], x) and np.allclose(uv[:4, 1], x[0])
+    assert np.allclose(uv[4, :], [x[0], x[1]])
+    assert abs(w.sum() - 1) < 1e-15
+
+
+def test_qgauss_one_over_r_identities(orc):
+    """SURVEY 8c KAT (1): sum w = 1 (area) to 2.3e-7 and sum w/R = 2 ln(1+sqrt 2) to 4.6e-8 at n=5;
+    both to <= 5e-15 at n=12."""
+    exact = 2 * np.log(1 + np.sqrt(2))
+    corners = np.array([[0, 0], [1, 0], [0, 1], [1, 1]], dtype=float)
+    for v in range(4):
+        uv, w = orc.qgauss_one_over_r(5, v)
+        assert len(w) == 50
+        assert (uv >= -1e-15).all() and (uv <= 1 + 1e-15).all()
+        r = np.linalg.norm(uv - corners[v], axis=1)
+        assert abs(w.sum() - 1) < 2.4e-7
+        assert abs((w / r).sum() - exact) < 4.7e-8
+        uv, w = orc.qgauss_one_over_r(12, v)
+        r = np.linalg.norm(uv - corners[v], axis=1)
+        assert abs(w.sum() - 1) < 5e-15
+        assert abs((w / r).sum() - exact) < 5e-15
+
+
+def test_fe_values_flat_and_flags(orc):
+    X = np.array([[0, 0, 0], [2, 0, 0], [0, 3, 0], [2, 3, 0]], dtype=float)
+    uv, w = orc.qgauss2(4)
+    qp, nr, jw, sh = orc.fe_values(X, 1, uv, w)
+    assert np.allclose(nr, [0, 0, 1]) and abs(jw.sum() - 6) < 1e-14
+    assert np.allclose(qp[:, 0], 2 * uv[:, 0]) and np.allclose(qp[:, 1], 3 * uv[:, 1])
+    assert np.allclose(sh.sum(axis=0), 1)
+    _, nr2, _, _ = orc.fe_values(X, 0, uv, w)
+    assert np.allclose(nr2, [0, 0, -1])
+
+
+def test_flat_panel_corner(orc):
+    """KAT (2): unit square panel, node at a corner: single-layer row sum = 2 ln(1+sqrt2)/(4 pi),
+    double layer = 0."""
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], dtype=float)
+    cells = np.array([[0, 1, 2, 3]], dtype=np.uint32)
+    ptr = np.arange(5, dtype=np.uint32)
+    idx = np.arange(4, dtype=np.uint32)
+    nm, dm = orc.assemble_rows(xyz, cells, np.ones(1, np.uint8), ptr, idx)
+    exact = 2 * np.log(1 + np.sqrt(2)) / (4 * np.pi)
+    assert np.abs(dm.sum(axis=1) - exact).max() < 1e-8
+    assert np.abs(nm).max() < 1e-16
+
+
+@pytest.mark.parametrize("n", [3, 6])
+def test_cube_solid_angles(orc, n):
+    """KAT (3): alpha = -sum_j N_ij -> 1/2 (face), 1/4 (edge), 1/8 (corner)."""
+    m = meshgen.cube(n)
+    nm, _ = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    alpha = orc.compute_alpha(nm)
+    sz = np.diff(m.dn_ptr)
+    assert np.abs(alpha[sz == 1] - 0.5).max() < 1e-5
+    assert np.abs(alpha[sz == 2] - 0.25).max() < 1e-5
+    assert np.abs(alpha[sz == 3] - 0.125).max() < 1e-8
+
+
+def test_renumbering_and_direction_flags_are_equivalent(orc):
+    m0 = meshgen.cube(3)
+    m1 = meshgen.cube(3, flip_every=2)
+    n0, d0 = orc.assemble_rows(m0.xyz, m0.cells, m0.dir_flag, m0.dn_ptr, m0.dn_idx)
+    n1, d1 = orc.assemble_rows(m1.xyz, m1.cells, m1.dir_flag, m1.dn_ptr, m1.dn_idx)
+    assert np.abs(n0 - n1).max() < 1e-14 and np.abs(d0 - d1).max() < 1e-14
+
+
+def test_sphere_alpha_and_harmonic_residual(orc):
+    """KAT (3)+(4): sphere alpha -> 1/2; phi = 1/|x - x0| (x0 outside) satisfies
+    alpha phi + N phi - D dphi/dn = 0 up to O(h^2)."""
+    errs = []
+    for n in (4, 8):
+        m = meshgen.sphere(n)
+        nm, dm = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+        alpha = orc.compute_alpha(nm)
+        x0 = np.array([2.5, 0.3, -0.4])
+        d = m.xyz - x0
+        r = np.linalg.norm(d, axis=1)
+        phi = 1 / r
+        normal = m.xyz / np.linalg.norm(m.xyz, axis=1, keepdims=True)
+        dphi = -(d * normal).sum(axis=1) / r ** 3
+        res = alpha * phi + nm @ phi - dm @ dphi
+        errs.append(np.abs(res).max())
+        assert np.abs(alpha - 0.5).max() < 0.65 / n  # faceted sphere: O(h) solid-angle defect
+    assert errs[1] < errs[0] / 2.5 and errs[1] < 5e-3
+
+
+def test_cube_linear_field_exact_geometry(orc):
+    """phi = x on the cube (flat faces: geometry exact, phi in the Q1 space)."""
+    m = meshgen.cube(6)
+    nm, dm = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    alpha = orc.compute_alpha(nm)
+    nn = meshgen.cell_normals_at_nodes(m)
+    res = alpha * m.xyz[:, 0] + nm @ m.xyz[:, 0] - dm @ nn[:, 0]
+    assert np.abs(res).max() < 2e-3
+
+
+def test_long_double_variant_agrees(orc):
+    m = meshgen.wigley_tank(nxm=8, nt=4, nxu=3, nxd=4, nz=3, nzh=3)
+    n0, d0 = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    n1, d1 = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, long_double=True)
+    from conftest import rel_err_rowscaled
+    # single layer: positive integrand, pure rounding
+    assert rel_err_rowscaled(d0, d1) < 1e-13
+    # double layer: (R.n)/r^3 between coplanar neighbours is a cancellation to ~1e-16 * |R|/r^3,
+    # an ABSOLUTE noise floor (~1e-16) that rows with small entries (flat free surface, ~1e-4)
+    # see as ~1e-12 relative.  It is a property of the reference arithmetic itself.
+    assert rel_err_rowscaled(n0, n1) < 2e-11
+    assert np.abs(n0 - n1).max() < 2e-13  # worst: singular pairs on flat patches (exact value 0)
+
+
+def test_row_slab_equals_full(orc):
+    m = meshgen.cube(4)
+    n0, d0 = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, nthreads=1)
+    n1, d1 = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, 37, 91, nthreads=3)
+    assert np.array_equal(n0[37:91], n1) and np.array_equal(d0[37:91], d1)
+
+
+def _tank_problem(orc, **kw):
+    m = meshgen.wigley_tank(nxm=10, nt=5, nxu=4, nxd=5, nz=3, nzh=3, **kw)
+    bc = meshgen.towing_tank_bc(m)
+    nn = meshgen.cell_normals_at_nodes(m)
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, m.surface_nodes, bc, nodes_normals=nn)
+    con = orc.Constraints(m.n_nodes, cl.lines, cl.ptr, cl.col, cl.val, cl.inhom)
+    nm, dm = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    return m, bc, con, nm, dm
+
+
+def test_operator_algebra_matches_numpy(orc):
+    """vmult / compute_rhs / constrained rows against direct numpy formulas (Appendix A.5)."""
+    m, bc, con, nm, dm = _tank_problem(orc)
+    s, o = m.surface_nodes, m.other_nodes
+    alpha = orc.compute_alpha(nm)
+    assert np.allclose(alpha, -nm.sum(axis=1), rtol=0, atol=1e-13)
+    x = np.sin(0.37 * np.arange(m.n_nodes))
+    y = orc.vmult(nm, dm, alpha, s, o, x)
+    assert np.allclose(y, -dm @ (s * x) + nm @ (o * x) + alpha * o * x, rtol=0, atol=1e-12)
+    b = orc.compute_rhs(nm, dm, alpha, s, o, x)
+    assert np.allclose(b, -(nm @ (s * x) + alpha * s * x) + dm @ (o * x), rtol=0, atol=1e-12)
+    yc = orc.constrained_vmult(nm, dm, alpha, s, o, con, x)
+    free = con.line_of < 0
+    assert np.array_equal(yc[free], y[free])
+    for k, i in enumerate(con.lines):
+        e = slice(con.ptr[k], con.ptr[k + 1])
+        assert abs(yc[i] - (x[i] - (con.val[e] * x[con.col[e]]).sum())) < 1e-14
+    r = orc.distribute_rhs(con, b)
+    assert np.array_equal(r[con.lines], con.inhom) and np.array_equal(r[free], b[free])
+
+
+def test_pure_neumann_shift(orc):
+    m, bc, con, nm, dm = _tank_problem(orc)
+    z = np.zeros(m.n_nodes)
+    one = np.ones(m.n_nodes)
+    alpha = orc.compute_alpha(nm)
+    x = np.cos(0.2 * np.arange(m.n_nodes))
+    y = orc.vmult(nm, dm, alpha, z, one, x)
+    y0 = nm @ x + alpha * x
+    assert np.allclose(y, y0 - np.linalg.norm(y0), rtol=0, atol=1e-11)
+
+
+def test_band_preconditioner_matches_numpy(orc):
+    m, bc, con, nm, dm = _tank_problem(orc)
+    s = m.surface_nodes
+    alpha = orc.compute_alpha(nm)
+    n = m.n_nodes
+    B = orc.band_system_dense(nm, dm, alpha, s, con, band=100)
+    # literal restatement of bem_problem.cc:1126-1145
+    ref = np.zeros((n, n))
+    for i in range(n):
+        if con.line_of[i] >= 0:
+            ref[i, i] = 1
+        for j in range(max(i - 50, 0), min(i + 50, n)):
+            if con.line_of[j] < 0:
+                if s[i] == 0:
+                    ref[j, i] = nm[j, i] + (alpha[i] if i == j else 0.0)
+                else:
+                    ref[j, i] = -dm[j, i]
+    assert np.array_equal(B, ref)
+    v = np.sin(np.arange(n) * 0.11)
+    z = orc.precond_apply(nm, dm, alpha, s, con, v, band=100)
+    assert np.allclose(ref @ z, v, rtol=0, atol=1e-11)
+
+
+def test_gmres_solution_matches_direct_solve(orc):
+    """KAT (6): solve_system vs a dense LU of the same constrained operator."""
+    m, bc, con, nm, dm = _tank_problem(orc)
+    s, o = m.surface_nodes, m.other_nodes
+    n = m.n_nodes
+    r = orc.solve_system(nm, dm, s, o, bc, con, np.zeros(n), np.zeros(n), tol=1e-12, max_steps=300)
+    assert r["converged"]
+    alpha = r["alpha"]
+    A = nm * o[None, :] + np.diag(alpha * o) - dm * s[None, :]
+    for k, i in enumerate(con.lines):
+        A[i, :] = 0
+        A[i, i] = 1
+        e = slice(con.ptr[k], con.ptr[k + 1])
+        A[i, con.col[e]] -= con.val[e]
+    x = np.linalg.solve(A, r["rhs"])
+    assert np.linalg.norm(r["sol"] - x) / np.linalg.norm(x) < 1e-9
+    assert np.array_equal(r["phi"][s == 0], r["sol"][s == 0])
+    assert np.array_equal(r["dphi_dn"][s == 1], r["sol"][s == 1])
+    # unpreconditioned GMRES reaches the same solution
+    r2 = orc.solve_system(nm, dm, s, o, bc, con, np.zeros(n), np.zeros(n), tol=1e-11, max_steps=2000,
+                          use_precond=False)
+    assert r2["converged"] and np.linalg.norm(r2["sol"] - x) / np.linalg.norm(x) < 1e-8
+    # residual() of the converged pair vanishes
+    phi = np.where(s == 1, bc, r["phi"])
+    dphi = np.where(s == 1, r["dphi_dn"], bc)
+    res = orc.residual(nm, dm, s, o, con, phi, dphi)
+    assert np.abs(res).max() < 1e-10
+
+
+def test_gmres_no_convergence_reported(orc):
+    m, bc, con, nm, dm = _tank_problem(orc)
+    n = m.n_nodes
+    r = orc.solve_system(nm, dm, m.surface_nodes, m.other_nodes, bc, con, np.zeros(n), np.zeros(n),
+                         tol=1e-30, max_steps=7)
+    assert not r["converged"] and r["iters"] == 7
+
+
+def test_mixed_problem_recovers_trace(orc):
+    """KAT (4): cube, top face Dirichlet, rest Neumann, exact field phi = 1/|x-x0|: the
+    solve recovers the missing trace to discretisation accuracy."""
+    errs = []
+    for n in (4, 8):
+        m = meshgen.cube(n)
+        x0 = np.array([1.9, 1.4, 2.2])
+        d = m.xyz - x0
+        r = np.linalg.norm(d, axis=1)
+        phi_ex = 1 / r
+        nn = meshgen.cell_normals_at_nodes(m)
+        dphi_ex = -(d * nn).sum(axis=1) / r ** 3
+        top = m.node_patch == m.patch_names.index("z1")
+        s = top.astype(float)
+        o = 1 - s
+        bc = np.where(top, phi_ex, dphi_ex)
+        cl = compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=nn)
+        con = orc.Constraints(m.n_nodes, cl.lines, cl.ptr, cl.col, cl.val, cl.inhom)
+        nm, dm = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+        out = orc.solve_system(nm, dm, s, o, bc, con, np.zeros(m.n_nodes), np.zeros(m.n_nodes), tol=1e-12,
+                               max_steps=400)
+        assert out["converged"]
+        errs.append(np.abs(out["phi"][~top] - phi_ex[~top]).max() / np.abs(phi_ex).max())
+    assert errs[1] < errs[0] and errs[1] < 2e-2

@@ -1,0 +1,677 @@
+// assemble.cu -- sm_100a kernels for BEMProblem<3>::assemble_system
+// (reference source/bem_problem.cc:106-590) and compute_alpha (:594-618).
+//
+//   k_cell_geometry      FEValues of the regular rule for every cell (:133-137, 192-196),
+//                        folded into per-(cell,q) constants:  y_q, n_q JxW_q /(-4 pi), JxW_q/(4 pi)
+//   k_assemble_tiled     regular (node, cell) pairs (:241-260, 531-537): one CTA per
+//                        (256-row tile, cell cluster); panel data staged in shared memory by a
+//                        TMA bulk copy; per-column accumulators in shared memory; deterministic
+//                        STORE/ADD flush (see plan.cpp)
+//   k_assemble_simple    same integrals, literal reference arithmetic, global atomics: the
+//                        independent cross-check and the fallback for quadrature orders != 4
+//   k_assemble_singular  pairs whose cell holds a dof of double_nodes_set[i] (:223-230,
+//                        261-525): QGaussOneOverR rule, one warp per row, shuffle reduction
+//   k_alpha_rowsum       alpha = -row sums of the Neumann matrix (:594-618)
+#include <cstdio>
+
+#include "internal.h"
+
+#define FOUR_PI 12.566370614359172953850573533118
+
+struct DevTables
+{
+  int nq, ns, n1, pad;
+  double g_u[WBEM_MAX_NQ], g_v[WBEM_MAX_NQ], g_w[WBEM_MAX_NQ];
+  double g_shape[4][WBEM_MAX_NQ];
+  double g1_x[8];
+  double s_u[4][WBEM_MAX_NS], s_v[4][WBEM_MAX_NS], s_w[4][WBEM_MAX_NS];
+};
+__constant__ DevTables c_qt;
+
+int wbem_upload_tables(wbem_ctx *ctx)
+{
+  static DevTables t; // large: keep off the stack
+  const QuadTables &q = ctx->qt;
+  t.nq = q.nq;
+  t.ns = q.ns;
+  t.n1 = q.n1;
+  t.pad = 0;
+  memcpy(t.g_u, q.g_u, sizeof(t.g_u));
+  memcpy(t.g_v, q.g_v, sizeof(t.g_v));
+  memcpy(t.g_w, q.g_w, sizeof(t.g_w));
+  memcpy(t.g_shape, q.g_shape, sizeof(t.g_shape));
+  memcpy(t.g1_x, q.g1_x, sizeof(t.g1_x));
+  memcpy(t.s_u, q.s_u, sizeof(t.s_u));
+  memcpy(t.s_v, q.s_v, sizeof(t.s_v));
+  memcpy(t.s_w, q.s_w, sizeof(t.s_w));
+  CUDA_OK(ctx, cudaMemcpyToSymbol(c_qt, &t, sizeof(t)));
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Q1 codimension-one mapping at reference point (u,v): position, d_u x d_v, shape values.
+// ---------------------------------------------------------------------------------------
+struct QuadVerts
+{
+  double x[4][3];
+};
+
+__device__ __forceinline__ void load_verts(const double *__restrict__ xyz,
+                                           const uint32_t *__restrict__ dofs, QuadVerts &X)
+{
+#pragma unroll
+  for (int k = 0; k < 4; ++k)
+    {
+      const double *p = xyz + 3 * (size_t)dofs[k];
+      X.x[k][0] = p[0];
+      X.x[k][1] = p[1];
+      X.x[k][2] = p[2];
+    }
+}
+
+__device__ __forceinline__ void map_q1(const QuadVerts &X, double u, double v, double y[3],
+                                       double cr[3], double phi[4])
+{
+  phi[0] = (1 - u) * (1 - v);
+  phi[1] = u * (1 - v);
+  phi[2] = (1 - u) * v;
+  phi[3] = u * v;
+  double tu[3], tv[3];
+#pragma unroll
+  for (int d = 0; d < 3; ++d)
+    {
+      y[d] = phi[0] * X.x[0][d] + phi[1] * X.x[1][d] + phi[2] * X.x[2][d] + phi[3] * X.x[3][d];
+      tu[d] = (1 - v) * (X.x[1][d] - X.x[0][d]) + v * (X.x[3][d] - X.x[2][d]);
+      tv[d] = (1 - u) * (X.x[2][d] - X.x[0][d]) + u * (X.x[3][d] - X.x[1][d]);
+    }
+  cr[0] = tu[1] * tv[2] - tu[2] * tv[1];
+  cr[1] = tu[2] * tv[0] - tu[0] * tv[2];
+  cr[2] = tu[0] * tv[1] - tu[1] * tv[0];
+}
+
+// One thread per (cell position, q).  Output layout per cell: [7][nq] =
+// y_x, y_y, y_z, nJ_x, nJ_y, nJ_z, wJ   with  nJ = n JxW / (-4 pi),  wJ = JxW / (4 pi).
+// n JxW = +-(d_u x d_v) w_q exactly (no normalisation needed).
+__global__ void k_cell_geometry(uint32_t C, int nq, const double *__restrict__ xyz,
+                                const uint32_t *__restrict__ cell_dofs,
+                                const uint8_t *__restrict__ dir, double *__restrict__ geo)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t c = t / nq;
+  const int q = t - c * nq;
+  if (c >= C) return;
+  QuadVerts X;
+  load_verts(xyz, cell_dofs + 4 * (size_t)c, X);
+  double y[3], cr[3], phi[4];
+  map_q1(X, c_qt.g_u[q], c_qt.g_v[q], y, cr, phi);
+  const double w = c_qt.g_w[q];
+  const double sgn = dir[c] ? 1.0 : -1.0;
+  const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+  double *g = geo + (size_t)c * 7 * nq;
+  g[0 * nq + q] = y[0];
+  g[1 * nq + q] = y[1];
+  g[2 * nq + q] = y[2];
+  const double f = sgn * w * (-1.0 / FOUR_PI);
+  g[3 * nq + q] = cr[0] * f;
+  g[4 * nq + q] = cr[1] * f;
+  g[5 * nq + q] = cr[2] * f;
+  g[6 * nq + q] = cn * w * (1.0 / FOUR_PI);
+}
+
+int wbem_launch_geometry(wbem_ctx *ctx)
+{
+  const int nq = ctx->qt.nq;
+  const uint32_t total = ctx->C * nq;
+  if (total == 0) return 0;
+  k_cell_geometry<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->C, nq, ctx->d_xyz,
+                                                               ctx->d_cell_dofs, ctx->d_dir,
+                                                               ctx->d_cellgeo);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// fast 1/sqrt(a): MUFU.RSQ64H seed (rel. error ~2^-22) + one third-order (Householder) step
+//   e = 1 - a y^2 ;  y <- y + y e (1/2 + 3/8 e)        -> rel. error O(e^3) < 2^-60
+// 5 FP64-pipe instructions instead of the ~10 + branch of the library rsqrt().
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double rsqrt_h3(double a)
+{
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+  const double t = a * y;
+  const double e = fma(-t, y, 1.0);
+  const double p = fma(0.375, e, 0.5);
+  const double ye = y * e;
+  return fma(p, ye, y);
+}
+
+__global__ void k_rsqrt_selftest(const double *__restrict__ in, double *__restrict__ out, int n)
+{
+  int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) out[i] = rsqrt_h3(in[i]);
+}
+
+// ---------------------------------------------------------------------------------------
+// mbarrier / TMA bulk-copy helpers (sm_90+ PTX; SASS: SYNCS / UBLKCP)
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+  return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+  asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)),
+               "r"(bytes)
+               : "memory");
+}
+__device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32_t bytes,
+                                              uint64_t *bar)
+{
+  asm volatile(
+    "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+      smem_u32(dst)),
+    "l"(src), "r"(bytes), "r"(smem_u32(bar))
+    : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+  uint32_t done;
+  do
+    {
+      asm volatile("{\n\t.reg .pred p;\n\t"
+                   "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+                   "selp.u32 %0, 1, 0, p;\n\t}"
+                   : "=r"(done)
+                   : "r"(smem_u32(bar)), "r"(parity)
+                   : "memory");
+    }
+  while (!done);
+}
+
+// ---------------------------------------------------------------------------------------
+// Tiled regular-pair kernel, Gauss 4x4.
+// ---------------------------------------------------------------------------------------
+#define TILE_ROWS 256
+#define TILE_W 48
+#define TILE_MAX_CELLS 36
+#define ACC_STRIDE (TILE_ROWS + 1)
+
+struct TiledArgs
+{
+  const double *xyz;        // [N][3]
+  const double *geo;        // [C][7][16] processing order
+  const uint8_t *cell_slots; // [C][4]
+  const uint32_t *cl_cell_ptr, *cl_slot_ptr, *slot_col, *color_clusters;
+  const uint32_t *sing_ptr, *sing_cellpos; // CSR by local row
+  double *Nm, *Dm;
+  uint32_t ld, row0, nloc, cluster_base;
+};
+
+constexpr size_t tiled_smem_bytes()
+{
+  return sizeof(double) * (2 * TILE_W * ACC_STRIDE + TILE_MAX_CELLS * 7 * 16) + 16 /*mbar*/ +
+         TILE_MAX_CELLS * 4 + TILE_W * 4;
+}
+
+__global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double *acc = reinterpret_cast<double *>(smem_raw);            // [2][W][ACC_STRIDE]
+  double *geo = acc + 2 * TILE_W * ACC_STRIDE;                   // [cells][7][16]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + TILE_MAX_CELLS * 7 * 16);
+  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 2);     // [cells] packed 4 x u8
+  uint32_t *s_col = s_slots + TILE_MAX_CELLS;                    // [W]
+
+  const int tid = threadIdx.x;
+  const uint32_t cluster = a.color_clusters[a.cluster_base + blockIdx.x];
+  const uint32_t p0 = a.cl_cell_ptr[cluster], p1 = a.cl_cell_ptr[cluster + 1];
+  const uint32_t s0 = a.cl_slot_ptr[cluster], s1 = a.cl_slot_ptr[cluster + 1];
+  const int ncell = (int)(p1 - p0), nslot = (int)(s1 - s0);
+  const uint32_t lrow_base = blockIdx.y * TILE_ROWS;
+  const uint32_t lrow = lrow_base + tid;
+  const bool row_ok = lrow < a.nloc;
+  const uint32_t lrow_c = row_ok ? lrow : a.nloc - 1;
+
+  if (tid == 0)
+    {
+      mbar_init(bar, 1);
+    }
+  __syncthreads();
+  if (tid == 0)
+    {
+      const uint32_t bytes = (uint32_t)ncell * 7 * 16 * sizeof(double);
+      mbar_expect_tx(bar, bytes);
+      bulk_copy_g2s(geo, a.geo + (size_t)p0 * 7 * 16, bytes, bar);
+    }
+  // singular cells of this row inside the cluster -> bit mask (they are integrated by
+  // k_assemble_singular only, reference :241/:261)
+  unsigned long long smask = 0ull;
+  {
+    const uint32_t b = a.sing_ptr[lrow_c], e = a.sing_ptr[lrow_c + 1];
+    for (uint32_t k = b; k < e; ++k)
+      {
+        const uint32_t pos = a.sing_cellpos[k];
+        if (pos >= p0 && pos < p1) smask |= 1ull << (pos - p0);
+      }
+  }
+  const double xi0 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 0];
+  const double xi1 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 1];
+  const double xi2 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 2];
+  for (int i = tid; i < ncell; i += TILE_ROWS)
+    s_slots[i] = reinterpret_cast<const uint32_t *>(a.cell_slots)[p0 + i];
+  for (int i = tid; i < nslot; i += TILE_ROWS) s_col[i] = a.slot_col[s0 + i];
+  // zero the accumulators of the slots in use
+  for (int s = 0; s < nslot; ++s)
+    {
+      acc[s * ACC_STRIDE + tid] = 0.0;
+      acc[(TILE_W + s) * ACC_STRIDE + tid] = 0.0;
+    }
+  __syncthreads();
+  mbar_wait(bar, 0);
+
+  double *accN = acc + tid;
+  double *accD = acc + TILE_W * ACC_STRIDE + tid;
+  for (int k = 0; k < ncell; ++k)
+    {
+      if ((smask >> k) & 1ull) continue;
+      const double *g = geo + k * 112;
+      double SN = 0, SuN = 0, SvN = 0, SuvN = 0;
+      double SD = 0, SuD = 0, SvD = 0, SuvD = 0;
+#pragma unroll
+      for (int qy = 0; qy < 4; ++qy)
+        {
+          double t0n = 0, t1n = 0, t0d = 0, t1d = 0;
+#pragma unroll
+          for (int qx = 0; qx < 4; ++qx)
+            {
+              const int q = qy * 4 + qx;
+              const double Rx = g[q] - xi0;
+              const double Ry = g[16 + q] - xi1;
+              const double Rz = g[32 + q] - xi2;
+              const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
+              const double ri = rsqrt_h3(r2);
+              const double ri2 = ri * ri;
+              const double ri3 = ri2 * ri;
+              const double Rn = fma(Rz, g[80 + q], fma(Ry, g[64 + q], Rx * g[48 + q]));
+              const double av = Rn * ri3;      // (D . n) JxW
+              const double bv = g[96 + q] * ri; // d JxW
+              const double uq = c_qt.g1_x[qx];
+              if (qx == 0)
+                {
+                  t0n = av;
+                  t1n = av * uq;
+                  t0d = bv;
+                  t1d = bv * uq;
+                }
+              else
+                {
+                  t0n += av;
+                  t1n = fma(av, uq, t1n);
+                  t0d += bv;
+                  t1d = fma(bv, uq, t1d);
+                }
+            }
+          const double vq = c_qt.g1_x[qy];
+          SN += t0n;
+          SuN += t1n;
+          SvN = fma(vq, t0n, SvN);
+          SuvN = fma(vq, t1n, SuvN);
+          SD += t0d;
+          SuD += t1d;
+          SvD = fma(vq, t0d, SvD);
+          SuvD = fma(vq, t1d, SuvD);
+        }
+      // moments -> the four Q1 shape-function sums
+      const double n3 = SuvN, n1 = SuN - SuvN, n2 = SvN - SuvN, n0 = (SN - SuN) - n2;
+      const double d3 = SuvD, d1 = SuD - SuvD, d2 = SvD - SuvD, d0 = (SD - SuD) - d2;
+      const uint32_t sl = s_slots[k];
+      const int sa = (sl & 0xff) * ACC_STRIDE, sb = ((sl >> 8) & 0xff) * ACC_STRIDE,
+                sc = ((sl >> 16) & 0xff) * ACC_STRIDE, sd = (sl >> 24) * ACC_STRIDE;
+      accN[sa] += n0;
+      accD[sa] += d0;
+      accN[sb] += n1;
+      accD[sb] += d1;
+      accN[sc] += n2;
+      accD[sc] += d2;
+      accN[sd] += n3;
+      accD[sd] += d3;
+    }
+  __syncthreads();
+
+  // flush: warp w handles rows w, w+8, ...; lanes run over the cluster's column slots
+  const int warp = tid >> 5, lane = tid & 31;
+  for (int r = warp; r < TILE_ROWS; r += TILE_ROWS / 32)
+    {
+      const uint32_t row = lrow_base + r;
+      if (row >= a.nloc) break;
+      double *gN = a.Nm + (size_t)row * a.ld;
+      double *gD = a.Dm + (size_t)row * a.ld;
+      for (int s = lane; s < nslot; s += 32)
+        {
+          const uint32_t cc = s_col[s];
+          const uint32_t col = cc & 0x7fffffffu;
+          double vn = acc[s * ACC_STRIDE + r];
+          double vd = acc[(TILE_W + s) * ACC_STRIDE + r];
+          if (cc >> 31)
+            {
+              vn += gN[col];
+              vd += gD[col];
+            }
+          gN[col] = vn;
+          gD[col] = vd;
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Simple kernel: one thread per local row, literal reference arithmetic, atomics.
+// grid = (row blocks, cell chunks); matrices must be zeroed first.
+// ---------------------------------------------------------------------------------------
+#define SIMPLE_ROWS 128
+#define SIMPLE_TC 4
+
+__global__ void __launch_bounds__(SIMPLE_ROWS)
+  k_assemble_simple(int nq, uint32_t C, uint32_t cells_per_chunk, const double *__restrict__ xyz,
+                    const double *__restrict__ geo, const uint32_t *__restrict__ cell_dofs,
+                    const uint32_t *__restrict__ colpos, const uint32_t *__restrict__ sing_ptr,
+                    const uint32_t *__restrict__ sing_cellpos, double *Nm, double *Dm, uint32_t ld,
+                    uint32_t row0, uint32_t nloc)
+{
+  extern __shared__ __align__(16) double sgeo[]; // [TC][7][nq]
+  __shared__ uint32_t scol[SIMPLE_TC][4];
+  const int tid = threadIdx.x;
+  const uint32_t lrow = blockIdx.x * SIMPLE_ROWS + tid;
+  const bool row_ok = lrow < nloc;
+  const uint32_t lrow_c = row_ok ? lrow : nloc - 1;
+  const uint32_t c_begin = blockIdx.y * cells_per_chunk;
+  const uint32_t c_end = min(C, c_begin + cells_per_chunk);
+  const double xi[3] = {xyz[3 * (size_t)(row0 + lrow_c)], xyz[3 * (size_t)(row0 + lrow_c) + 1],
+                        xyz[3 * (size_t)(row0 + lrow_c) + 2]};
+  uint32_t sp = sing_ptr[lrow_c];
+  const uint32_t se = sing_ptr[lrow_c + 1];
+  while (sp < se && sing_cellpos[sp] < c_begin) ++sp;
+  uint32_t next_sing = sp < se ? sing_cellpos[sp] : 0xffffffffu;
+
+  for (uint32_t cb = c_begin; cb < c_end; cb += SIMPLE_TC)
+    {
+      const int nc = min((uint32_t)SIMPLE_TC, c_end - cb);
+      __syncthreads();
+      for (int i = tid; i < nc * 7 * nq; i += SIMPLE_ROWS) sgeo[i] = geo[(size_t)cb * 7 * nq + i];
+      if (tid < nc * 4) scol[tid / 4][tid % 4] = colpos[cell_dofs[4 * (size_t)cb + tid]];
+      __syncthreads();
+      for (int k = 0; k < nc; ++k)
+        {
+          const uint32_t cpos = cb + k;
+          if (cpos == next_sing)
+            {
+              ++sp;
+              next_sing = sp < se ? sing_cellpos[sp] : 0xffffffffu;
+              continue;
+            }
+          const double *g = sgeo + k * 7 * nq;
+          double ln[4] = {0, 0, 0, 0}, ldd[4] = {0, 0, 0, 0};
+          for (int q = 0; q < nq; ++q)
+            {
+              const double Rx = g[q] - xi[0], Ry = g[nq + q] - xi[1], Rz = g[2 * nq + q] - xi[2];
+              const double r = sqrt(Rx * Rx + Ry * Ry + Rz * Rz);
+              const double r2 = r * r;
+              // folded constants: nJ carries n JxW/(-4 pi), wJ carries JxW/(4 pi)
+              const double Dn = (Rx * g[3 * nq + q] + Ry * g[4 * nq + q] + Rz * g[5 * nq + q]) / (r2 * r);
+              const double s = g[6 * nq + q] / r;
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                {
+                  ln[j] += Dn * c_qt.g_shape[j][q];
+                  ldd[j] += s * c_qt.g_shape[j][q];
+                }
+            }
+          if (row_ok)
+            {
+#pragma unroll
+              for (int j = 0; j < 4; ++j)
+                {
+                  atomicAdd(Nm + (size_t)lrow * ld + scol[k][j], ln[j]);
+                  atomicAdd(Dm + (size_t)lrow * ld + scol[k][j], ldd[j]);
+                }
+            }
+        }
+    }
+}
+
+// ---------------------------------------------------------------------------------------
+// Singular pairs: one warp per local row; lanes run over the 2 n^2 polar points; literal
+// reference arithmetic (LaplaceKernel::kernels, include/laplace_kernel.h:55-58).  The warp
+// shuffle-reduces the 8 integrals of a pair and lanes 0..7 add them into row i (the regular
+// kernels have finished on this stream; no other warp touches row i).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256)
+  k_assemble_singular(const double *__restrict__ xyz, const uint32_t *__restrict__ cell_dofs,
+                      const uint8_t *__restrict__ dir, const uint32_t *__restrict__ colpos,
+                      const uint32_t *__restrict__ sing_ptr,
+                      const uint32_t *__restrict__ sing_cellpos,
+                      const uint8_t *__restrict__ sing_idx, double *Nm, double *Dm, uint32_t ld,
+                      uint32_t row0, uint32_t nloc)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (lrow >= nloc) return;
+  const double *px = xyz + 3 * (size_t)(row0 + lrow);
+  const double xi[3] = {px[0], px[1], px[2]};
+  const int ns = c_qt.ns;
+  for (uint32_t k = sing_ptr[lrow]; k < sing_ptr[lrow + 1]; ++k)
+    {
+      const uint32_t cpos = sing_cellpos[k];
+      const int sj = sing_idx[k];
+      const uint32_t *dofs = cell_dofs + 4 * (size_t)cpos;
+      QuadVerts X;
+      load_verts(xyz, dofs, X);
+      const double sgn = dir[cpos] ? 1.0 : -1.0;
+      double v8[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+      for (int q = lane; q < ns; q += 32)
+        {
+          double y[3], cr[3], phi[4];
+          map_q1(X, c_qt.s_u[sj][q], c_qt.s_v[sj][q], y, cr, phi);
+          const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+          const double jxw = cn * c_qt.s_w[sj][q];
+          const double nx = sgn * cr[0] / cn, ny = sgn * cr[1] / cn, nz = sgn * cr[2] / cn;
+          const double Rx = y[0] - xi[0], Ry = y[1] - xi[1], Rz = y[2] - xi[2];
+          const double r = sqrt(Rx * Rx + Ry * Ry + Rz * Rz);
+          const double r2 = r * r;
+          const double s = 1.0 / (r * FOUR_PI);
+          const double den = -FOUR_PI * r2 * r;
+          const double Dn = (Rx / den) * nx + (Ry / den) * ny + (Rz / den) * nz;
+#pragma unroll
+          for (int j = 0; j < 4; ++j)
+            {
+              v8[j] += Dn * phi[j] * jxw;
+              v8[4 + j] += s * phi[j] * jxw;
+            }
+        }
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        {
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v8[j] += __shfl_xor_sync(0xffffffffu, v8[j], off);
+        }
+      // lanes 0..3 -> Neumann, 4..7 -> Dirichlet; sequential over j for repeated dofs
+      double mine = 0;
+#pragma unroll
+      for (int j = 0; j < 8; ++j)
+        if (lane == j) mine = v8[j];
+      if (lane < 8)
+        {
+          double *M = (lane < 4 ? Nm : Dm) + (size_t)lrow * ld;
+          const uint32_t col = colpos[dofs[lane & 3]];
+          // two local dofs of a degenerate cell may share a column: serialise
+          for (int j = 0; j < 4; ++j)
+            {
+              if ((lane & 3) == j) M[col] += mine;
+              __syncwarp(0xffu);
+            }
+        }
+      __syncwarp();
+    }
+}
+
+// alpha_loc[r] = - sum_j N[r][j]   (one warp per local row, 128-bit loads)
+__global__ void __launch_bounds__(256)
+  k_alpha_rowsum(const double *__restrict__ Nm, uint32_t ld, uint32_t nloc, double *__restrict__ out)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  if (lrow >= nloc) return;
+  const double2 *row = reinterpret_cast<const double2 *>(Nm + (size_t)lrow * ld);
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  const uint32_t n2 = ld / 2;
+  uint32_t j = lane;
+  for (; j + 96 < n2; j += 128)
+    {
+      const double2 a = row[j], b = row[j + 32], c = row[j + 64], d = row[j + 96];
+      s0 += a.x + a.y;
+      s1 += b.x + b.y;
+      s2 += c.x + c.y;
+      s3 += d.x + d.y;
+    }
+  for (; j < n2; j += 32)
+    {
+      const double2 a = row[j];
+      s0 += a.x + a.y;
+    }
+  double s = (s0 + s1) + (s2 + s3);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if (lane == 0) out[lrow] = -s;
+}
+
+// ---------------------------------------------------------------------------------------
+// host launchers
+// ---------------------------------------------------------------------------------------
+static bool g_tiled_attr_set = false;
+
+int wbem_launch_assemble(wbem_ctx *ctx)
+{
+  cudaStream_t st = ctx->stream;
+  const int nq = ctx->qt.nq;
+  if (ctx->nloc == 0 || ctx->C == 0) return 0;
+  const bool tiled = (ctx->p.assemble_variant == 0) && (ctx->qt.n1 == 4);
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
+  if (tiled)
+    {
+      const AssemblyPlan &pl = ctx->plan;
+      if (!g_tiled_attr_set)
+        {
+          CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_tiled,
+                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)tiled_smem_bytes()));
+          g_tiled_attr_set = true;
+        }
+      // columns no cell touches (none on deal.II meshes) stay zero
+      if (pl.n_cols_written < ctx->ld)
+        {
+          const size_t w = (ctx->ld - pl.n_cols_written) * sizeof(double);
+          CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_Nm + pl.n_cols_written, ctx->ld * sizeof(double), 0,
+                                         w, ctx->nloc, st));
+          CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_Dm + pl.n_cols_written, ctx->ld * sizeof(double), 0,
+                                         w, ctx->nloc, st));
+        }
+      TiledArgs a;
+      a.xyz = ctx->d_xyz;
+      a.geo = ctx->d_cellgeo;
+      a.cell_slots = ctx->d_cell_slots;
+      a.cl_cell_ptr = ctx->d_cl_cell_ptr;
+      a.cl_slot_ptr = ctx->d_cl_slot_ptr;
+      a.slot_col = ctx->d_slot_col;
+      a.color_clusters = ctx->d_color_clusters;
+      a.sing_ptr = ctx->d_sing_ptr;
+      a.sing_cellpos = ctx->d_sing_cellpos;
+      a.Nm = ctx->d_Nm;
+      a.Dm = ctx->d_Dm;
+      a.ld = ctx->ld;
+      a.row0 = ctx->row0;
+      a.nloc = ctx->nloc;
+      const uint32_t row_tiles = (ctx->nloc + TILE_ROWS - 1) / TILE_ROWS;
+      for (uint32_t c = 0; c < pl.n_colors; ++c)
+        {
+          const uint32_t nclu = pl.color_ptr[c + 1] - pl.color_ptr[c];
+          if (nclu == 0) continue;
+          a.cluster_base = pl.color_ptr[c];
+          dim3 grid(nclu, row_tiles);
+          k_assemble_tiled<<<grid, TILE_ROWS, tiled_smem_bytes(), st>>>(a);
+          ctx->launches++;
+        }
+      CUDA_OK(ctx, cudaGetLastError());
+    }
+  else
+    {
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_Nm, 0, sizeof(double) * (size_t)ctx->nloc * ctx->ld, st));
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_Dm, 0, sizeof(double) * (size_t)ctx->nloc * ctx->ld, st));
+      const uint32_t row_blocks = (ctx->nloc + SIMPLE_ROWS - 1) / SIMPLE_ROWS;
+      uint32_t chunks = (4 * 148 + row_blocks - 1) / row_blocks; // ~4 CTAs per SM in flight
+      if (chunks < 1) chunks = 1;
+      uint32_t per = (ctx->C + chunks - 1) / chunks;
+      per = ((per + SIMPLE_TC - 1) / SIMPLE_TC) * SIMPLE_TC;
+      chunks = (ctx->C + per - 1) / per;
+      dim3 grid(row_blocks, chunks);
+      const size_t sm = sizeof(double) * SIMPLE_TC * 7 * nq;
+      k_assemble_simple<<<grid, SIMPLE_ROWS, sm, st>>>(nq, ctx->C, per, ctx->d_xyz, ctx->d_cellgeo,
+                                                       ctx->d_cell_dofs, ctx->d_colpos,
+                                                       ctx->d_sing_ptr, ctx->d_sing_cellpos,
+                                                       ctx->d_Nm, ctx->d_Dm, ctx->ld, ctx->row0,
+                                                       ctx->nloc);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+    }
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[1], st));
+  if (ctx->n_sing)
+    {
+      const uint32_t warps_per_block = 8;
+      k_assemble_singular<<<(ctx->nloc + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
+        ctx->d_xyz, ctx->d_cell_dofs, ctx->d_dir, ctx->d_colpos, ctx->d_sing_ptr,
+        ctx->d_sing_cellpos, ctx->d_sing_idx, ctx->d_Nm, ctx->d_Dm, ctx->ld, ctx->row0, ctx->nloc);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+    }
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], st));
+  return 0;
+}
+
+int wbem_launch_alpha(wbem_ctx *ctx)
+{
+  cudaStream_t st = ctx->stream;
+  if (ctx->nloc)
+    {
+      k_alpha_rowsum<<<(ctx->nloc + 7) / 8, 256, 0, st>>>(ctx->d_Nm, ctx->ld, ctx->nloc,
+                                                         ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+    }
+  int rc = wbem_allgather_rows(ctx, ctx->d_yloc);
+  if (rc) return rc;
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_alpha, ctx->d_yloc, sizeof(double) * ctx->N,
+                               cudaMemcpyDeviceToDevice, st));
+  ctx->have_alpha = true;
+  return 0;
+}
+
+// exported self test of the fast reciprocal square root (tests/test_gpu_kernels.py)
+extern "C" int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out, int n)
+{
+  double *d_in = nullptr, *d_out = nullptr;
+  CUDA_OK(ctx, cudaMalloc(&d_in, sizeof(double) * n));
+  CUDA_OK(ctx, cudaMalloc(&d_out, sizeof(double) * n));
+  CUDA_OK(ctx, cudaMemcpy(d_in, in, sizeof(double) * n, cudaMemcpyHostToDevice));
+  k_rsqrt_selftest<<<(n + 255) / 256, 256, 0, ctx->stream>>>(d_in, d_out, n);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost));
+  cudaFree(d_in);
+  cudaFree(d_out);
+  return 0;
+}

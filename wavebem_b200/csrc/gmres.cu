@@ -1,0 +1,530 @@
+// gmres.cu -- BEMProblem<3>::solve_system (reference source/bem_problem.cc:821-895):
+//   alpha, compute_rhs, distribute_rhs, band preconditioner, restarted left-preconditioned
+//   GMRES (deal.II SolverGMRES with AdditionalData(100): 98 Krylov vectors per cycle,
+//   absolute tolerance on the preconditioned residual estimate), unpack into phi / dphi_dn.
+//
+// Krylov vectors live in device memory (replicated on every rank, so no all-reduce is ever
+// needed); the Hessenberg column, the Givens rotations and the stopping test are host
+// scalars, fetched with one small D2H copy per iteration.  Orthogonalisation is classical
+// Gram-Schmidt applied twice (CGS2) -- two batched kernels per pass instead of the 2k vector
+// kernels of deal.II's modified Gram-Schmidt loop; same Arnoldi relation to rounding.
+#include <cmath>
+#include <cstdio>
+#include <cstring>
+
+#include "internal.h"
+
+// ---------------------------------------------------------------------------------------
+// vector kernels
+// ---------------------------------------------------------------------------------------
+// h[i] = V[i] . w  for i < k  (one CTA per basis vector; fixed reduction order)
+__global__ void __launch_bounds__(256)
+  k_dots(uint32_t N, const double *__restrict__ V, size_t ldv, const double *__restrict__ w,
+         double *__restrict__ h)
+{
+  __shared__ double red[8];
+  const double *v = V + (size_t)blockIdx.x * ldv;
+  double s0 = 0, s1 = 0;
+  uint32_t i = threadIdx.x;
+  for (; i + 256 < N; i += 512)
+    {
+      s0 = fma(v[i], w[i], s0);
+      s1 = fma(v[i + 256], w[i + 256], s1);
+    }
+  if (i < N) s0 = fma(v[i], w[i], s0);
+  double s = s0 + s1;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    {
+      double t = 0;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) t += red[k];
+      h[blockIdx.x] = t;
+    }
+}
+
+// w -= sum_i h[i] V[i] ; optionally hacc[i] += h[i] (block 0)
+__global__ void __launch_bounds__(256)
+  k_project_out(uint32_t N, int k, const double *__restrict__ V, size_t ldv,
+                const double *__restrict__ h, double *__restrict__ w, double *__restrict__ hacc,
+                int accumulate)
+{
+  extern __shared__ double sh[];
+  for (int i = threadIdx.x; i < k; i += blockDim.x) sh[i] = h[i];
+  __syncthreads();
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N)
+    {
+      double s = w[j];
+      for (int i = 0; i < k; ++i) s = fma(-sh[i], V[(size_t)i * ldv + j], s);
+      w[j] = s;
+    }
+  if (blockIdx.x == 0 && hacc)
+    for (int i = threadIdx.x; i < k; i += blockDim.x) hacc[i] = accumulate ? hacc[i] + sh[i] : sh[i];
+}
+
+// out[0] = ||v||_2   (single CTA, fixed order)
+__global__ void __launch_bounds__(1024) k_norm2(uint32_t N, const double *__restrict__ v, double *out)
+{
+  __shared__ double red[32];
+  double s = 0;
+  for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s = fma(v[i], v[i], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32)
+    {
+      s = red[threadIdx.x];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (threadIdx.x == 0) out[0] = sqrt(s);
+    }
+}
+
+__global__ void k_scale(uint32_t N, double *__restrict__ v, double a)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) v[i] *= a;
+}
+// r = b - p
+__global__ void k_residual(uint32_t N, const double *__restrict__ b, const double *p,
+                           double *r)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) r[i] = b[i] - p[i];
+}
+// x += sum_i y[i] V[i]
+__global__ void __launch_bounds__(256)
+  k_update_solution(uint32_t N, int k, const double *__restrict__ V, size_t ldv,
+                    const double *__restrict__ y, double *__restrict__ x)
+{
+  extern __shared__ double sh[];
+  for (int i = threadIdx.x; i < k; i += blockDim.x) sh[i] = y[i];
+  __syncthreads();
+  const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  if (j < N)
+    {
+      double s = x[j];
+      for (int i = 0; i < k; ++i) s = fma(sh[i], V[(size_t)i * ldv + j], s);
+      x[j] = s;
+    }
+}
+__global__ void k_distribute_rhs(uint32_t n_lines, const uint32_t *__restrict__ lines,
+                                 const double *__restrict__ inhom, double *__restrict__ rhs)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k < n_lines) rhs[lines[k]] = inhom[k];
+}
+__global__ void k_unpack(uint32_t N, const double *__restrict__ surf, const double *__restrict__ sol,
+                         double *__restrict__ phi, double *__restrict__ dphi)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  if (surf[i] == 0)
+    phi[i] = sol[i];
+  else
+    dphi[i] = sol[i];
+}
+
+// ---------------------------------------------------------------------------------------
+// band preconditioner (reference source/bem_problem.cc:1107-1149)
+// band row r holds columns i = r - hb + 1 .. r + hb  (r in [i - hb, i + hb))
+// ---------------------------------------------------------------------------------------
+__global__ void k_extract_band(uint32_t N, uint32_t nloc, uint32_t row0, uint32_t ld, int band,
+                               const double *__restrict__ Nm, const double *__restrict__ Dm,
+                               const double *__restrict__ alpha, const double *__restrict__ surf,
+                               const int32_t *__restrict__ line_of,
+                               const uint32_t *__restrict__ colpos, double *__restrict__ out)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t r = t / band;
+  const int k = t - r * band;
+  if (r >= nloc) return;
+  const int hb = band / 2;
+  const long g = (long)row0 + r;
+  const long i = g - hb + 1 + k;
+  double v = 0.0;
+  if (i >= 0 && i < (long)N)
+    {
+      const bool row_con = line_of && line_of[g] >= 0;
+      if (row_con)
+        v = (i == g) ? 1.0 : 0.0;
+      else if (surf[i] == 0)
+        {
+          v = Nm[(size_t)r * ld + colpos[i]];
+          if (i == g) v += alpha[i];
+        }
+      else
+        v = -Dm[(size_t)r * ld + colpos[i]];
+    }
+  out[(size_t)r * band + k] = v;
+}
+
+// host banded LU with partial pivoting (row interchanges inside the band), LAPACK gbtrf
+// layout: column-major band with kl extra rows of fill.
+namespace
+{
+struct HostBand
+{
+  int n, kl, ku, ld;
+  double *ab;
+  int *piv;
+  inline double &at(int i, int j) { return ab[(size_t)j * ld + (kl + ku + i - j)]; }
+};
+
+int host_band_factor(HostBand &B)
+{
+  const int n = B.n;
+  int reach = 0; // last column touched by row interchanges so far
+  for (int j = 0; j < n; ++j)
+    {
+      const int below = std::min(B.kl, n - 1 - j);
+      int p = 0;
+      double best = std::fabs(B.at(j, j));
+      for (int k = 1; k <= below; ++k)
+        {
+          const double a = std::fabs(B.at(j + k, j));
+          if (a > best)
+            {
+              best = a;
+              p = k;
+            }
+        }
+      B.piv[j] = j + p;
+      if (best == 0.0) return j + 1;
+      reach = std::max(reach, std::min(j + B.ku + p, n - 1));
+      if (p)
+        for (int c = j; c <= reach; ++c) std::swap(B.at(j, c), B.at(j + p, c));
+      const double inv = 1.0 / B.at(j, j);
+      for (int k = 1; k <= below; ++k) B.at(j + k, j) *= inv;
+      for (int c = j + 1; c <= reach; ++c)
+        {
+          const double u = B.at(j, c);
+          if (u == 0.0) continue;
+          for (int k = 1; k <= below; ++k) B.at(j + k, c) -= B.at(j + k, j) * u;
+        }
+    }
+  return 0;
+}
+
+void host_band_solve(HostBand &B, double *x)
+{
+  const int n = B.n, span = B.kl + B.ku;
+  for (int j = 0; j < n; ++j)
+    {
+      const int below = std::min(B.kl, n - 1 - j);
+      if (B.piv[j] != j) std::swap(x[j], x[B.piv[j]]);
+      const double xj = x[j];
+      for (int k = 1; k <= below; ++k) x[j + k] -= B.at(j + k, j) * xj;
+    }
+  for (int j = n - 1; j >= 0; --j)
+    {
+      x[j] /= B.at(j, j);
+      const double xj = x[j];
+      for (int i = std::max(0, j - span); i < j; ++i) x[i] -= B.at(i, j) * xj;
+    }
+}
+} // namespace
+
+int wbem_build_preconditioner(wbem_ctx *ctx)
+{
+  const int band = ctx->p.preconditioner_band;
+  if (band <= 0)
+    {
+      ctx->precond_ready = true;
+      return 0;
+    }
+  if (ctx->precond_ready && ctx->precond_version == ctx->op_version) return 0;
+  cudaStream_t st = ctx->stream;
+  const uint32_t N = ctx->N;
+  double *loc = ctx->d_band + (size_t)ctx->p.rank * ctx->chunk * band;
+  if (ctx->nloc)
+    {
+      const size_t total = (size_t)ctx->nloc * band;
+      k_extract_band<<<(unsigned)((total + 255) / 256), 256, 0, st>>>(
+        N, ctx->nloc, ctx->row0, ctx->ld, band, ctx->d_Nm, ctx->d_Dm, ctx->d_alpha, ctx->d_surf,
+        ctx->n_lines ? ctx->d_con_line_of : nullptr, ctx->d_colpos, loc);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+    }
+  int rc = wbem_allgather_bytes(ctx, ctx->d_band, sizeof(double) * (size_t)ctx->chunk * band);
+  if (rc) return rc;
+
+  // host factorisation (precond_on_host) -- the device variant lives in precond.cu
+  if (ctx->p.precond_on_host)
+    {
+      std::vector<double> hb((size_t)N * band);
+      CUDA_OK(ctx, cudaMemcpyAsync(hb.data(), ctx->d_band, sizeof(double) * (size_t)N * band,
+                                   cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaStreamSynchronize(st));
+      const int half = band / 2;
+      HostBand B;
+      B.n = (int)N;
+      B.kl = half;      // rows below the diagonal: r - i <= half - 1
+      B.ku = half;      // rows above: i - r <= half
+      B.ld = 2 * B.kl + B.ku + 1;
+      ctx->h_lu.assign((size_t)N * B.ld, 0.0);
+      ctx->h_piv.assign(N, 0);
+      B.ab = ctx->h_lu.data();
+      B.piv = ctx->h_piv.data();
+      for (uint32_t r = 0; r < N; ++r)
+        for (int k = 0; k < band; ++k)
+          {
+            const long i = (long)r - half + 1 + k;
+            if (i >= 0 && i < (long)N) B.at((int)r, (int)i) = hb[(size_t)r * band + k];
+          }
+      const int info = host_band_factor(B);
+      if (info) WBEM_FAIL(ctx, -6, "band preconditioner is singular at column %d", info - 1);
+      ctx->h_kl = B.kl;
+      ctx->h_ku = B.ku;
+      ctx->h_ldab = B.ld;
+    }
+  else
+    {
+      rc = wbem_device_precond_factor(ctx);
+      if (rc) return rc;
+    }
+  ctx->precond_ready = true;
+  ctx->precond_version = ctx->op_version;
+  return 0;
+}
+
+int wbem_apply_preconditioner(wbem_ctx *ctx, const double *d_in, double *d_out)
+{
+  cudaStream_t st = ctx->stream;
+  const uint32_t N = ctx->N;
+  if (ctx->p.preconditioner_band <= 0)
+    {
+      if (d_in != d_out)
+        CUDA_OK(ctx, cudaMemcpyAsync(d_out, d_in, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+      return 0;
+    }
+  if (!ctx->precond_ready) WBEM_FAIL(ctx, -3, "preconditioner applied before it was assembled");
+  if (ctx->p.precond_on_host)
+    {
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, d_in, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaStreamSynchronize(st));
+      HostBand B;
+      B.n = (int)N;
+      B.kl = ctx->h_kl;
+      B.ku = ctx->h_ku;
+      B.ld = ctx->h_ldab;
+      B.ab = ctx->h_lu.data();
+      B.piv = ctx->h_piv.data();
+      host_band_solve(B, ctx->h_pinned);
+      CUDA_OK(ctx, cudaMemcpyAsync(d_out, ctx->h_pinned, sizeof(double) * N, cudaMemcpyHostToDevice, st));
+      return 0;
+    }
+  return wbem_device_precond_solve(ctx, d_in, d_out);
+}
+
+// ---------------------------------------------------------------------------------------
+// GMRES
+// ---------------------------------------------------------------------------------------
+namespace
+{
+inline void givens(std::vector<double> &h, std::vector<double> &b, std::vector<double> &ci,
+                   std::vector<double> &si, int col)
+{
+  for (int i = 0; i < col; ++i)
+    {
+      const double s = si[i], c = ci[i], t = h[i];
+      h[i] = c * t + s * h[i + 1];
+      h[i + 1] = -s * t + c * h[i + 1];
+    }
+  const double r = 1.0 / std::sqrt(h[col] * h[col] + h[col + 1] * h[col + 1]);
+  si[col] = h[col + 1] * r;
+  ci[col] = h[col] * r;
+  h[col] = ci[col] * h[col] + si[col] * h[col + 1];
+  b[col + 1] = -si[col] * b[col];
+  b[col] *= ci[col];
+}
+} // namespace
+
+struct EvTimer
+{ // accumulates device time of bracketed regions; resolved after a sync
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;
+  size_t used = 0;
+  cudaStream_t st;
+  void begin(int t)
+  {
+    if (used + 2 > ev.size())
+      {
+        const size_t old = ev.size();
+        ev.resize(old + 64);
+        for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]);
+      }
+    tag.push_back(t);
+    cudaEventRecord(ev[used++], st);
+  }
+  void end() { cudaEventRecord(ev[used++], st); }
+  void resolve(double *sums, int ntags)
+  {
+    for (int i = 0; i < ntags; ++i) sums[i] = 0;
+    for (size_t k = 0; k < tag.size(); ++k)
+      {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]);
+        sums[tag[k]] += ms;
+      }
+    used = 0;
+    tag.clear();
+  }
+};
+static EvTimer g_timer;
+
+int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, const double *d_bc,
+                             int *iters_out, double *last_res_out)
+{
+  cudaStream_t st = ctx->stream;
+  const uint32_t N = ctx->N;
+  const unsigned nb = (N + 255) / 256;
+  if (!ctx->assembled) WBEM_FAIL(ctx, -3, "solve_system before assemble_system");
+  if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "solve_system before wbem_set_masks");
+  g_timer.st = st;
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
+  int rc;
+  // alpha (compute_alpha, :833) -- a function of the assembled Neumann matrix only
+  if (!ctx->have_alpha)
+    {
+      g_timer.begin(3);
+      rc = wbem_launch_alpha(ctx);
+      g_timer.end();
+      if (rc) return rc;
+    }
+  // system_rhs (:839) and constrained rows (:845)
+  g_timer.begin(0);
+  rc = wbem_apply_operator(ctx, 1, d_bc, ctx->d_rhs, false);
+  g_timer.end();
+  if (rc) return rc;
+  if (ctx->n_lines)
+    {
+      k_distribute_rhs<<<(ctx->n_lines + 255) / 256, 256, 0, st>>>(ctx->n_lines, ctx->d_con_lines,
+                                                                   ctx->d_con_inhom, ctx->d_rhs);
+      ctx->launches++;
+    }
+  // preconditioner (:851)
+  g_timer.begin(1);
+  rc = wbem_build_preconditioner(ctx);
+  g_timer.end();
+  if (rc) return rc;
+
+  // solver.solve(cc, sol, system_rhs, preconditioner) (:853), x0 = 0 (:830)
+  const int ntmp = ctx->p.gmres_n_tmp_vectors;
+  const int m = ntmp - 2;
+  const double tol = ctx->p.gmres_tol;
+  const int max_steps = ctx->p.gmres_max_steps;
+  const size_t ldv = ctx->ld;
+  double *V = ctx->d_V, *p = ctx->d_tmp[0], *x = ctx->d_sol;
+  double *d_h = ctx->d_h;         // [0..ntmp) current pass, [128..) accumulated, [256] norm
+  double *hp = ctx->h_pinned;
+  CUDA_OK(ctx, cudaMemsetAsync(x, 0, sizeof(double) * N, st));
+  std::vector<double> H((size_t)ntmp * ntmp, 0.0), gamma(ntmp + 1), ci(ntmp + 1), si(ntmp + 1),
+    h(ntmp + 1), y(ntmp + 1);
+  int accumulated = 0, state = 0;
+  double rho = 0;
+  bool x_is_zero = true;
+  g_timer.begin(2);
+  int n_gemv = 0;
+  do
+    {
+      double *v0 = V;
+      if (x_is_zero)
+        CUDA_OK(ctx, cudaMemcpyAsync(p, ctx->d_rhs, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+      else
+        {
+          rc = wbem_apply_operator(ctx, 0, x, p, true);
+          ++n_gemv;
+          if (rc) return rc;
+          k_residual<<<nb, 256, 0, st>>>(N, ctx->d_rhs, p, p);
+          ctx->launches++;
+        }
+      rc = wbem_apply_preconditioner(ctx, p, v0);
+      if (rc) return rc;
+      k_norm2<<<1, 1024, 0, st>>>(N, v0, d_h + 256);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaMemcpyAsync(hp, d_h + 256, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaStreamSynchronize(st));
+      rho = hp[0];
+      state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
+      if (!(rho == rho)) state = 2;
+      if (state != 0) break;
+      gamma[0] = rho;
+      k_scale<<<nb, 256, 0, st>>>(N, v0, 1.0 / rho);
+      ctx->launches++;
+      int dim = 0;
+      for (int inner = 0; inner < m && state == 0; ++inner)
+        {
+          ++accumulated;
+          double *vv = V + (size_t)(inner + 1) * ldv;
+          rc = wbem_apply_operator(ctx, 0, V + (size_t)inner * ldv, p, true);
+          ++n_gemv;
+          if (rc) return rc;
+          rc = wbem_apply_preconditioner(ctx, p, vv);
+          if (rc) return rc;
+          dim = inner + 1;
+          // CGS2
+          for (int pass = 0; pass < 2; ++pass)
+            {
+              k_dots<<<dim, 256, 0, st>>>(N, V, ldv, vv, d_h);
+              k_project_out<<<nb, 256, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_h, vv, d_h + 128,
+                                                                  pass);
+              ctx->launches += 2;
+            }
+          k_norm2<<<1, 1024, 0, st>>>(N, vv, d_h + 128 + dim);
+          ctx->launches++;
+          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_h + 128, sizeof(double) * (dim + 1),
+                                       cudaMemcpyDeviceToHost, st));
+          CUDA_OK(ctx, cudaStreamSynchronize(st));
+          for (int i = 0; i <= dim; ++i) h[i] = hp[i];
+          const double s = h[dim];
+          k_scale<<<nb, 256, 0, st>>>(N, vv, 1.0 / s);
+          ctx->launches++;
+          givens(h, gamma, ci, si, inner);
+          for (int i = 0; i < dim; ++i) H[(size_t)i * ntmp + inner] = h[i];
+          rho = std::fabs(gamma[dim]);
+          state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
+          if (!(rho == rho)) state = 2;
+        }
+      // H y = gamma, x += V y
+      for (int i = dim - 1; i >= 0; --i)
+        {
+          double s = gamma[i];
+          for (int k = i + 1; k < dim; ++k) s -= H[(size_t)i * ntmp + k] * y[k];
+          y[i] = s / H[(size_t)i * ntmp + i];
+        }
+      for (int i = 0; i < dim; ++i) hp[i] = y[i];
+      CUDA_OK(ctx, cudaMemcpyAsync(d_h, hp, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+      k_update_solution<<<nb, 256, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_h, x);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaStreamSynchronize(st)); // hp is reused next cycle
+      x_is_zero = false;
+    }
+  while (state == 0);
+  g_timer.end();
+  // unpack (:869-879)
+  k_unpack<<<nb, 256, 0, st>>>(N, ctx->d_surf, x, d_phi, d_dphi_dn);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], st));
+  CUDA_OK(ctx, cudaStreamSynchronize(st));
+  CUDA_OK(ctx, cudaGetLastError());
+  double sums[4];
+  g_timer.resolve(sums, 4);
+  float ms = 0;
+  cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
+  ctx->tm.rhs_ms = sums[0];
+  ctx->tm.precond_setup_ms = sums[1];
+  ctx->tm.gmres_ms = sums[2];
+  if (sums[3] > 0) ctx->tm.alpha_ms = sums[3];
+  ctx->tm.solve_system_total_ms = ms;
+  ctx->tm.gmres_iters = accumulated;
+  ctx->tm.gemv_calls = n_gemv + 1;
+  if (iters_out) *iters_out = accumulated;
+  if (last_res_out) *last_res_out = rho;
+  return state == 1 ? 0 : 1;
+}

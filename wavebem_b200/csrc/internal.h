@@ -1,0 +1,171 @@
+// internal.h -- shared declarations of libwbem (not part of the ABI).
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+#include <string>
+#include <vector>
+
+#include "../../include/wbem.h"
+
+#define WBEM_MAX_NQ 64   // regular rule: up to 8 x 8
+#define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
+
+struct QuadTables
+{ // host copies of the reference-cell tables (uploaded to __constant__ memory)
+  int nq, ns;
+  double g_u[WBEM_MAX_NQ], g_v[WBEM_MAX_NQ], g_w[WBEM_MAX_NQ];
+  double g_shape[4][WBEM_MAX_NQ];
+  double s_u[4][WBEM_MAX_NS], s_v[4][WBEM_MAX_NS], s_w[4][WBEM_MAX_NS];
+  double g1_x[8], g1_w[8]; // 1-D rule (tensor structure of the regular rule)
+  int n1;
+};
+int wbem_build_quadrature(int quad_order, int sing_order, QuadTables *qt);
+
+struct NcclApi; // comm.cpp
+
+// Tiling plan of the regular-pair kernel, built once per topology (plan.cpp).
+struct AssemblyPlan
+{
+  uint32_t n_clusters = 0, n_colors = 0;
+  uint32_t W = 0;                        // max column slots per cluster
+  uint32_t n_cols_written = 0;           // storage columns [0,n) are written by the kernel
+  uint32_t max_cells = 0;                // largest cluster (cells)
+  std::vector<uint32_t> cl_cell_ptr;     // [ncl+1] range in cell processing order
+  std::vector<uint32_t> cell_order;      // [C] processing position -> cell id
+  std::vector<uint32_t> cell_pos;        // [C] cell id -> processing position
+  std::vector<uint8_t> cell_slots;       // [C*4] in processing order: slot of local dof j
+  std::vector<uint32_t> cl_slot_ptr;     // [ncl+1]
+  std::vector<uint32_t> slot_col;        // storage column of each slot | (add flag << 31)
+  std::vector<uint32_t> color_ptr;       // [ncolors+1] range in cluster launch order
+  std::vector<uint32_t> color_clusters;  // cluster ids grouped by color
+  std::vector<uint32_t> colpos;          // [N] global dof -> storage column
+  std::vector<uint32_t> colperm;         // [N] storage column -> global dof
+};
+int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t W_max,
+                    uint32_t max_cells_per_cluster, AssemblyPlan *plan);
+
+struct wbem_ctx
+{
+  wbem_params p;
+  std::string err;
+  int dev = 0;
+  cudaStream_t stream = nullptr;
+  cudaEvent_t ev[16] = {};
+  QuadTables qt;
+
+  // sizes
+  uint32_t N = 0, C = 0, ld = 0;
+  uint32_t chunk = 0, row0 = 0, row1 = 0, nloc = 0;
+
+  // host topology
+  std::vector<uint32_t> h_cell_dofs, h_dn_ptr, h_dn_idx;
+  std::vector<uint8_t> h_dir;
+  AssemblyPlan plan;
+
+  // device topology
+  uint32_t *d_cell_dofs = nullptr; // [C][4] in processing order (storage columns NOT applied)
+  uint8_t *d_dir = nullptr;        // processing order
+  uint32_t *d_cell_order = nullptr;
+  uint32_t *d_colpos = nullptr, *d_colperm = nullptr;
+  // singular pairs of the local rows: CSR by local row
+  uint32_t *d_sing_ptr = nullptr, *d_sing_cellpos = nullptr; // cell processing position, sorted
+  uint8_t *d_sing_idx = nullptr;
+  uint32_t n_sing = 0;
+  // plan on device
+  uint32_t *d_cl_cell_ptr = nullptr, *d_cl_slot_ptr = nullptr, *d_slot_col = nullptr,
+           *d_color_clusters = nullptr;
+  uint8_t *d_cell_slots = nullptr;
+
+  // geometry
+  double *d_xyz = nullptr;     // [N][3]
+  double *d_cellgeo = nullptr; // [C][7][nq] in processing order
+  bool have_geometry = false, assembled = false, have_alpha = false;
+
+  // matrices: nloc x ld, row-major, columns in storage order (colperm)
+  double *d_Nm = nullptr, *d_Dm = nullptr;
+  double *d_alpha = nullptr; // [N] replicated
+
+  // masks / constraints (replicated)
+  double *d_surf = nullptr, *d_other = nullptr;
+  bool have_masks = false, pure_neumann = false;
+  std::vector<double> h_surf, h_other;
+  uint32_t n_lines = 0;
+  int32_t *d_con_line_of = nullptr;
+  uint32_t *d_con_lines = nullptr, *d_con_ptr = nullptr, *d_con_col = nullptr;
+  double *d_con_val = nullptr, *d_con_inhom = nullptr;
+  std::vector<int32_t> h_con_line_of;
+  uint64_t op_version = 0, precond_version = ~0ull; // preconditioner cache key
+
+  // work vectors (device, length N or chunk*world)
+  double *d_xn = nullptr, *d_xd = nullptr; // permuted multipliers of N and D
+  double *d_yloc = nullptr;                // [chunk*world] gather buffer
+  double *d_xdiag = nullptr;               // [N] multiplier of N in global order
+  uint32_t *d_list_o = nullptr, *d_list_s = nullptr; // 64-column chunks with non-zero mask
+  int n_list_o = 0, n_list_s = 0;
+  double *d_tmp[8] = {};
+  double *d_rhs = nullptr, *d_sol = nullptr;
+  double *d_V = nullptr;   // Krylov basis [n_tmp-1][N]
+  double *d_h = nullptr;   // small scalars
+  double *h_pinned = nullptr; // pinned staging, >= 4N doubles
+  size_t pinned_doubles = 0;
+
+  // preconditioner
+  double *d_band = nullptr;     // [N][band] band_system rows (all ranks' rows after gather)
+  std::vector<double> h_lu;     // host LU (precond_on_host)
+  std::vector<int> h_piv;
+  int h_kl = 0, h_ku = 0, h_ldab = 0;
+  bool precond_ready = false;
+  void *dev_precond = nullptr;  // precond.cu state
+
+  // comm
+  NcclApi *nccl = nullptr;
+  void *nccl_comm = nullptr;
+
+  wbem_timings tm = {};
+  long long launches = 0;
+};
+
+#define WBEM_FAIL(ctx, code, ...)                                   \
+  do                                                                \
+    {                                                               \
+      char _b[512];                                                 \
+      snprintf(_b, sizeof(_b), __VA_ARGS__);                        \
+      (ctx)->err = _b;                                              \
+      return (code);                                                \
+    }                                                               \
+  while (0)
+
+#define CUDA_OK(ctx, call)                                                            \
+  do                                                                                  \
+    {                                                                                 \
+      cudaError_t _e = (call);                                                        \
+      if (_e != cudaSuccess)                                                          \
+        WBEM_FAIL(ctx, -2, "CUDA error %s at %s:%d (%s)", cudaGetErrorString(_e),     \
+                  __FILE__, __LINE__, #call);                                         \
+    }                                                                                 \
+  while (0)
+
+// assemble.cu
+int wbem_upload_tables(wbem_ctx *ctx);
+int wbem_launch_geometry(wbem_ctx *ctx);
+int wbem_launch_assemble(wbem_ctx *ctx);
+int wbem_launch_alpha(wbem_ctx *ctx);
+// operator.cu
+int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double *d_src,
+                        double *d_dst, bool constrained);
+int wbem_allgather_rows(wbem_ctx *ctx, double *d_buf /* [chunk*world], own block filled */);
+int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank);
+// gmres.cu
+int wbem_build_preconditioner(wbem_ctx *ctx);
+int wbem_apply_preconditioner(wbem_ctx *ctx, const double *d_in, double *d_out);
+int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn,
+                             const double *d_bc, int *iters, double *last_res);
+// precond.cu
+int wbem_device_precond_factor(wbem_ctx *ctx);
+int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out);
+void wbem_device_precond_free(wbem_ctx *ctx);
+// comm.cpp
+int wbem_nccl_unique_id(void *id128, std::string *err);
+int wbem_nccl_init(wbem_ctx *ctx, const void *id128);
+void wbem_nccl_destroy(wbem_ctx *ctx);
+int wbem_nccl_allgather(wbem_ctx *ctx, const void *send, void *recv, size_t bytes_per_rank);

@@ -1,0 +1,231 @@
+// operator.cu -- the dense operator applications of the GMRES solve.
+//
+//   BEMProblem<3>::vmult        dst = -D (s.x) + N (o.x) + alpha.o.x   (source/bem_problem.cc:620-670)
+//   BEMProblem<3>::compute_rhs  dst = -(N (s.t) + alpha.s.t) + D (o.t) (source/bem_problem.cc:673-707)
+//   ConstrainedOperator::vmult  constrained rows overwritten          (include/constrained_matrix.h:73-86)
+//
+// s = surface_nodes, o = other_nodes.  Because the multiplier of N (resp. D) is exactly zero
+// wherever its mask is zero, only the 64-column chunks of each matrix whose mask is non-zero
+// are streamed (chunk lists built in wbem_set_masks): with complementary 0/1 masks one
+// operator application reads ~8 N^2 bytes instead of the reference's 16 N^2.
+// Each warp owns 4 rows: the x chunk is loaded once and reused for 4 streamed 128-bit
+// matrix loads per lane.
+#include <cstdio>
+
+#include "internal.h"
+
+#define GEMV_RPW 4     // rows per warp
+#define GEMV_WARPS 8   // warps per CTA
+
+__device__ __forceinline__ double2 ld_stream(const double *p)
+{
+  double2 r;
+  asm volatile("ld.global.nc.L1::no_allocate.v2.f64 {%0, %1}, [%2];" : "=d"(r.x), "=d"(r.y) : "l"(p));
+  return r;
+}
+
+__device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const double *__restrict__ x,
+                                          const uint32_t *__restrict__ list, int n, uint32_t ld,
+                                          const uint32_t rows[GEMV_RPW], int lane,
+                                          double acc[GEMV_RPW])
+{
+  int i = 0;
+  for (; i + 1 < n; i += 2)
+    {
+      const uint32_t c0 = list[i] * 64 + lane * 2, c1 = list[i + 1] * 64 + lane * 2;
+      double2 m0[GEMV_RPW], m1[GEMV_RPW];
+#pragma unroll
+      for (int r = 0; r < GEMV_RPW; ++r)
+        {
+          m0[r] = ld_stream(M + (size_t)rows[r] * ld + c0);
+          m1[r] = ld_stream(M + (size_t)rows[r] * ld + c1);
+        }
+      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0);
+      const double2 x1 = *reinterpret_cast<const double2 *>(x + c1);
+#pragma unroll
+      for (int r = 0; r < GEMV_RPW; ++r)
+        {
+          acc[r] = fma(m0[r].x, x0.x, acc[r]);
+          acc[r] = fma(m0[r].y, x0.y, acc[r]);
+          acc[r] = fma(m1[r].x, x1.x, acc[r]);
+          acc[r] = fma(m1[r].y, x1.y, acc[r]);
+        }
+    }
+  if (i < n)
+    {
+      const uint32_t c0 = list[i] * 64 + lane * 2;
+      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0);
+#pragma unroll
+      for (int r = 0; r < GEMV_RPW; ++r)
+        {
+          const double2 m0 = ld_stream(M + (size_t)rows[r] * ld + c0);
+          acc[r] = fma(m0.x, x0.x, acc[r]);
+          acc[r] = fma(m0.y, x0.y, acc[r]);
+        }
+    }
+}
+
+// y[r] = s1 * (M1[r,:] . x1) + s2 * (M2[r,:] . x2) + sdiag * alpha[row0+r] * xdiag[row0+r]
+__global__ void __launch_bounds__(GEMV_WARPS * 32)
+  k_bem_gemv(const double *__restrict__ M1, const double *__restrict__ x1,
+             const uint32_t *__restrict__ list1, int n1, double s1, const double *__restrict__ M2,
+             const double *__restrict__ x2, const uint32_t *__restrict__ list2, int n2, double s2,
+             const double *__restrict__ alpha, const double *__restrict__ xdiag, double sdiag,
+             uint32_t ld, uint32_t nloc, uint32_t row0, double *__restrict__ y)
+{
+  const int lane = threadIdx.x & 31;
+  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+  const uint32_t r0 = w * GEMV_RPW;
+  if (r0 >= nloc) return;
+  uint32_t rows[GEMV_RPW];
+#pragma unroll
+  for (int r = 0; r < GEMV_RPW; ++r) rows[r] = min(r0 + r, nloc - 1);
+  double a1[GEMV_RPW], a2[GEMV_RPW];
+#pragma unroll
+  for (int r = 0; r < GEMV_RPW; ++r) a1[r] = a2[r] = 0.0;
+  gemv_pass(M1, x1, list1, n1, ld, rows, lane, a1);
+  gemv_pass(M2, x2, list2, n2, ld, rows, lane, a2);
+#pragma unroll
+  for (int r = 0; r < GEMV_RPW; ++r)
+    {
+      double v = s1 * a1[r] + s2 * a2[r];
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+      if (lane == 0 && r0 + r < nloc)
+        {
+          const uint32_t g = row0 + r0 + r;
+          y[r0 + r] = v + sdiag * alpha[g] * xdiag[g];
+        }
+    }
+}
+
+// multipliers: x1p[colpos[i]] = m1[i] src[i], x2p[colpos[i]] = m2[i] src[i], xdiag[i] = m1[i] src[i]
+__global__ void k_prep_multipliers(uint32_t N, const double *__restrict__ src,
+                                   const double *__restrict__ m1, const double *__restrict__ m2,
+                                   const uint32_t *__restrict__ colpos, double *__restrict__ x1p,
+                                   double *__restrict__ x2p, double *__restrict__ xdiag)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double s = src[i];
+  const double a = m1[i] * s, b = m2[i] * s;
+  const uint32_t c = colpos[i];
+  x1p[c] = a;
+  x2p[c] = b;
+  xdiag[i] = a;
+}
+
+// dst = gathered rows, with constrained rows replaced by src_i - sum c_ik src_k
+__global__ void k_epilogue(uint32_t N, const double *__restrict__ y, const double *__restrict__ src,
+                           const int32_t *__restrict__ line_of, const uint32_t *__restrict__ cptr,
+                           const uint32_t *__restrict__ ccol, const double *__restrict__ cval,
+                           double shift, double *__restrict__ dst)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  double v = y[i] + shift;
+  if (line_of)
+    {
+      const int l = line_of[i];
+      if (l >= 0)
+        {
+          v = src[i];
+          for (uint32_t k = cptr[l]; k < cptr[l + 1]; ++k) v -= cval[k] * src[ccol[k]];
+        }
+    }
+  dst[i] = v;
+}
+
+// single-CTA l2 norm (used only by the pure-Neumann shift of vmult, :667-668)
+__global__ void k_norm2_single(uint32_t N, const double *__restrict__ v, double *__restrict__ out)
+{
+  __shared__ double red[32];
+  double s = 0;
+  for (uint32_t i = threadIdx.x; i < N; i += blockDim.x) s = fma(v[i], v[i], s);
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
+  __syncthreads();
+  if (threadIdx.x < 32)
+    {
+      s = threadIdx.x < (blockDim.x >> 5) ? red[threadIdx.x] : 0.0;
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
+      if (threadIdx.x == 0) out[0] = sqrt(s);
+    }
+}
+
+__global__ void k_add_neg_scalar(uint32_t N, double *__restrict__ v, const double *__restrict__ s)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N) v[i] -= s[0];
+}
+
+int wbem_allgather_rows(wbem_ctx *ctx, double *d_buf)
+{
+  if (ctx->p.world_size <= 1) return 0;
+  return wbem_allgather_bytes(ctx, d_buf, sizeof(double) * (size_t)ctx->chunk);
+}
+
+int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank)
+{
+  if (ctx->p.world_size <= 1) return 0;
+  if (!ctx->nccl_comm)
+    WBEM_FAIL(ctx, -5, "world_size=%d but wbem_comm_init was not called", ctx->p.world_size);
+  const char *base = (const char *)d_buf;
+  return wbem_nccl_allgather(ctx, base + bytes_per_rank * ctx->p.rank, d_buf, bytes_per_rank);
+}
+
+// chunk lists (see header comment): d_list_o = chunks with any other_nodes != 0, d_list_s =
+// chunks with any surface_nodes != 0, in storage-column order; built by wbem_set_masks.
+int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_dst,
+                        bool constrained)
+{
+  cudaStream_t st = ctx->stream;
+  const uint32_t N = ctx->N;
+  if (!ctx->assembled) WBEM_FAIL(ctx, -3, "operator applied before wbem_assemble");
+  if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "operator applied before wbem_set_masks");
+  if (!ctx->have_alpha) WBEM_FAIL(ctx, -3, "operator applied before alpha was computed");
+  const uint32_t *list_o = ctx->d_list_o, *list_s = ctx->d_list_s;
+  const int n_o = ctx->n_list_o, n_s = ctx->n_list_s;
+  const double *m1 = mode == 0 ? ctx->d_other : ctx->d_surf; // multiplier mask of N
+  const double *m2 = mode == 0 ? ctx->d_surf : ctx->d_other; // multiplier mask of D
+  k_prep_multipliers<<<(N + 255) / 256, 256, 0, st>>>(N, d_src, m1, m2, ctx->d_colpos, ctx->d_xn,
+                                                     ctx->d_xd, ctx->d_xdiag);
+  ctx->launches++;
+  double *yloc = ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk;
+  if (ctx->nloc)
+    {
+      const uint32_t warps = (ctx->nloc + GEMV_RPW - 1) / GEMV_RPW;
+      const uint32_t blocks = (warps + GEMV_WARPS - 1) / GEMV_WARPS;
+      if (mode == 0)
+        k_bem_gemv<<<blocks, GEMV_WARPS * 32, 0, st>>>(ctx->d_Nm, ctx->d_xn, list_o, n_o, 1.0,
+                                                      ctx->d_Dm, ctx->d_xd, list_s, n_s, -1.0,
+                                                      ctx->d_alpha, ctx->d_xdiag, 1.0, ctx->ld,
+                                                      ctx->nloc, ctx->row0, yloc);
+      else
+        k_bem_gemv<<<blocks, GEMV_WARPS * 32, 0, st>>>(ctx->d_Nm, ctx->d_xn, list_s, n_s, -1.0,
+                                                      ctx->d_Dm, ctx->d_xd, list_o, n_o, 1.0,
+                                                      ctx->d_alpha, ctx->d_xdiag, -1.0, ctx->ld,
+                                                      ctx->nloc, ctx->row0, yloc);
+      ctx->launches++;
+    }
+  ctx->tm.gemv_bytes_last = 8.0 * 64.0 * (double)(n_o + n_s) * (double)ctx->nloc;
+  int rc = wbem_allgather_rows(ctx, ctx->d_yloc);
+  if (rc) return rc;
+  const bool shift = (mode == 0) && ctx->pure_neumann;
+  if (shift)
+    {
+      k_norm2_single<<<1, 1024, 0, st>>>(N, ctx->d_yloc, ctx->d_h + 512);
+      ctx->launches++;
+      k_add_neg_scalar<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->d_yloc, ctx->d_h + 512);
+      ctx->launches++;
+    }
+  const bool con = constrained && ctx->n_lines > 0;
+  k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->d_yloc, d_src, con ? ctx->d_con_line_of : nullptr,
+                                             ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0,
+                                             d_dst);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
