@@ -1,0 +1,342 @@
+#!/usr/bin/env python
+"""Benchmark of the BEM hot path: one step = BEMProblem::solve() = assemble_system + solve_system
+(dense fp64 assembly of both matrices + preconditioned GMRES) on a synthetic tank + Wigley hull.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl ours|reference]
+
+N = 1: BASELINE.json configs[1] (~20k collocation nodes, one B200).  N > 1 (torchrun, one rank
+per GPU): weak scaling -- the matrices are row-sharded and the node count grows as
+20k * sqrt(N), so every GPU keeps ~the same number of matrix entries (N = 4 is configs[2],
+~40k nodes).  Prints ONE JSON line on rank 0.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import math
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "BEM matrix entries/s (fp64) through assemble_system + GMRES solve_system"
+UNIT = "entries/s"
+FLOP_PER_EVAL = 34.0   # algorithmic flop per (node, quadrature point)
+
+
+def measured_peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler(threading.Thread):
+    """nvidia-smi clocks / throttle reasons during the timed region."""
+    Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
+         "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
+         "clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        super().__init__(daemon=True)
+        self.gpu = gpu_index
+        self.samples = []
+        self.stop_flag = False
+
+    def run(self):
+        while not self.stop_flag:
+            try:
+                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+                f = [x.strip() for x in out.strip().split(",")]
+                if len(f) >= 8:
+                    self.samples.append(f)
+            except Exception:
+                pass
+            time.sleep(0.2)
+
+    def summary(self):
+        if not self.samples:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
+        sm = sorted(float(s[1]) for s in self.samples)
+        reasons = []
+        for name, k in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
+                        ("sw_power_cap", 7)):
+            if any(s[k].lower().startswith("active") for s in self.samples):
+                reasons.append(name)
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": reasons,
+                "power_w_max": max(float(s[3]) for s in self.samples), "samples": len(self.samples)}
+
+
+def build_case(n_target, froude=0.28):
+    from wavebem_b200 import meshgen
+    from wavebem_b200.constraints import compute_constraints
+    m = meshgen.wigley_tank_for_nodes(n_target)
+    bc = meshgen.towing_tank_bc(m, froude=froude)
+    nn = meshgen.cell_normals_at_nodes(m)
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, m.surface_nodes, bc, nodes_normals=nn)
+    return m, bc, cl
+
+
+# ------------------------------------------------------------------------------------------
+# CPU reference arm / cpu_baseline: the oracle (a port: the reference cannot be built here)
+# ------------------------------------------------------------------------------------------
+def cpu_sample(m, bc, cl, slab_rows, gmres_iters, threads):
+    """One bounded sample of the step on the host cores: assemble `slab_rows` rows of both
+    matrices and stream them through the (3 + 2k) dense mat-vec units of solve_system
+    (alpha, 2 for the rhs, 2 per GMRES iteration; reference bem_problem.cc:609, 648-650, 702-706).
+    Rows are independent, so entries/s of the slab is the throughput of the full step."""
+    from oracle import oracle as orc
+    n = m.n_nodes
+    r0 = (n - slab_rows) // 2
+    t0 = time.perf_counter()
+    nm, dm = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, r0, r0 + slab_rows,
+                               nthreads=threads)
+    t_asm = time.perf_counter() - t0
+    x = np.sin(0.37 * np.arange(n))
+    t0 = time.perf_counter()
+    units = 3 + 2 * gmres_iters
+    for u in range(units):
+        orc.fullmatrix_vmult(nm if u % 2 == 0 else dm, x, nthreads=threads)
+    t_mv = time.perf_counter() - t0
+    return t_asm, t_mv, 2.0 * slab_rows * n
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    from oracle import oracle as orc
+    orc.build()
+    threads = orc.max_threads()
+    world = max(1, args.gpus)
+    n_target = int(round(args.nodes * math.sqrt(world)))
+    m, bc, cl = build_case(n_target)
+    slab = args.ref_slab_rows
+    for _ in range(args.warmup):
+        cpu_sample(m, bc, cl, max(16, slab // 8), 2, threads)
+    tot_t, tot_e, asm_t = 0.0, 0.0, 0.0
+    for _ in range(args.steps):
+        ta, tm, ent = cpu_sample(m, bc, cl, slab, args.ref_gmres_iters, threads)
+        tot_t += ta + tm
+        asm_t += ta
+        tot_e += ent
+    value = tot_e / tot_t
+    sample = (f"{slab}-row slab of the N={m.n_nodes} step per timed step: both matrices assembled + "
+              f"{3 + 2 * args.ref_gmres_iters} dense mat-vec units (k={args.ref_gmres_iters} GMRES its); "
+              "oracle/wbem_oracle.c with OpenMP over rows")
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * tot_t / args.steps,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+        "config": {"workload": f"tank+Wigley hull, N={m.n_nodes} nodes, C={m.n_cells} cells, Gauss 4x4 + "
+                               "QGaussOneOverR(5); CPU sample", "nodes": m.n_nodes, "slab_rows": slab},
+        "cpu_baseline": {"value": value, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
+                         "assembly_entries_per_s": tot_e / asm_t},
+        "e2e": {"value": value, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+
+    import wavebem_b200 as wb
+    from wavebem_b200 import dist as wd
+
+    rank, world, local = wd.env_rank_world()
+    if world != max(1, args.gpus) and rank == 0:
+        print(f"warning: WORLD_SIZE={world} but --gpus {args.gpus}", file=sys.stderr)
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl")
+    n_target = int(round(args.nodes * math.sqrt(world)))
+    m, bc, cl = build_case(n_target)
+    n = m.n_nodes
+    ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=args.max_steps)
+    ctx.set_topology(n, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    wd.init_comm(ctx)
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(cl)
+
+    dev = torch.device("cuda", local)
+    d_xyz = torch.from_numpy(m.xyz).to(dev)
+    d_bc = torch.from_numpy(bc).to(dev)
+    d_phi = torch.zeros(n, dtype=torch.float64, device=dev)
+    d_dphi = torch.zeros(n, dtype=torch.float64, device=dev)
+    torch.cuda.synchronize()
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    def step_dev():
+        rc, it, res = ctx.solve_dev(d_xyz.data_ptr(), d_phi.data_ptr(), d_dphi.data_ptr(), d_bc.data_ptr())
+        return rc, it, res
+
+    # ---- device-resident leg (value) ----
+    for _ in range(args.warmup):
+        step_dev()
+    sampler = ClockSampler(local)
+    barrier()
+    sampler.start()
+    ctx.reset_counters()
+    ctx.timer_start()
+    acc = dict(asm=0.0, reg=0.0, sing=0.0, geo=0.0, alpha=0.0, solve=0.0, gmres=0.0, gemv=0.0, gemv_calls=0,
+               precond_setup=0.0, precond_apply=0.0, allgather=0.0, rhs=0.0)
+    iters = res = rc = 0
+    for _ in range(args.steps):
+        rc, iters, res = step_dev()
+        t = ctx.timings()
+        acc["asm"] += t["assemble_total_ms"]; acc["reg"] += t["assemble_regular_ms"]
+        acc["sing"] += t["assemble_singular_ms"]; acc["geo"] += t["geometry_ms"]; acc["alpha"] += t["alpha_ms"]
+        acc["solve"] += t["solve_system_total_ms"]; acc["gmres"] += t["gmres_ms"]; acc["gemv"] += t["gemv_ms_sum"]
+        acc["gemv_calls"] += t["gemv_calls"]; acc["precond_setup"] += t["precond_setup_ms"]
+        acc["precond_apply"] += t["precond_apply_ms_sum"]; acc["allgather"] += t["allgather_ms_sum"]
+        acc["rhs"] += t["rhs_ms"]
+    ms_total = ctx.timer_stop()
+    barrier()
+    sampler.stop_flag = True
+    launches = ctx.timings()["kernel_launches"]
+    gemv_bytes = ctx.timings()["gemv_bytes_last"]
+    ms_total = max_over_ranks(ms_total)
+    K = args.steps
+    entries = 2.0 * n * n
+    value = entries * K / (ms_total * 1e-3)
+
+    # ---- end-to-end leg through the host-buffer C ABI (wbem_solve) ----
+    h_xyz = torch.from_numpy(m.xyz).pin_memory().numpy()
+    h_bc = torch.from_numpy(bc).pin_memory().numpy()
+    h_phi = torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+    h_dphi = torch.zeros(n, dtype=torch.float64).pin_memory().numpy()
+    import ctypes as C
+    it_c, res_c = C.c_int(0), C.c_double(0)
+
+    def step_host():
+        return wb.lib().wbem_solve(ctx._h, h_xyz.ctypes.data_as(C.c_void_p), h_phi.ctypes.data_as(C.c_void_p),
+                                   h_dphi.ctypes.data_as(C.c_void_p), h_bc.ctypes.data_as(C.c_void_p),
+                                   C.byref(it_c), C.byref(res_c))
+    for _ in range(max(1, args.warmup // 2)):
+        step_host()
+    barrier()
+    ctx.timer_start()
+    for _ in range(K):
+        step_host()
+    e2e_ms = max_over_ranks(ctx.timer_stop())
+    barrier()
+    e2e_value = entries * K / (e2e_ms * 1e-3)
+    h2d = 8 * n * (3 + 3)   # support points, phi, dphi_dn, tmp_rhs
+    d2h = 8 * n * 2         # phi, dphi_dn
+
+    # ---- rooflines ----
+    hbm_peak, peak_src = measured_peaks()
+    gemv_ms_avg = acc["gemv"] / max(1, acc["gemv_calls"])
+    nloc = ctx.row1 - ctx.row0
+    gemv_alg_bytes = gemv_bytes + 16.0 * n          # matrix chunks + x in + y out
+    gemv_gbs = gemv_alg_bytes / (gemv_ms_avg * 1e-3) / 1e9 if gemv_ms_avg > 0 else 0.0
+    fp64_peak = ctx.measure_fp64_peak()
+    copy_bw = ctx.measure_copy_bw()
+    S = 0  # singular pairs use the 50-point rule; their share of F_A is < 0.1 %
+    evals = 16.0 * nloc * m.n_cells
+    asm_tflops = FLOP_PER_EVAL * evals / (acc["reg"] / K * 1e-3) / 1e12 if acc["reg"] > 0 else 0.0
+    traffic = None
+    tf = os.path.join(ROOT, "profiles", "gemv_dram_bytes_per_launch.json")
+    if os.path.exists(tf):
+        try:
+            traffic = json.load(open(tf)).get("bytes_per_launch")
+        except Exception:
+            traffic = None
+
+    line = None
+    if rank == 0:
+        line = {
+            "metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": K, "warmup": args.warmup,
+            "ms_per_step": ms_total / K, "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"tank+Wigley hull (BASELINE configs[1] at 1 GPU), N={n} nodes, C={m.n_cells} "
+                                   f"cells, Gauss 4x4 + QGaussOneOverR(5), GMRES tol {args.tol:g}/max {args.max_steps}, "
+                                   "band-100 preconditioner",
+                       "nodes": n, "cells": m.n_cells, "rows_per_gpu": nloc, "parallelism": f"rows/{world}",
+                       "l2_policy": "inputs larger than L2 (both matrices, 16 N^2 bytes >> 126 MB)"},
+            "gmres_iters": iters, "gmres_last_residual": res, "gmres_converged": rc == 0,
+            "assembly_entries_per_s": entries / (acc["asm"] / K * 1e-3),
+            "assemble_ms": acc["asm"] / K, "assemble_regular_ms": acc["reg"] / K,
+            "assemble_singular_ms": acc["sing"] / K, "geometry_ms": acc["geo"] / K, "alpha_ms": acc["alpha"] / K,
+            "gmres_solve_ms": acc["solve"] / K, "rhs_ms": acc["rhs"] / K,
+            "precond_setup_ms": acc["precond_setup"] / K, "precond_apply_ms_per_call": acc["precond_apply"] / max(1, acc["gemv_calls"]),
+            "gemv_ms_per_call": gemv_ms_avg, "gemv_calls_per_step": acc["gemv_calls"] / K,
+            "allgather_ms_per_step": acc["allgather"] / K,
+            "roofline": {"bound": "hbm", "kernel": "k_bem_gemv", "achieved": gemv_gbs, "peak": hbm_peak,
+                         "unit": "GB/s", "frac": gemv_gbs / hbm_peak, "traffic": traffic,
+                         "peak_source": peak_src, "bytes_per_launch": gemv_alg_bytes,
+                         "share_of_step": acc["gemv"] / (ms_total)},
+            "roofline_assembly": {"bound": "fp64", "kernel": "k_assemble_tiled", "achieved": asm_tflops,
+                                  "peak": fp64_peak, "unit": "TFLOP/s", "frac": asm_tflops / fp64_peak if fp64_peak else None,
+                                  "flop_per_eval": FLOP_PER_EVAL, "evals_per_step": evals,
+                                  "peak_source": "DFMA loop measured in this run (wbem_measure_fp64_peak)",
+                                  "share_of_step": acc["reg"] / ms_total},
+            "copy_bw_gbs_this_run": copy_bw,
+            "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h,
+                    "ms_per_step": e2e_ms / K},
+            "gpu_launches": int(launches),
+            "clocks": sampler.summary(),
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            from oracle import oracle as orc
+            orc.build()
+            threads = orc.max_threads()
+            slab = args.cpu_slab_rows
+            ta, tm, ent = cpu_sample(m, bc, cl, slab, iters, threads)
+            line["cpu_baseline"] = {
+                "value": ent / (ta + tm), "unit": UNIT, "cores": threads, "kind": "port",
+                "sample": f"{slab}-row slab of the same N={n} step: assembly + {3 + 2 * iters} dense mat-vec units "
+                          f"(k={iters} its as on the GPU), OpenMP over rows; entries/s of the slab = of the full step",
+                "assembly_entries_per_s": ent / ta, "assembly_s": ta, "matvec_s": tm}
+        print(json.dumps(line), flush=True)
+    ctx.close()
+    if world > 1:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--nodes", type=int, default=20000)
+    ap.add_argument("--tol", type=float, default=1e-10)       # prm-files/default-2.prm:107-113
+    ap.add_argument("--max-steps", type=int, default=1000)
+    ap.add_argument("--cpu-slab-rows", type=int, default=2048)
+    ap.add_argument("--ref-slab-rows", type=int, default=1024)
+    ap.add_argument("--ref-gmres-iters", type=int, default=100)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        run_reference(args)
+    else:
+        run_ours(args)
+
+
+if __name__ == "__main__":
+    main()

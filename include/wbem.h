@@ -149,6 +149,9 @@ int wbem_get_system_rhs(wbem_ctx *ctx, double *out);
 int wbem_get_sol(wbem_ctx *ctx, double *out);
 
 int wbem_get_timings(wbem_ctx *ctx, wbem_timings *out);
+/* CUDA-event stopwatch on the library's own stream (torch.cuda.Event only sees torch's). */
+int wbem_timer_start(wbem_ctx *ctx);
+int wbem_timer_stop(wbem_ctx *ctx, double *ms);
 int wbem_reset_counters(wbem_ctx *ctx);
 
 /* Row-sharded runs: rank 0 makes an id (128 bytes), the launcher (torch.distributed, MPI,

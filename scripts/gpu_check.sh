@@ -1,0 +1,34 @@
+#!/bin/bash
+# One gpurun call: smoke (under compute-sanitizer first), GPU tests, bench, ncu launch list + full captures.
+# Usage: gpurun --timeout 1500 -- 'bash scripts/gpu_check.sh [quick|full]'
+set -u
+MODE=${1:-full}
+OUT=gpurun_out
+mkdir -p $OUT
+export PYTHONUNBUFFERED=1
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw,memory.total --format=csv > $OUT/gpu_info.csv 2>&1
+echo "== build + smoke" | tee $OUT/summary.log
+timeout 600 python -c "import __graft_entry__ as g; g.build(); g.smoke()" > $OUT/smoke.log 2>&1; echo "smoke rc=$?" | tee -a $OUT/summary.log
+tail -3 $OUT/smoke.log | tee -a $OUT/summary.log
+if [ "$MODE" != "quick" ]; then
+  echo "== compute-sanitizer memcheck (smoke)" | tee -a $OUT/summary.log
+  timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/summary.log
+  grep -E "ERROR SUMMARY|Invalid|out of bounds" $OUT/memcheck.log | head -5 | tee -a $OUT/summary.log
+fi
+echo "== pytest -m gpu" | tee -a $OUT/summary.log
+timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.log
+tail -15 $OUT/pytest_gpu.log | tee -a $OUT/summary.log
+echo "== bench" | tee -a $OUT/summary.log
+timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.log
+cat $OUT/bench.json | tee -a $OUT/summary.log; tail -5 $OUT/bench.err | tee -a $OUT/summary.log
+if [ "$MODE" != "quick" ]; then
+  echo "== ncu launch list" | tee -a $OUT/summary.log
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/summary.log
+  echo "== ncu full: assembly + gemv" | tee -a $OUT/summary.log
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiled -s 6 -c 2 -f -o $OUT/prof_assemble \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_asm.log 2>&1; echo "ncu asm rc=$?" | tee -a $OUT/summary.log
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bem_gemv -s 4 -c 2 -f -o $OUT/prof_gemv \
+      python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_gemv.log 2>&1; echo "ncu gemv rc=$?" | tee -a $OUT/summary.log
+fi
+echo "== done" | tee -a $OUT/summary.log

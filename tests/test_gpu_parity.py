@@ -1,0 +1,338 @@
+"""GPU parity tests: the CUDA path, called through the C ABI, against the CPU oracle on the
+same inputs -- and, at BASELINE.json's full size, through size-independent properties.
+
+Tolerances (north_star): matrix entries 1e-11 relative (row-scaled, see conftest.rel_err_rowscaled
+and DESIGN.md "Parity metric"), GMRES solution within the solver tolerance, hull
+drag/potential 1e-8 relative.
+"""
+import numpy as np
+import pytest
+
+from conftest import make_problem, rel_err_rowscaled
+from wavebem_b200 import meshgen
+from wavebem_b200.postproc import hull_pressure_force
+
+pytestmark = pytest.mark.gpu
+
+ENTRY_TOL = 1e-11
+
+
+def _ctx(wb, mesh, **params):
+    ctx = wb.Context(**params)
+    ctx.set_topology(mesh.n_nodes, mesh.cells, mesh.dir_flag, mesh.dn_ptr, mesh.dn_idx)
+    ctx.set_geometry(mesh.xyz)
+    return ctx
+
+
+def _orc_con(orc, cl):
+    return orc.Constraints(cl.n, cl.lines, cl.ptr, cl.col, cl.val, cl.inhom)
+
+
+MESHES = {
+    "cube1": lambda: meshgen.cube(1),
+    "cube5": lambda: meshgen.cube(5),
+    "cube4_random_flipped": lambda: meshgen.cube(4, renumber="random", seed=5, flip_every=3),
+    "sphere6": lambda: meshgen.sphere(6, radius=0.7, center=(0.1, -0.2, 0.3)),
+    "tank": lambda: meshgen.wigley_tank(),
+    "tank_random": lambda: meshgen.wigley_tank(nxm=12, nt=6, nxu=4, nxd=6, nz=3, nzh=3, renumber="random", seed=2),
+    "tank_wave": lambda: meshgen.wigley_tank(nxm=12, nt=6, nxu=4, nxd=6, nz=3, nzh=3, wave_amp=0.025, wave_phase=0.7),
+}
+
+
+def test_fast_rsqrt_is_accurate(wb):
+    ctx = wb.Context()
+    rng = np.random.default_rng(0)
+    x = np.concatenate([10.0 ** rng.uniform(-12, 12, 200000), rng.uniform(0.5, 2.0, 200000),
+                        [1.0, 4.0, 0.25, 1e-300, 1e300]])
+    y = ctx.selftest_rsqrt(x)
+    ref = 1.0 / np.sqrt(x.astype(np.longdouble))
+    rel = np.abs((y - ref) / ref).astype(np.float64)
+    assert rel.max() < 2.3e-16, rel.max()  # ~1 ulp
+
+
+@pytest.mark.parametrize("name", list(MESHES))
+def test_assembly_matches_oracle(wb, orc, name):
+    m = MESHES[name]()
+    ctx = _ctx(wb, m)
+    ctx.assemble()
+    gn, gd = ctx.get_rows(0), ctx.get_rows(1)
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    assert rel_err_rowscaled(gd, od) < ENTRY_TOL
+    assert rel_err_rowscaled(gn, on) < ENTRY_TOL
+    # against the long-double arbiter the GPU is as accurate as the reference arithmetic
+    ln, ld = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, long_double=True)
+    assert rel_err_rowscaled(gd, ld) < max(4 * rel_err_rowscaled(od, ld), 1e-13)
+    assert np.abs(gn - ln).max() < max(4 * np.abs(on - ln).max(), 1e-14)
+    # alpha (compute_alpha) = -row sums
+    alpha = ctx.get_alpha()
+    assert np.abs(alpha - orc.compute_alpha(on)).max() < 1e-12
+    ctx.close()
+
+
+@pytest.mark.parametrize("orders", [(4, 5), (3, 4), (5, 6), (2, 8), (8, 12)])
+def test_simple_variant_and_other_quadrature_orders(wb, orc, orders):
+    q, s = orders
+    m = meshgen.wigley_tank(nxm=10, nt=5, nxu=4, nxd=5, nz=3, nzh=3)
+    ctx = _ctx(wb, m, quad_order=q, sing_order=s, assemble_variant=1)
+    ctx.assemble()
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, quad_order=q, sing_order=s)
+    assert rel_err_rowscaled(ctx.get_rows(1), od) < ENTRY_TOL
+    assert rel_err_rowscaled(ctx.get_rows(0), on) < ENTRY_TOL
+    if q != 4:  # default variant falls back to the same generic kernel
+        c2 = _ctx(wb, m, quad_order=q, sing_order=s)
+        c2.assemble()
+        assert rel_err_rowscaled(c2.get_rows(1), od) < ENTRY_TOL
+        c2.close()
+    ctx.close()
+
+
+def test_tiled_and_simple_kernels_agree_and_tiled_is_deterministic(wb):
+    m = meshgen.wigley_tank(renumber="random", seed=9)
+    a = _ctx(wb, m)
+    a.assemble()
+    n1, d1 = a.get_rows(0), a.get_rows(1)
+    a.set_geometry(m.xyz)
+    a.assemble()
+    assert np.array_equal(n1, a.get_rows(0)) and np.array_equal(d1, a.get_rows(1))  # bitwise
+    b = _ctx(wb, m, assemble_variant=1)
+    b.assemble()
+    assert rel_err_rowscaled(n1, b.get_rows(0)) < 1e-12
+    assert rel_err_rowscaled(d1, b.get_rows(1)) < 1e-12
+    a.close()
+    b.close()
+
+
+@pytest.fixture(scope="module")
+def tank_case(wb, orc):
+    m = meshgen.wigley_tank()
+    bc, nn, cl = make_problem(m)
+    ctx = _ctx(wb, m)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(cl)
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    alpha = orc.compute_alpha(on)
+    yield dict(m=m, bc=bc, cl=cl, con=_orc_con(orc, cl), ctx=ctx, on=on, od=od, alpha=alpha)
+    ctx.close()
+
+
+def test_operator_applications_match_oracle(wb, orc, tank_case):
+    t = tank_case
+    m, ctx = t["m"], t["ctx"]
+    s, o = m.surface_nodes, m.other_nodes
+    for x in (np.sin(0.37 * np.arange(m.n_nodes)), t["bc"], np.ones(m.n_nodes)):
+        for g, r in ((ctx.vmult(x), orc.vmult(t["on"], t["od"], t["alpha"], s, o, x)),
+                     (ctx.compute_rhs(x), orc.compute_rhs(t["on"], t["od"], t["alpha"], s, o, x)),
+                     (ctx.constrained_vmult(x), orc.constrained_vmult(t["on"], t["od"], t["alpha"], s, o, t["con"], x))):
+            assert np.abs(g - r).max() <= 1e-12 * max(1.0, np.abs(r).max())
+    rhs = ctx.compute_rhs(t["bc"])
+    assert np.array_equal(ctx.distribute_rhs(rhs), orc.distribute_rhs(t["con"], rhs))
+    # linearity (size-independent property)
+    x, y = np.cos(0.1 * np.arange(m.n_nodes)), np.sin(0.3 * np.arange(m.n_nodes))
+    lhs = ctx.constrained_vmult(2.5 * x - 0.75 * y)
+    rhs2 = 2.5 * ctx.constrained_vmult(x) - 0.75 * ctx.constrained_vmult(y)
+    assert np.abs(lhs - rhs2).max() < 1e-12
+
+
+def test_arbitrary_masks_and_pure_neumann(wb, orc, tank_case):
+    """Masks need not be 0/1 or complementary for vmult/compute_rhs to follow the reference
+    formula; an all-Neumann mask triggers the -||dst|| shift (bem_problem.cc:667-668)."""
+    t = tank_case
+    m = t["m"]
+    ctx = _ctx(wb, m)
+    ctx.assemble()
+    rng = np.random.default_rng(3)
+    x = rng.uniform(-1, 1, m.n_nodes)
+    for s, o in ((np.zeros(m.n_nodes), np.ones(m.n_nodes)),
+                 (rng.integers(0, 2, m.n_nodes).astype(float), rng.uniform(0, 1, m.n_nodes)),
+                 (np.ones(m.n_nodes), np.zeros(m.n_nodes))):
+        ctx.set_masks(s, o)
+        r = orc.vmult(t["on"], t["od"], t["alpha"], s, o, x)
+        assert np.abs(ctx.vmult(x) - r).max() <= 1e-12 * max(1.0, np.abs(r).max())
+        r = orc.compute_rhs(t["on"], t["od"], t["alpha"], s, o, x)
+        assert np.abs(ctx.compute_rhs(x) - r).max() <= 1e-12 * max(1.0, np.abs(r).max())
+    ctx.close()
+
+
+@pytest.mark.parametrize("on_host", [0, 1])
+def test_band_preconditioner_matches_oracle(wb, orc, tank_case, on_host):
+    t = tank_case
+    m = t["m"]
+    ctx = _ctx(wb, m, precond_on_host=on_host)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(t["cl"])
+    ctx.assemble_preconditioner()
+    dense = orc.band_system_dense(t["on"], t["od"], t["alpha"], m.surface_nodes, t["con"], band=100)
+    band = ctx.get_band()
+    n = m.n_nodes
+    for r in (0, 1, 49, 50, 51, n // 2, n - 51, n - 50, n - 1):
+        for k in range(100):
+            i = r - 50 + 1 + k
+            ref = dense[r, i] if 0 <= i < n else 0.0
+            assert abs(band[r, k] - ref) <= 1e-12 * max(1.0, abs(ref))
+    v = np.sin(0.11 * np.arange(n))
+    z = ctx.precond_vmult(v)
+    zo = orc.precond_apply(t["on"], t["od"], t["alpha"], m.surface_nodes, t["con"], v, band=100)
+    assert np.abs(z - zo).max() <= 1e-9 * np.abs(zo).max()
+    assert np.abs(dense @ z - v).max() < 1e-10
+    ctx.close()
+
+
+@pytest.mark.parametrize("tol,max_steps", [(1e-10, 400), (1e-16, 200)])
+def test_solve_system_matches_oracle(wb, orc, tank_case, tol, max_steps):
+    t = tank_case
+    m = t["m"]
+    n = m.n_nodes
+    ctx = _ctx(wb, m, gmres_tol=tol, gmres_max_steps=max_steps)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(t["cl"])
+    phi0 = np.where(m.surface_nodes == 1, t["bc"], 0.0)
+    dphi0 = np.where(m.surface_nodes == 1, 0.0, t["bc"])
+    phi, dphi, iters, res = ctx.solve_system(phi0, dphi0, t["bc"])
+    ref = orc.solve_system(t["on"], t["od"], m.surface_nodes, m.other_nodes, t["bc"], t["con"], phi0, dphi0,
+                           tol=tol, max_steps=max_steps)
+    assert ref["converged"] and res <= tol
+    assert abs(iters - ref["iters"]) <= max(3, ref["iters"] // 10)
+    assert np.abs(ctx.get_system_rhs() - ref["rhs"]).max() < 1e-12
+    scale = np.linalg.norm(ref["sol"])
+    # "within the solver tolerance": both are tol-accurate solutions of the same system
+    assert np.linalg.norm(ctx.get_sol() - ref["sol"]) <= max(50 * tol, 1e-11) * max(scale, 1.0)
+    # only the unknown half is overwritten (bem_problem.cc:869-879)
+    s = m.surface_nodes == 1
+    assert np.array_equal(phi[s], phi0[s]) and np.array_equal(dphi[~s], dphi0[~s])
+    # hull drag / potential functional, 1e-8 relative
+    vinf = np.array([0.28 * np.sqrt(9.81 * 2.5), 0, 0])
+    fg, pg = hull_pressure_force(m, phi, dphi, vinf)
+    fo, po = hull_pressure_force(m, np.where(s, phi0, ref["phi"]), np.where(s, ref["dphi_dn"], dphi0), vinf)
+    assert abs(fg[0] - fo[0]) <= 1e-8 * abs(fo[0]) and abs(pg - po) <= 1e-8 * abs(po)
+    # the BIE residual of the converged pair vanishes
+    r = ctx.residual(phi, dphi)
+    ro = orc.residual(t["on"], t["od"], m.surface_nodes, m.other_nodes, t["con"], phi, dphi)
+    assert np.abs(r - ro).max() < 1e-11 and np.abs(r).max() < max(1e3 * tol, 1e-11)
+    ctx.close()
+
+
+def test_no_convergence_is_reported(wb, tank_case):
+    t = tank_case
+    m = t["m"]
+    ctx = _ctx(wb, m, gmres_tol=1e-30, gmres_max_steps=9)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(t["cl"])
+    z = np.zeros(m.n_nodes)
+    with pytest.raises(wb.NoConvergence) as e:
+        ctx.solve_system(z, z, t["bc"])
+    assert e.value.last_step == 9
+    ctx.close()
+
+
+def test_calls_out_of_order_fail_loudly(wb):
+    m = meshgen.cube(2)
+    ctx = wb.Context()
+    with pytest.raises(wb.WbemError):
+        ctx._chk(wb.lib().wbem_assemble(ctx._h))
+    ctx.set_topology(m.n_nodes, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    with pytest.raises(wb.WbemError, match="set_geometry"):
+        ctx.assemble()
+    ctx.set_geometry(m.xyz)
+    with pytest.raises(wb.WbemError, match="assemble"):
+        ctx.vmult(np.zeros(m.n_nodes))
+    ctx.close()
+
+
+def test_bem_problem_mirror_api(wb, orc):
+    """The reference-shaped class: reinit / solve / solve_system / vmult / residual."""
+    m = meshgen.wigley_tank(nxm=12, nt=6, nxu=4, nxd=6, nz=3, nzh=3)
+    m.nodes_normals = meshgen.cell_normals_at_nodes(m)
+    bc = meshgen.towing_tank_bc(m)
+    bem = wb.BEMProblem(m, gmres_tol=1e-12, gmres_max_steps=300)
+    bem.reinit()
+    n = m.n_nodes
+    phi, dphi = np.zeros(n), np.zeros(n)
+    bem.solve(phi, dphi, bc)
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    con = _orc_con(orc, bem.constraints)
+    ref = orc.solve_system(on, od, m.surface_nodes, m.other_nodes, bc, con, np.zeros(n), np.zeros(n),
+                           tol=1e-12, max_steps=300)
+    assert np.linalg.norm(bem.sol - ref["sol"]) < 1e-9 * np.linalg.norm(ref["sol"])
+    assert np.abs(bem.alpha - ref["alpha"]).max() < 1e-12
+    assert rel_err_rowscaled(bem.neumann_matrix(5, 9), on[5:9]) < ENTRY_TOL
+    # solve_system again with changed boundary data (the J.v pattern): matrices are reused
+    phi2, dphi2 = np.zeros(n), np.zeros(n)
+    bem.solve_system(phi2, dphi2, 2 * bc)
+    assert np.linalg.norm(bem.sol - 2 * ref["sol"]) < 1e-8 * np.linalg.norm(ref["sol"])
+    dst = np.zeros(n)
+    bem.vmult(dst, ref["sol"])
+    assert np.abs(dst - orc.vmult(on, od, ref["alpha"], m.surface_nodes, m.other_nodes, ref["sol"])).max() < 1e-12
+    res = np.zeros(n)
+    bem.residual(res, np.where(m.surface_nodes == 1, bc, phi), np.where(m.surface_nodes == 1, dphi, bc))
+    assert np.abs(res).max() < 1e-9
+    bem2 = wb.BEMProblem(m, gmres_tol=1e-30, gmres_max_steps=5)
+    bem2.reinit()
+    with pytest.raises(wb.NoConvergence):
+        bem2.solve(np.zeros(n), np.zeros(n), bc)
+
+
+def test_hanging_node_lines(wb, orc):
+    """Constraint lines with two masters and weight 1/2 (make_hanging_node_constraints)."""
+    from wavebem_b200.constraints import compute_constraints
+    m = meshgen.cube(4)
+    n = m.n_nodes
+    top = m.node_patch == m.patch_names.index("z1")
+    s, o = top.astype(float), 1.0 - top
+    interior = np.nonzero(~m.node_on_patch_boundary & ~top)[0]
+    hang = [(int(interior[3]), [(int(interior[2]), 0.5), (int(interior[4]), 0.5)])]
+    bc = np.sin(np.arange(n) * 0.2)
+    nn = meshgen.cell_normals_at_nodes(m)
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=nn, hanging=hang)
+    ctx = _ctx(wb, m, gmres_tol=1e-12, gmres_max_steps=400)
+    ctx.assemble()
+    ctx.set_masks(s, o)
+    ctx.set_constraints(cl)
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    con = _orc_con(orc, cl)
+    alpha = orc.compute_alpha(on)
+    x = np.cos(np.arange(n) * 0.3)
+    assert np.abs(ctx.constrained_vmult(x) - orc.constrained_vmult(on, od, alpha, s, o, con, x)).max() < 1e-12
+    z = np.zeros(n)
+    _, _, it, _ = ctx.solve_system(z, z, bc)
+    ref = orc.solve_system(on, od, s, o, bc, con, z, z, tol=1e-12, max_steps=400)
+    assert np.linalg.norm(ctx.get_sol() - ref["sol"]) < 1e-9 * np.linalg.norm(ref["sol"])
+    h = hang[0]
+    assert abs(ctx.get_sol()[h[0]] - 0.5 * (ctx.get_sol()[h[1][0][0]] + ctx.get_sol()[h[1][1][0]])) < 1e-10
+    ctx.close()
+
+
+def test_full_size_20k_properties_and_row_slab_parity(wb, orc):
+    """BASELINE configs[1] size (N ~ 20k): entries of a row slab against the oracle, and
+    size-independent properties of the whole path."""
+    m = meshgen.wigley_tank_for_nodes(20000)
+    bc, nn, cl = make_problem(m)
+    n = m.n_nodes
+    ctx = _ctx(wb, m, gmres_tol=1e-10, gmres_max_steps=400)
+    ctx.assemble()
+    for r0 in (0, n // 2 - 64, n - 128):
+        on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, r0, r0 + 128)
+        assert rel_err_rowscaled(ctx.get_rows(0, r0, r0 + 128), on) < ENTRY_TOL
+        assert rel_err_rowscaled(ctx.get_rows(1, r0, r0 + 128), od) < ENTRY_TOL
+    alpha = ctx.get_alpha()
+    flat = np.isin(m.node_patch, [m.patch_names.index(k) for k in ("bottom", "fs_up", "fs_down")]) & \
+        ~m.node_on_patch_boundary
+    assert np.abs(alpha[flat] - 0.5).max() < 1e-3   # solid angle of a smooth point
+    assert alpha.min() > 0 and alpha.max() <= 1.0 + 1e-6
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(cl)
+    x, y = np.cos(0.1 * np.arange(n)), np.sin(0.3 * np.arange(n))
+    assert np.abs(ctx.constrained_vmult(x + 2 * y) - (ctx.constrained_vmult(x) + 2 * ctx.constrained_vmult(y))).max() < 1e-11
+    z = np.zeros(n)
+    phi, dphi, it, res = ctx.solve_system(z, z, bc)
+    assert res <= 1e-10 and it < 400
+    s = m.surface_nodes == 1
+    r = ctx.residual(np.where(s, bc, phi), np.where(s, dphi, bc))
+    assert np.abs(r).max() < 1e-8
+    # re-solving with the same data reproduces the result (cached preconditioner path)
+    phi2, dphi2, it2, _ = ctx.solve_system(z, z, bc)
+    assert it2 == it and np.array_equal(phi2, phi)
+    ctx.close()

@@ -1,0 +1,101 @@
+"""Host logic that runs without a GPU: the assembly tiling plan, the mesh generators'
+double-node sets, and the compute_constraints restatement."""
+import ctypes as C
+
+import numpy as np
+import pytest
+
+from wavebem_b200 import meshgen
+from wavebem_b200.constraints import compute_constraints
+
+
+def _plan_check(wb, mesh, w=48, mc=36):
+    st = np.zeros(8)
+    rc = wb.lib().wbem_plan_check(C.c_uint32(mesh.n_nodes), C.c_uint32(mesh.n_cells),
+                                  mesh.cells.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(mc),
+                                  st.ctypes.data_as(C.c_void_p))
+    return rc, st
+
+
+@pytest.mark.parametrize("make", [
+    lambda: meshgen.cube(1), lambda: meshgen.cube(5), lambda: meshgen.cube(5, renumber="random", seed=3),
+    lambda: meshgen.sphere(7, flip_every=3), lambda: meshgen.wigley_tank(),
+    lambda: meshgen.wigley_tank(renumber="random", seed=11), lambda: meshgen.wigley_tank_for_nodes(20000),
+])
+def test_plan_invariants(wb, make):
+    m = make()
+    rc, st = _plan_check(wb, m)
+    assert rc == 0, f"plan invariant {rc} violated"
+    assert st[2] <= 36 and st[3] <= 48 and st[6] == m.n_nodes
+
+
+def test_plan_small_tiles_and_degenerate_cells(wb):
+    m = meshgen.cube(4)
+    for w, mc in ((4, 1), (6, 2), (9, 4), (16, 64)):
+        rc, st = _plan_check(wb, m, w, mc)
+        assert rc == 0 and st[3] <= w and st[2] <= mc
+    # a cell with a repeated dof (collapsed quad) and a dof no cell uses
+    cells = np.array([[0, 1, 2, 2], [1, 3, 2, 4]], dtype=np.uint32)
+    st = np.zeros(8)
+    rc = wb.lib().wbem_plan_check(C.c_uint32(6), C.c_uint32(2), cells.ctypes.data_as(C.c_void_p),
+                                  C.c_uint32(48), C.c_uint32(36), st.ctypes.data_as(C.c_void_p))
+    assert rc == 0 and st[6] == 5
+    bad = np.array([[0, 1, 2, 9]], dtype=np.uint32)
+    rc = wb.lib().wbem_plan_check(C.c_uint32(4), C.c_uint32(1), bad.ctypes.data_as(C.c_void_p),
+                                  C.c_uint32(48), C.c_uint32(36), None)
+    assert rc != 0
+
+
+def test_double_nodes_sets():
+    m = meshgen.cube(3)
+    sz = np.diff(m.dn_ptr)
+    assert (sz == 3).sum() == 24 and (sz == 2).sum() == 12 * 2 * 2 and (sz == 1).sum() == 6 * 4
+    for i in range(m.n_nodes):
+        s = m.double_nodes_set(i)
+        assert i in s and (np.diff(s) > 0).all()
+        for j in s:  # symmetric
+            assert i in m.double_nodes_set(j)
+            assert np.linalg.norm(m.xyz[i] - m.xyz[j]) < 1e-8
+    t = meshgen.wigley_tank()
+    assert (np.diff(t.dn_ptr)[~t.node_on_patch_boundary] == 1).all()
+    assert set(np.unique(t.surface_nodes + t.other_nodes)) == {1.0}
+
+
+def test_tank_node_count_targets():
+    for target in (4000, 20000):
+        m = meshgen.wigley_tank_for_nodes(target)
+        assert abs(m.n_nodes - target) / target < 0.02
+
+
+def test_compute_constraints_branches():
+    m = meshgen.cube(2)
+    n = m.n_nodes
+    nn = meshgen.cell_normals_at_nodes(m)
+    top = m.node_patch == m.patch_names.index("z1")
+    bc = np.arange(n, dtype=float)
+    # all Neumann: every double is tied to the smallest member
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, np.zeros(n), bc)
+    assert (np.diff(cl.lines.astype(int)) > 0).all()
+    for k, d in enumerate(cl.lines):
+        s = m.double_nodes_set(d)
+        assert d != s[0] and list(cl.col[cl.ptr[k]:cl.ptr[k + 1]]) == [s[0]] and cl.inhom[k] == 0
+    assert cl.n_lines == sum(len(m.double_nodes_set(i)) - 1 for i in range(n) if m.double_nodes_set(i)[0] == i)
+    # top Dirichlet: Neumann doubles of a Dirichlet node take its boundary value
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, top.astype(float), bc, nodes_normals=nn)
+    for k, d in enumerate(cl.lines):
+        s = list(m.double_nodes_set(d))
+        dir_members = [j for j in s if top[j]]
+        if dir_members and not top[d]:
+            assert cl.ptr[k] == cl.ptr[k + 1] and cl.inhom[k] == bc[dir_members[0]]
+    # two Dirichlet faces meeting at an edge need the surface gradients
+    two = top | (m.node_patch == m.patch_names.index("x1"))
+    with pytest.raises(ValueError):
+        compute_constraints(m.dn_ptr, m.dn_idx, two.astype(float), bc, nodes_normals=nn)
+    g = np.zeros((n, 3))
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, two.astype(float), bc, nodes_normals=nn,
+                             node_surface_gradients=g)
+    assert cl.n_lines > 0
+    # hanging-node lines pass through
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, np.zeros(n), bc, hanging=[(4, [(0, 0.5), (8, 0.5)])])
+    k = list(cl.lines).index(4)
+    assert list(cl.val[cl.ptr[k]:cl.ptr[k + 1]]) == [0.5, 0.5]

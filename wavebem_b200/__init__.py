@@ -74,6 +74,7 @@ ABI_SYMBOLS = [
     "wbem_get_system_rhs", "wbem_get_sol", "wbem_get_timings", "wbem_reset_counters",
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
+    "wbem_timer_start", "wbem_timer_stop",
 ]
 
 
@@ -257,6 +258,14 @@ class Context:
         t = Timings()
         self._chk(lib().wbem_get_timings(self._h, C.byref(t)))
         return t.as_dict()
+
+    def timer_start(self):
+        self._chk(lib().wbem_timer_start(self._h))
+
+    def timer_stop(self) -> float:
+        ms = C.c_double(0)
+        self._chk(lib().wbem_timer_stop(self._h, C.byref(ms)))
+        return ms.value
 
     def reset_counters(self):
         self._chk(lib().wbem_reset_counters(self._h))

@@ -187,6 +187,7 @@ int wbem_destroy(wbem_ctx *ctx)
   wbem_nccl_destroy(ctx);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
+  ctx->timer.release();
   if (ctx->stream) cudaStreamDestroy(ctx->stream);
   delete ctx;
   return 0;
@@ -772,6 +773,27 @@ int wbem_reset_counters(wbem_ctx *ctx)
   CHECK_CTX(ctx);
   ctx->launches = 0;
   memset(&ctx->tm, 0, sizeof(ctx->tm));
+  return 0;
+}
+
+// CUDA-event stopwatch on the library's stream (bench.py brackets its timed region with it)
+int wbem_timer_start(wbem_ctx *ctx)
+{
+  CHECK_CTX(ctx);
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
+  return 0;
+}
+int wbem_timer_stop(wbem_ctx *ctx, double *ms)
+{
+  CHECK_CTX(ctx);
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
+  CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[11]));
+  float f = 0;
+  CUDA_OK(ctx, cudaEventElapsedTime(&f, ctx->ev[10], ctx->ev[11]));
+  *ms = f;
   return 0;
 }
 

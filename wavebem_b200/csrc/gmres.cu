@@ -345,38 +345,6 @@ inline void givens(std::vector<double> &h, std::vector<double> &b, std::vector<d
 }
 } // namespace
 
-struct EvTimer
-{ // accumulates device time of bracketed regions; resolved after a sync
-  std::vector<cudaEvent_t> ev;
-  std::vector<int> tag;
-  size_t used = 0;
-  cudaStream_t st;
-  void begin(int t)
-  {
-    if (used + 2 > ev.size())
-      {
-        const size_t old = ev.size();
-        ev.resize(old + 64);
-        for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]);
-      }
-    tag.push_back(t);
-    cudaEventRecord(ev[used++], st);
-  }
-  void end() { cudaEventRecord(ev[used++], st); }
-  void resolve(double *sums, int ntags)
-  {
-    for (int i = 0; i < ntags; ++i) sums[i] = 0;
-    for (size_t k = 0; k < tag.size(); ++k)
-      {
-        float ms = 0;
-        cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]);
-        sums[tag[k]] += ms;
-      }
-    used = 0;
-    tag.clear();
-  }
-};
-static EvTimer g_timer;
 
 int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, const double *d_bc,
                              int *iters_out, double *last_res_out)
@@ -386,19 +354,23 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   const unsigned nb = (N + 255) / 256;
   if (!ctx->assembled) WBEM_FAIL(ctx, -3, "solve_system before assemble_system");
   if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "solve_system before wbem_set_masks");
+  EvTimer &g_timer = ctx->timer;
   g_timer.st = st;
+  g_timer.on = true;
+  g_timer.used = 0;
+  g_timer.tag.clear();
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
   int rc;
   // alpha (compute_alpha, :833) -- a function of the assembled Neumann matrix only
   if (!ctx->have_alpha)
     {
-      g_timer.begin(3);
+      g_timer.begin(T_ALPHA);
       rc = wbem_launch_alpha(ctx);
       g_timer.end();
       if (rc) return rc;
     }
   // system_rhs (:839) and constrained rows (:845)
-  g_timer.begin(0);
+  g_timer.begin(T_RHS);
   rc = wbem_apply_operator(ctx, 1, d_bc, ctx->d_rhs, false);
   g_timer.end();
   if (rc) return rc;
@@ -409,7 +381,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
       ctx->launches++;
     }
   // preconditioner (:851)
-  g_timer.begin(1);
+  g_timer.begin(T_PRECOND_SETUP);
   rc = wbem_build_preconditioner(ctx);
   g_timer.end();
   if (rc) return rc;
@@ -429,7 +401,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   int accumulated = 0, state = 0;
   double rho = 0;
   bool x_is_zero = true;
-  g_timer.begin(2);
+  g_timer.begin(T_GMRES);
   int n_gemv = 0;
   do
     {
@@ -444,7 +416,9 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
           k_residual<<<nb, 256, 0, st>>>(N, ctx->d_rhs, p, p);
           ctx->launches++;
         }
+      g_timer.begin(T_PRECOND_APPLY);
       rc = wbem_apply_preconditioner(ctx, p, v0);
+      g_timer.end();
       if (rc) return rc;
       k_norm2<<<1, 1024, 0, st>>>(N, v0, d_h + 256);
       ctx->launches++;
@@ -465,7 +439,9 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
           rc = wbem_apply_operator(ctx, 0, V + (size_t)inner * ldv, p, true);
           ++n_gemv;
           if (rc) return rc;
+          g_timer.begin(T_PRECOND_APPLY);
           rc = wbem_apply_preconditioner(ctx, p, vv);
+          g_timer.end();
           if (rc) return rc;
           dim = inner + 1;
           // CGS2
@@ -513,17 +489,23 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   CUDA_OK(ctx, cudaGetLastError());
-  double sums[4];
-  g_timer.resolve(sums, 4);
+  double sums[T_NTAGS];
+  int counts[T_NTAGS];
+  g_timer.resolve(sums, counts, T_NTAGS);
+  g_timer.on = false;
   float ms = 0;
   cudaEventElapsedTime(&ms, ctx->ev[4], ctx->ev[5]);
-  ctx->tm.rhs_ms = sums[0];
-  ctx->tm.precond_setup_ms = sums[1];
-  ctx->tm.gmres_ms = sums[2];
-  if (sums[3] > 0) ctx->tm.alpha_ms = sums[3];
+  ctx->tm.rhs_ms = sums[T_RHS];
+  ctx->tm.precond_setup_ms = sums[T_PRECOND_SETUP];
+  ctx->tm.gmres_ms = sums[T_GMRES];
+  if (counts[T_ALPHA]) ctx->tm.alpha_ms = sums[T_ALPHA];
+  ctx->tm.gemv_ms_sum = sums[T_GEMV];
+  ctx->tm.precond_apply_ms_sum = sums[T_PRECOND_APPLY];
+  ctx->tm.allgather_ms_sum = sums[T_ALLGATHER];
   ctx->tm.solve_system_total_ms = ms;
   ctx->tm.gmres_iters = accumulated;
-  ctx->tm.gemv_calls = n_gemv + 1;
+  ctx->tm.gemv_calls = counts[T_GEMV];
+  (void)n_gemv;
   if (iters_out) *iters_out = accumulated;
   if (last_res_out) *last_res_out = rho;
   return state == 1 ? 0 : 1;

@@ -44,9 +44,54 @@ struct AssemblyPlan
 int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t W_max,
                     uint32_t max_cells_per_cluster, AssemblyPlan *plan);
 
+struct EvTimer
+{ // accumulates device time of bracketed regions on one stream; resolved after a sync
+  std::vector<cudaEvent_t> ev;
+  std::vector<int> tag;
+  size_t used = 0;
+  cudaStream_t st = nullptr;
+  bool on = false;
+  void begin(int t)
+  {
+    if (!on) return;
+    if (used + 2 > ev.size())
+      {
+        const size_t old = ev.size();
+        ev.resize(old + 256);
+        for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]);
+      }
+    tag.push_back(t);
+    cudaEventRecord(ev[used++], st);
+  }
+  void end()
+  {
+    if (on) cudaEventRecord(ev[used++], st);
+  }
+  void resolve(double *sums, int *counts, int ntags)
+  {
+    for (int i = 0; i < ntags; ++i) sums[i] = 0, counts[i] = 0;
+    for (size_t k = 0; k < tag.size(); ++k)
+      {
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]);
+        sums[tag[k]] += ms;
+        counts[tag[k]]++;
+      }
+    used = 0;
+    tag.clear();
+  }
+  void release()
+  {
+    for (auto e : ev) cudaEventDestroy(e);
+    ev.clear();
+  }
+};
+enum { T_RHS = 0, T_PRECOND_SETUP, T_GMRES, T_ALPHA, T_GEMV, T_PRECOND_APPLY, T_ALLGATHER, T_NTAGS };
+
 struct wbem_ctx
 {
   wbem_params p;
+  EvTimer timer;
   std::string err;
   int dev = 0;
   cudaStream_t stream = nullptr;

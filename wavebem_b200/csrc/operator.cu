@@ -196,6 +196,7 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   double *yloc = ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk;
   if (ctx->nloc)
     {
+      ctx->timer.begin(T_GEMV);
       const uint32_t warps = (ctx->nloc + GEMV_RPW - 1) / GEMV_RPW;
       const uint32_t blocks = (warps + GEMV_WARPS - 1) / GEMV_WARPS;
       if (mode == 0)
@@ -209,9 +210,12 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
                                                       ctx->d_alpha, ctx->d_xdiag, -1.0, ctx->ld,
                                                       ctx->nloc, ctx->row0, yloc);
       ctx->launches++;
+      ctx->timer.end();
     }
   ctx->tm.gemv_bytes_last = 8.0 * 64.0 * (double)(n_o + n_s) * (double)ctx->nloc;
+  if (ctx->p.world_size > 1) ctx->timer.begin(T_ALLGATHER);
   int rc = wbem_allgather_rows(ctx, ctx->d_yloc);
+  if (ctx->p.world_size > 1) ctx->timer.end();
   if (rc) return rc;
   const bool shift = (mode == 0) && ctx->pure_neumann;
   if (shift)
