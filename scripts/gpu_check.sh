@@ -16,8 +16,8 @@ if [ "$MODE" != "quick" ]; then
   grep -E "ERROR SUMMARY|Invalid|out of bounds" $OUT/memcheck.log | head -5 | tee -a $OUT/summary.log
 fi
 echo "== pytest -m gpu" | tee -a $OUT/summary.log
-timeout 1500 python -m pytest tests -x -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.log
-tail -15 $OUT/pytest_gpu.log | tee -a $OUT/summary.log
+timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.log
+tail -40 $OUT/pytest_gpu.log | tee -a $OUT/summary.log
 echo "== bench" | tee -a $OUT/summary.log
 timeout 900 python bench.py > $OUT/bench.json 2> $OUT/bench.err; echo "bench rc=$?" | tee -a $OUT/summary.log
 cat $OUT/bench.json | tee -a $OUT/summary.log; tail -5 $OUT/bench.err | tee -a $OUT/summary.log

@@ -30,13 +30,20 @@ def wb():
     return wavebem_b200
 
 
-def rel_err_rowscaled(a, b):
-    """Parity metric of SURVEY 7/8c: |a-b| <= tol * max(|a|,|b|,row_scale), row_scale = max_j |b_ij|.
-    Returns max over entries of |a-b| / that scale (double-layer entries between coplanar
-    panels are analytically 0, so a purely relative error is meaningless there)."""
+def rel_err_rowscaled(a, b, diag=None):
+    """Parity metric for matrix entries (DESIGN.md "Parity metric"):
+        |a_ij - b_ij| / max(|a_ij|, |b_ij|, row_scale_i),   row_scale_i = max(max_j |b_ij|, |diag_i|).
+    Double-layer entries between coplanar panels are analytically 0, and the integrand
+    (R.n)/r^3 of near-coplanar neighbours carries an ABSOLUTE rounding floor ~1e-16..1e-14 in the
+    reference arithmetic itself, so a purely relative error is meaningless there.  For the
+    Neumann matrix the natural row scale is the operator row N + diag(alpha) that enters the
+    solve (pass diag=alpha, alpha_i >= 1/8); for the Dirichlet matrix it is max_j |D_ij|."""
     a = np.asarray(a)
     b = np.asarray(b)
-    scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), np.abs(b).max(axis=-1, keepdims=True))
+    row = np.abs(b).max(axis=-1, keepdims=True)
+    if diag is not None:
+        row = np.maximum(row, np.abs(np.asarray(diag)).reshape(row.shape))
+    scale = np.maximum(np.maximum(np.abs(a), np.abs(b)), row)
     scale = np.where(scale == 0, 1.0, scale)
     return float((np.abs(a - b) / scale).max())
 

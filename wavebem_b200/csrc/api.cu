@@ -140,6 +140,7 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_sing_ptr);
   FREE_DEV(ctx->d_sing_cellpos);
   FREE_DEV(ctx->d_sing_idx);
+  FREE_DEV(ctx->d_tile_sing);
   FREE_DEV(ctx->d_cl_cell_ptr);
   FREE_DEV(ctx->d_cl_slot_ptr);
   FREE_DEV(ctx->d_slot_col);
@@ -277,6 +278,15 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
       sing_ptr[r + 1] = (uint32_t)sing_pos.size();
     }
   ctx->n_sing = (uint32_t)sing_pos.size();
+  // byte map: does (row tile, cluster) hold any singular pair?  (k_assemble_tiled)
+  std::vector<uint32_t> cluster_of_pos(C);
+  for (uint32_t k = 0; k < pl.n_clusters; ++k)
+    for (uint32_t p = pl.cl_cell_ptr[k]; p < pl.cl_cell_ptr[k + 1]; ++p) cluster_of_pos[p] = k;
+  const uint32_t row_tiles = (ctx->nloc + WBEM_TILE_ROWS - 1) / WBEM_TILE_ROWS;
+  std::vector<uint8_t> tile_sing((size_t)std::max(1u, row_tiles) * std::max(1u, pl.n_clusters), 0);
+  for (uint32_t r = 0; r < ctx->nloc; ++r)
+    for (uint32_t k = sing_ptr[r]; k < sing_ptr[r + 1]; ++k)
+      tile_sing[(size_t)(r / WBEM_TILE_ROWS) * pl.n_clusters + cluster_of_pos[sing_pos[k]]] = 1;
 
   // uploads
   if ((rc = dev_upload(ctx, &ctx->d_cell_dofs, dofs_po))) return rc;
@@ -287,6 +297,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_upload(ctx, &ctx->d_sing_ptr, sing_ptr))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_sing_cellpos, sing_pos))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_sing_idx, sing_idx))) return rc;
+  if ((rc = dev_upload(ctx, &ctx->d_tile_sing, tile_sing))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_cl_cell_ptr, pl.cl_cell_ptr))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_cl_slot_ptr, pl.cl_slot_ptr))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_slot_col, pl.slot_col))) return rc;

@@ -198,7 +198,7 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // ---------------------------------------------------------------------------------------
 // Tiled regular-pair kernel, Gauss 4x4.
 // ---------------------------------------------------------------------------------------
-#define TILE_ROWS 256
+#define TILE_ROWS WBEM_TILE_ROWS
 #define TILE_W 48
 #define TILE_MAX_CELLS 36
 #define ACC_STRIDE (TILE_ROWS + 1)
@@ -210,8 +210,9 @@ struct TiledArgs
   const uint8_t *cell_slots; // [C][4]
   const uint32_t *cl_cell_ptr, *cl_slot_ptr, *slot_col, *color_clusters;
   const uint32_t *sing_ptr, *sing_cellpos; // CSR by local row
+  const uint8_t *tile_sing;                // [row tiles][clusters]: any singular pair inside?
   double *Nm, *Dm;
-  uint32_t ld, row0, nloc, cluster_base;
+  uint32_t ld, row0, nloc, cluster_base, n_clusters;
 };
 
 constexpr size_t tiled_smem_bytes()
@@ -251,16 +252,22 @@ __global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs
       bulk_copy_g2s(geo, a.geo + (size_t)p0 * 7 * 16, bytes, bar);
     }
   // singular cells of this row inside the cluster -> bit mask (they are integrated by
-  // k_assemble_singular only, reference :241/:261)
+  // k_assemble_singular only, reference :241/:261).  Most (row tile, cluster) pairs hold no
+  // singular pair at all: a host-built byte map lets them skip the list walk.
   unsigned long long smask = 0ull;
-  {
-    const uint32_t b = a.sing_ptr[lrow_c], e = a.sing_ptr[lrow_c + 1];
-    for (uint32_t k = b; k < e; ++k)
-      {
-        const uint32_t pos = a.sing_cellpos[k];
-        if (pos >= p0 && pos < p1) smask |= 1ull << (pos - p0);
-      }
-  }
+  if (a.tile_sing[(size_t)blockIdx.y * a.n_clusters + cluster])
+    {
+      const uint32_t b = a.sing_ptr[lrow_c], e = a.sing_ptr[lrow_c + 1];
+      for (uint32_t k = b; k < e; k += 4)
+        {
+          uint32_t pos[4];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) pos[i] = (k + i < e) ? a.sing_cellpos[k + i] : 0xffffffffu;
+#pragma unroll
+          for (int i = 0; i < 4; ++i)
+            if (pos[i] >= p0 && pos[i] < p1) smask |= 1ull << (pos[i] - p0);
+        }
+    }
   const double xi0 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 0];
   const double xi1 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 1];
   const double xi2 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 2];
@@ -345,27 +352,51 @@ __global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs
     }
   __syncthreads();
 
-  // flush: warp w handles rows w, w+8, ...; lanes run over the cluster's column slots
+  // flush: warp w owns rows [32w, 32w+32) of the tile; lanes run over the cluster's column
+  // slots (coalesced row segments); 8 rows are in flight per lane so that the read-modify-
+  // write of ADD columns has 16 independent loads outstanding instead of one.
   const int warp = tid >> 5, lane = tid & 31;
-  for (int r = warp; r < TILE_ROWS; r += TILE_ROWS / 32)
+  for (int rb = warp * 32; rb < warp * 32 + 32; rb += 8)
     {
-      const uint32_t row = lrow_base + r;
-      if (row >= a.nloc) break;
-      double *gN = a.Nm + (size_t)row * a.ld;
-      double *gD = a.Dm + (size_t)row * a.ld;
+      const uint32_t row_b = lrow_base + rb;
+      if (row_b >= a.nloc) break;
+      const int nr = min(8, (int)(a.nloc - row_b));
       for (int s = lane; s < nslot; s += 32)
         {
           const uint32_t cc = s_col[s];
           const uint32_t col = cc & 0x7fffffffu;
-          double vn = acc[s * ACC_STRIDE + r];
-          double vd = acc[(TILE_W + s) * ACC_STRIDE + r];
+          double vn[8], vd[8];
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            {
+              vn[i] = acc[s * ACC_STRIDE + rb + i];
+              vd[i] = acc[(TILE_W + s) * ACC_STRIDE + rb + i];
+            }
+          double *gN = a.Nm + (size_t)row_b * a.ld + col;
+          double *gD = a.Dm + (size_t)row_b * a.ld + col;
           if (cc >> 31)
             {
-              vn += gN[col];
-              vd += gD[col];
+              double on[8], od[8];
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                {
+                  on[i] = (i < nr) ? gN[(size_t)i * a.ld] : 0.0;
+                  od[i] = (i < nr) ? gD[(size_t)i * a.ld] : 0.0;
+                }
+#pragma unroll
+              for (int i = 0; i < 8; ++i)
+                {
+                  vn[i] += on[i];
+                  vd[i] += od[i];
+                }
             }
-          gN[col] = vn;
-          gD[col] = vd;
+#pragma unroll
+          for (int i = 0; i < 8; ++i)
+            if (i < nr)
+              {
+                gN[(size_t)i * a.ld] = vn[i];
+                gD[(size_t)i * a.ld] = vd[i];
+              }
         }
     }
 }
@@ -591,6 +622,8 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       a.color_clusters = ctx->d_color_clusters;
       a.sing_ptr = ctx->d_sing_ptr;
       a.sing_cellpos = ctx->d_sing_cellpos;
+      a.tile_sing = ctx->d_tile_sing;
+      a.n_clusters = pl.n_clusters;
       a.Nm = ctx->d_Nm;
       a.Dm = ctx->d_Dm;
       a.ld = ctx->ld;

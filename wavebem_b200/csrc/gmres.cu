@@ -357,8 +357,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   EvTimer &g_timer = ctx->timer;
   g_timer.st = st;
   g_timer.on = true;
-  g_timer.used = 0;
-  g_timer.tag.clear();
+  g_timer.reset();
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
   int rc;
   // alpha (compute_alpha, :833) -- a function of the assembled Neumann matrix only

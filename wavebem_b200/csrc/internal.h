@@ -9,6 +9,7 @@
 
 #define WBEM_MAX_NQ 64   // regular rule: up to 8 x 8
 #define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
+#define WBEM_TILE_ROWS 256 // rows per CTA of the tiled regular-pair kernel
 
 struct QuadTables
 { // host copies of the reference-cell tables (uploaded to __constant__ memory)
@@ -45,40 +46,58 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
                     uint32_t max_cells_per_cluster, AssemblyPlan *plan);
 
 struct EvTimer
-{ // accumulates device time of bracketed regions on one stream; resolved after a sync
+{ // accumulates device time of (possibly nested) bracketed regions on one stream
   std::vector<cudaEvent_t> ev;
-  std::vector<int> tag;
+  struct Region { int tag; size_t e0, e1; };
+  std::vector<Region> regions;
+  std::vector<size_t> open; // stack of region ids
   size_t used = 0;
   cudaStream_t st = nullptr;
   bool on = false;
-  void begin(int t)
+  size_t take()
   {
-    if (!on) return;
-    if (used + 2 > ev.size())
+    if (used + 1 > ev.size())
       {
         const size_t old = ev.size();
         ev.resize(old + 256);
         for (size_t i = old; i < ev.size(); ++i) cudaEventCreate(&ev[i]);
       }
-    tag.push_back(t);
-    cudaEventRecord(ev[used++], st);
+    return used++;
+  }
+  void begin(int t)
+  {
+    if (!on) return;
+    const size_t e = take();
+    regions.push_back({t, e, e});
+    open.push_back(regions.size() - 1);
+    cudaEventRecord(ev[e], st);
   }
   void end()
   {
-    if (on) cudaEventRecord(ev[used++], st);
+    if (!on || open.empty()) return;
+    const size_t e = take();
+    regions[open.back()].e1 = e;
+    open.pop_back();
+    cudaEventRecord(ev[e], st);
+  }
+  void reset()
+  {
+    used = 0;
+    regions.clear();
+    open.clear();
   }
   void resolve(double *sums, int *counts, int ntags)
   {
     for (int i = 0; i < ntags; ++i) sums[i] = 0, counts[i] = 0;
-    for (size_t k = 0; k < tag.size(); ++k)
+    for (const Region &r : regions)
       {
+        if (r.e1 == r.e0) continue;
         float ms = 0;
-        cudaEventElapsedTime(&ms, ev[2 * k], ev[2 * k + 1]);
-        sums[tag[k]] += ms;
-        counts[tag[k]]++;
+        cudaEventElapsedTime(&ms, ev[r.e0], ev[r.e1]);
+        sums[r.tag] += ms;
+        counts[r.tag]++;
       }
-    used = 0;
-    tag.clear();
+    reset();
   }
   void release()
   {
@@ -115,6 +134,7 @@ struct wbem_ctx
   // singular pairs of the local rows: CSR by local row
   uint32_t *d_sing_ptr = nullptr, *d_sing_cellpos = nullptr; // cell processing position, sorted
   uint8_t *d_sing_idx = nullptr;
+  uint8_t *d_tile_sing = nullptr; // [row tiles][clusters]
   uint32_t n_sing = 0;
   // plan on device
   uint32_t *d_cl_cell_ptr = nullptr, *d_cl_slot_ptr = nullptr, *d_slot_col = nullptr,

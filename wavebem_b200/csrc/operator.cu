@@ -14,8 +14,8 @@
 
 #include "internal.h"
 
-#define GEMV_RPW 4     // rows per warp
 #define GEMV_WARPS 8   // warps per CTA
+#define GEMV_MAXR 5    // rows one warp streams in one pass
 
 __device__ __forceinline__ double2 ld_stream(const double *p)
 {
@@ -24,26 +24,30 @@ __device__ __forceinline__ double2 ld_stream(const double *p)
   return r;
 }
 
+// acc[r] += sum over the listed 64-column chunks of M[row0+r, :] . x   (NR rows per pass:
+// the x chunk is loaded once and reused for NR streamed 128-bit matrix loads per lane; two
+// chunks are in flight per iteration)
+template <int NR>
 __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const double *__restrict__ x,
                                           const uint32_t *__restrict__ list, int n, uint32_t ld,
-                                          const uint32_t rows[GEMV_RPW], int lane,
-                                          double acc[GEMV_RPW])
+                                          uint32_t row0, int lane, double acc[GEMV_MAXR])
 {
+  const double *base = M + (size_t)row0 * ld + lane * 2;
   int i = 0;
   for (; i + 1 < n; i += 2)
     {
-      const uint32_t c0 = list[i] * 64 + lane * 2, c1 = list[i + 1] * 64 + lane * 2;
-      double2 m0[GEMV_RPW], m1[GEMV_RPW];
+      const uint32_t c0 = list[i] * 64, c1 = list[i + 1] * 64;
+      double2 m0[NR], m1[NR];
 #pragma unroll
-      for (int r = 0; r < GEMV_RPW; ++r)
+      for (int r = 0; r < NR; ++r)
         {
-          m0[r] = ld_stream(M + (size_t)rows[r] * ld + c0);
-          m1[r] = ld_stream(M + (size_t)rows[r] * ld + c1);
+          m0[r] = ld_stream(base + (size_t)r * ld + c0);
+          m1[r] = ld_stream(base + (size_t)r * ld + c1);
         }
-      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0);
-      const double2 x1 = *reinterpret_cast<const double2 *>(x + c1);
+      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0 + lane * 2);
+      const double2 x1 = *reinterpret_cast<const double2 *>(x + c1 + lane * 2);
 #pragma unroll
-      for (int r = 0; r < GEMV_RPW; ++r)
+      for (int r = 0; r < NR; ++r)
         {
           acc[r] = fma(m0[r].x, x0.x, acc[r]);
           acc[r] = fma(m0[r].y, x0.y, acc[r]);
@@ -53,49 +57,76 @@ __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const do
     }
   if (i < n)
     {
-      const uint32_t c0 = list[i] * 64 + lane * 2;
-      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0);
+      const uint32_t c0 = list[i] * 64;
+      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0 + lane * 2);
 #pragma unroll
-      for (int r = 0; r < GEMV_RPW; ++r)
+      for (int r = 0; r < NR; ++r)
         {
-          const double2 m0 = ld_stream(M + (size_t)rows[r] * ld + c0);
+          const double2 m0 = ld_stream(base + (size_t)r * ld + c0);
           acc[r] = fma(m0.x, x0.x, acc[r]);
           acc[r] = fma(m0.y, x0.y, acc[r]);
         }
     }
 }
 
-// y[r] = s1 * (M1[r,:] . x1) + s2 * (M2[r,:] . x2) + sdiag * alpha[row0+r] * xdiag[row0+r]
-__global__ void __launch_bounds__(GEMV_WARPS * 32)
-  k_bem_gemv(const double *__restrict__ M1, const double *__restrict__ x1,
-             const uint32_t *__restrict__ list1, int n1, double s1, const double *__restrict__ M2,
-             const double *__restrict__ x2, const uint32_t *__restrict__ list2, int n2, double s2,
-             const double *__restrict__ alpha, const double *__restrict__ xdiag, double sdiag,
-             uint32_t ld, uint32_t nloc, uint32_t row0, double *__restrict__ y)
+struct GemvArgs
 {
-  const int lane = threadIdx.x & 31;
-  const uint32_t w = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
-  const uint32_t r0 = w * GEMV_RPW;
-  if (r0 >= nloc) return;
-  uint32_t rows[GEMV_RPW];
+  const double *M1, *x1, *M2, *x2, *alpha, *xdiag;
+  const uint32_t *list1, *list2;
+  int n1, n2;
+  double s1, s2, sdiag;
+  uint32_t ld, nloc, row0;
+  double *y;
+};
+
+template <int NR>
+__device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int lane)
+{
+  double a1[GEMV_MAXR], a2[GEMV_MAXR];
 #pragma unroll
-  for (int r = 0; r < GEMV_RPW; ++r) rows[r] = min(r0 + r, nloc - 1);
-  double a1[GEMV_RPW], a2[GEMV_RPW];
+  for (int r = 0; r < GEMV_MAXR; ++r) a1[r] = a2[r] = 0.0;
+  gemv_pass<NR>(a.M1, a.x1, a.list1, a.n1, a.ld, r0, lane, a1);
+  gemv_pass<NR>(a.M2, a.x2, a.list2, a.n2, a.ld, r0, lane, a2);
 #pragma unroll
-  for (int r = 0; r < GEMV_RPW; ++r) a1[r] = a2[r] = 0.0;
-  gemv_pass(M1, x1, list1, n1, ld, rows, lane, a1);
-  gemv_pass(M2, x2, list2, n2, ld, rows, lane, a2);
-#pragma unroll
-  for (int r = 0; r < GEMV_RPW; ++r)
+  for (int r = 0; r < NR; ++r)
     {
-      double v = s1 * a1[r] + s2 * a2[r];
+      double v = a.s1 * a1[r] + a.s2 * a2[r];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0 && r0 + r < nloc)
+      if (lane == 0)
         {
-          const uint32_t g = row0 + r0 + r;
-          y[r0 + r] = v + sdiag * alpha[g] * xdiag[g];
+          const uint32_t g = a.row0 + r0 + r;
+          a.y[r0 + r] = v + a.sdiag * a.alpha[g] * a.xdiag[g];
         }
+    }
+}
+
+// y[r] = s1 * (M1[r,:] . x1) + s2 * (M2[r,:] . x2) + sdiag * alpha[row0+r] * xdiag[row0+r]
+// One resident wave of CTAs (grid = SMs x occupancy); the rows are split evenly over CTAs and
+// then over the warps of a CTA, so every SM streams the same number of bytes (no tail wave).
+__global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
+{
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t G = gridDim.x, c = blockIdx.x;
+  const uint32_t cr0 = (uint32_t)((uint64_t)a.nloc * c / G), cr1 = (uint32_t)((uint64_t)a.nloc * (c + 1) / G);
+  const uint32_t nr = cr1 - cr0;
+  uint32_t r0 = cr0 + nr * warp / GEMV_WARPS;
+  const uint32_t r1 = cr0 + nr * (warp + 1) / GEMV_WARPS;
+  while (r0 < r1)
+    {
+      const uint32_t left = r1 - r0;
+      // passes of at most GEMV_MAXR rows, split evenly (e.g. 6 -> 3 + 3, 9 -> 5 + 4)
+      const uint32_t passes = (left + GEMV_MAXR - 1) / GEMV_MAXR;
+      const uint32_t take = (left + passes - 1) / passes;
+      switch (take)
+        {
+        case 1: gemv_rows<1>(a, r0, lane); break;
+        case 2: gemv_rows<2>(a, r0, lane); break;
+        case 3: gemv_rows<3>(a, r0, lane); break;
+        case 4: gemv_rows<4>(a, r0, lane); break;
+        default: gemv_rows<5>(a, r0, lane); break;
+        }
+      r0 += take;
     }
 }
 
@@ -197,18 +228,40 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   if (ctx->nloc)
     {
       ctx->timer.begin(T_GEMV);
-      const uint32_t warps = (ctx->nloc + GEMV_RPW - 1) / GEMV_RPW;
-      const uint32_t blocks = (warps + GEMV_WARPS - 1) / GEMV_WARPS;
+      static int ctas_per_sm = 0, n_sm = 0;
+      if (!ctas_per_sm)
+        {
+          CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_bem_gemv, GEMV_WARPS * 32, 0));
+          CUDA_OK(ctx, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->dev));
+          if (ctas_per_sm < 1) ctas_per_sm = 1;
+        }
+      GemvArgs ga;
+      ga.M1 = ctx->d_Nm;
+      ga.x1 = ctx->d_xn;
+      ga.M2 = ctx->d_Dm;
+      ga.x2 = ctx->d_xd;
+      ga.alpha = ctx->d_alpha;
+      ga.xdiag = ctx->d_xdiag;
+      ga.ld = ctx->ld;
+      ga.nloc = ctx->nloc;
+      ga.row0 = ctx->row0;
+      ga.y = yloc;
       if (mode == 0)
-        k_bem_gemv<<<blocks, GEMV_WARPS * 32, 0, st>>>(ctx->d_Nm, ctx->d_xn, list_o, n_o, 1.0,
-                                                      ctx->d_Dm, ctx->d_xd, list_s, n_s, -1.0,
-                                                      ctx->d_alpha, ctx->d_xdiag, 1.0, ctx->ld,
-                                                      ctx->nloc, ctx->row0, yloc);
+        {
+          ga.list1 = list_o; ga.n1 = n_o; ga.s1 = 1.0;
+          ga.list2 = list_s; ga.n2 = n_s; ga.s2 = -1.0;
+          ga.sdiag = 1.0;
+        }
       else
-        k_bem_gemv<<<blocks, GEMV_WARPS * 32, 0, st>>>(ctx->d_Nm, ctx->d_xn, list_s, n_s, -1.0,
-                                                      ctx->d_Dm, ctx->d_xd, list_o, n_o, 1.0,
-                                                      ctx->d_alpha, ctx->d_xdiag, -1.0, ctx->ld,
-                                                      ctx->nloc, ctx->row0, yloc);
+        {
+          ga.list1 = list_s; ga.n1 = n_s; ga.s1 = -1.0;
+          ga.list2 = list_o; ga.n2 = n_o; ga.s2 = 1.0;
+          ga.sdiag = -1.0;
+        }
+      uint32_t grid = (uint32_t)(n_sm * ctas_per_sm);
+      const uint32_t max_useful = (ctx->nloc + GEMV_WARPS - 1) / GEMV_WARPS; // >= 1 row per warp
+      if (grid > max_useful) grid = max_useful;
+      k_bem_gemv<<<grid, GEMV_WARPS * 32, 0, st>>>(ga);
       ctx->launches++;
       ctx->timer.end();
     }

@@ -1,36 +1,54 @@
 // precond.cu -- device-resident form of the reference's band preconditioner.
 //
-// The reference factorises band_system (|row - col| < 50 band of the merged operator,
-// source/bem_problem.cc:1107-1149) with UMFPACK on the host and does two sparse triangular
-// solves per GMRES iteration.  Here the same band matrix is viewed as BLOCK TRIDIAGONAL with
-// 64 x 64 blocks (band/2 <= 64, so all entries fall in adjacent blocks) and factorised by
-// the block Thomas algorithm on the device:
+// The reference factorises band_system (the |row - col| < 50 band of the merged operator,
+// source/bem_problem.cc:1107-1149) with UMFPACK on the host and runs two sequential sparse
+// triangular solves per GMRES iteration.  Here the same band matrix is viewed as BLOCK
+// TRIDIAGONAL with 64 x 64 blocks (band/2 <= 64, so every entry falls in adjacent blocks;
+// the tail is padded with an identity) and solved by BLOCK CYCLIC REDUCTION:
 //
-//     S_0 = A_0,   L_k = B_{k-1} S_{k-1}^{-1},   S_k = A_k - L_k C_{k-1},   U_k = S_k^{-1} C_k
-//     forward   y_k = b_k - L_k y_{k-1}
-//     diagonal  z_k = S_k^{-1} y_k                     (independent blocks: K CTAs)
-//     backward  x_k = z_k - U_k x_{k+1}
-//
-// (A = diagonal, B = sub-, C = super-diagonal blocks).  Diagonal blocks are inverted by
-// Gauss-Jordan with partial pivoting inside the block.  M^{-1} v is the same vector as the
-// reference's LU solve up to rounding.  The two sequential sweeps run in one CTA that streams
-// the 32 KB blocks through a 3-stage ring of TMA bulk copies.
+//   level l, active positions 0..n-1 (original block index = position << l):
+//     eliminate the odd positions p:   x_p = D_p^-1 (b_p - L_p x_{p-1} - U_p x_{p+1})
+//     kept (even) positions q:         P-_q = L_q D_{q-1}^-1,  P+_q = U_q D_{q+1}^-1
+//                                      D'_q = D_q - P-_q U_{q-1} - P+_q L_{q+1}
+//                                      L'_q = -P-_q L_{q-1},   U'_q = -P+_q U_{q+1}
+//                                      b'_q = b_q - P-_q b_{q-1} - P+_q b_{q+1}
+//   until one block is left.  log2(K) levels, every level fully parallel over blocks: the
+//   factorisation is ~9 rounds of independent 64x64 inversions/GEMMs instead of a chain of K
+//   of them, and one application of M^-1 streams ~5 K blocks once (HBM-bound) instead of
+//   walking a K-long dependency chain.  Diagonal blocks are inverted by Gauss-Jordan with
+//   partial (row) pivoting inside the block.  M^-1 v equals the reference's LU solve up to
+//   rounding (checked against the oracle's pivoted band LU in tests/test_gpu_parity.py).
 #include <cstdio>
+#include <vector>
 
 #include "internal.h"
 
-#define BS 64           // block size
+#define BS 64
 #define BS2 (BS * BS)
-#define LDS_ (BS + 1)   // padded shared-memory leading dimension
+#define LDP (BS + 1) // padded shared-memory leading dimension
+
+struct BcrLevel
+{
+  uint32_t n, n_elim, n_kept;
+  size_t off_dinvT, off_lT, off_uT; // [n_elim] blocks each (column-major = transposed)
+  size_t off_pmT, off_ppT;          // [n_kept] blocks each
+};
 
 struct DevPrecond
 {
   uint32_t K = 0;
-  double *SinvT = nullptr, *Lt = nullptr, *Ut = nullptr; // [K][64*64], column-major blocks
-  double *work = nullptr;                                // [K*64]
+  std::vector<BcrLevel> lev;
+  double *pool = nullptr;     // saved blocks of every level + the last inverse
+  size_t off_last = 0, pool_blocks = 0;
+  double *Lw[2] = {nullptr, nullptr}, *Dw[2] = {nullptr, nullptr}, *Uw[2] = {nullptr, nullptr};
+  double *dinv_rm = nullptr;  // [K/2] row-major inverses of the level being processed
+  double *work = nullptr;     // [K*64] right-hand side / solution, indexed by original block
   int *info = nullptr;
 };
 
+// ---------------------------------------------------------------------------------------
+// helpers
+// ---------------------------------------------------------------------------------------
 __device__ __forceinline__ double band_entry(const double *__restrict__ bandm, uint32_t N, int band,
                                              long r, long i)
 {
@@ -39,32 +57,59 @@ __device__ __forceinline__ double band_entry(const double *__restrict__ bandm, u
   return (k >= 0 && k < band) ? bandm[(size_t)r * band + k] : 0.0;
 }
 
-__device__ void load_block(double *dst, const double *__restrict__ bandm, uint32_t N, int band,
-                           uint32_t bi, uint32_t bj)
+// band rows -> explicit block arrays (row-major 64x64): L = block(k,k-1), D, U = block(k,k+1)
+__global__ void __launch_bounds__(256)
+  k_band_to_blocks(uint32_t N, uint32_t K, int band, const double *__restrict__ bandm,
+                   double *__restrict__ L, double *__restrict__ D, double *__restrict__ U)
 {
+  const uint32_t k = blockIdx.x;
+  const int which = blockIdx.y; // 0 L, 1 D, 2 U
+  double *dst = (which == 0 ? L : which == 1 ? D : U) + (size_t)k * BS2;
+  const long cb = (long)k + which - 1;
   for (int idx = threadIdx.x; idx < BS2; idx += blockDim.x)
     {
       const int a = idx / BS, b = idx % BS;
-      dst[a * LDS_ + b] = band_entry(bandm, N, band, (long)bi * BS + a, (long)bj * BS + b);
+      double v = 0.0;
+      if (cb >= 0 && cb < (long)K) v = band_entry(bandm, N, band, (long)k * BS + a, cb * BS + b);
+      dst[idx] = v;
     }
 }
 
-// C = A * B (64x64, padded smem), optionally C = D - A*B.  256 threads, 4x4 per thread.
-__device__ void gemm64(double *C, const double *A, const double *B, const double *D)
+__device__ __forceinline__ void tile_load(double *t, const double *__restrict__ g)
+{ // global row-major 64x64 -> padded smem
+  for (int idx = threadIdx.x; idx < BS2; idx += blockDim.x) t[(idx >> 6) * LDP + (idx & 63)] = g[idx];
+}
+__device__ __forceinline__ void tile_store(double *__restrict__ g, const double *t)
 {
-  const int ty = threadIdx.x / 16, tx = threadIdx.x % 16;
+  for (int idx = threadIdx.x; idx < BS2; idx += blockDim.x) g[idx] = t[(idx >> 6) * LDP + (idx & 63)];
+}
+__device__ __forceinline__ void tile_store_T(double *__restrict__ g, const double *t)
+{ // g[b*64 + a] = t[a][b]
+  for (int idx = threadIdx.x; idx < BS2; idx += blockDim.x) g[idx] = t[(idx & 63) * LDP + (idx >> 6)];
+}
+__device__ __forceinline__ void tile_zero_store(double *__restrict__ g)
+{
+  for (int idx = threadIdx.x; idx < BS2; idx += blockDim.x) g[idx] = 0.0;
+}
+
+// C = sign * A * B  (+ D if D != nullptr), all padded smem tiles; 256 threads; thread (ty,tx)
+// owns rows 4ty..4ty+3 and columns tx, tx+16, tx+32, tx+48 (conflict-free smem reads).
+__device__ void gemm64(double *C, const double *A, const double *B, const double *D, double sign)
+{
+  const int ty = threadIdx.x >> 4, tx = threadIdx.x & 15;
   double acc[4][4];
 #pragma unroll
   for (int i = 0; i < 4; ++i)
 #pragma unroll
     for (int j = 0; j < 4; ++j) acc[i][j] = 0.0;
+#pragma unroll 4
   for (int kk = 0; kk < BS; ++kk)
     {
       double a[4], b[4];
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = A[(4 * ty + i) * LDS_ + kk];
+      for (int i = 0; i < 4; ++i) a[i] = A[(4 * ty + i) * LDP + kk];
 #pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = B[kk * LDS_ + 4 * tx + j];
+      for (int j = 0; j < 4; ++j) b[j] = B[kk * LDP + tx + 16 * j];
 #pragma unroll
       for (int i = 0; i < 4; ++i)
 #pragma unroll
@@ -75,268 +120,281 @@ __device__ void gemm64(double *C, const double *A, const double *B, const double
 #pragma unroll
     for (int j = 0; j < 4; ++j)
       {
-        const int o = (4 * ty + i) * LDS_ + 4 * tx + j;
-        C[o] = D ? D[o] - acc[i][j] : acc[i][j];
+        const int o = (4 * ty + i) * LDP + tx + 16 * j;
+        const double v = sign * acc[i][j];
+        C[o] = D ? D[o] + v : v;
       }
 }
 
-// in-place inverse of the 64x64 matrix S (padded smem) by Gauss-Jordan with partial pivoting
-__device__ void invert64(double *S, int *piv, int *info, int blk)
+// In-place Gauss-Jordan inverse with implicit partial pivoting.  256 threads; thread t keeps
+// the 16 entries S[r][16q .. 16q+15] (r = t >> 2, q = t & 3) in registers for all 64 steps.
+// Step c: the not-yet-used row with the largest |S[.][c]| becomes the pivot row; no rows are
+// swapped -- the permutation is undone when the result is written:
+//     inverse[col_of_row[r]][row_of_col[j]] = S[r][j].
+__device__ void invert64(const double *Sin, double *Sout, int *info, int tag)
 {
-  __shared__ int s_p;
-  __shared__ double s_pivinv;
-  const int tid = threadIdx.x;
+  __shared__ double colbuf[2][BS];
+  __shared__ double prow[2][BS];
+  __shared__ int row_of_col[BS];
+  const int t = threadIdx.x, lane = t & 31;
+  const int r = t >> 2, q = t & 3;
+  double a[16];
+#pragma unroll
+  for (int j = 0; j < 16; ++j) a[j] = Sin[r * LDP + 16 * q + j];
+  bool used = false;
+  int my_col = 0;
+#pragma unroll
   for (int c = 0; c < BS; ++c)
     {
-      if (tid < 32)
-        { // arg-max |S[r][c]|, r >= c
-          double best = -1.0;
-          int bi = c;
-          for (int r = c + tid; r < BS; r += 32)
-            {
-              const double v = fabs(S[r * LDS_ + c]);
-              if (v > best)
-                {
-                  best = v;
-                  bi = r;
-                }
-            }
-#pragma unroll
-          for (int off = 16; off > 0; off >>= 1)
-            {
-              const double ob = __shfl_xor_sync(0xffffffffu, best, off);
-              const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
-              if (ob > best || (ob == best && oi < bi))
-                {
-                  best = ob;
-                  bi = oi;
-                }
-            }
-          if (tid == 0)
-            {
-              s_p = bi;
-              piv[c] = bi;
-              if (best == 0.0) atomicExch(info, blk * BS + c + 1);
-            }
-        }
+      const int buf = c & 1;
+      const double acol = a[c & 15];
+      if (q == (c >> 4)) colbuf[buf][r] = used ? -1.0 : fabs(acol);
       __syncthreads();
-      const int p = s_p;
-      if (p != c && tid < BS)
-        {
-          const double t = S[c * LDS_ + tid];
-          S[c * LDS_ + tid] = S[p * LDS_ + tid];
-          S[p * LDS_ + tid] = t;
-        }
-      __syncthreads();
-      if (tid == 0)
-        {
-          s_pivinv = 1.0 / S[c * LDS_ + c];
-          S[c * LDS_ + c] = 1.0;
-        }
-      __syncthreads();
-      if (tid < BS) S[c * LDS_ + tid] *= s_pivinv;
-      __syncthreads();
-      // eliminate column c from every other row: thread -> (row r = tid/4 + 64*?..)
+      // every warp finds the pivot row redundantly (no second barrier needed)
+      double best = colbuf[buf][lane];
+      int bi = lane;
       {
-        const int r = tid >> 2, q = tid & 3; // 64 rows x 4 column quarters
-        double f = 0.0;
-        if (r != c) f = S[r * LDS_ + c];
-        __syncthreads();
-        if (r != c)
+        const double v1 = colbuf[buf][lane + 32];
+        if (v1 > best)
           {
-            if (q == 0) S[r * LDS_ + c] = 0.0;
+            best = v1;
+            bi = lane + 32;
           }
-        __syncthreads();
-        if (r != c && f != 0.0)
-          for (int j = q * 16; j < q * 16 + 16; ++j) S[r * LDS_ + j] = fma(-f, S[c * LDS_ + j], S[r * LDS_ + j]);
-        __syncthreads();
       }
-    }
-  // undo the row interchanges: columns of the inverse, in reverse order
-  for (int c = BS - 1; c >= 0; --c)
-    {
-      const int p = piv[c];
-      if (p != c && tid < BS)
+#pragma unroll
+      for (int off = 16; off > 0; off >>= 1)
         {
-          const double t = S[tid * LDS_ + c];
-          S[tid * LDS_ + c] = S[tid * LDS_ + p];
-          S[tid * LDS_ + p] = t;
+          const double ob = __shfl_xor_sync(0xffffffffu, best, off);
+          const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+          if (ob > best || (ob == best && oi < bi))
+            {
+              best = ob;
+              bi = oi;
+            }
+        }
+      const int p = bi;
+      if (t == 0)
+        {
+          row_of_col[c] = p;
+          if (!(best > 0.0)) atomicExch(info, tag * BS + c + 1);
+        }
+      // multiplier of my row: S[r][c], held by the lane of my 4-lane group with q == c >> 4
+      const double f = __shfl_sync(0xffffffffu, acol, (lane & ~3) | (c >> 4));
+      if (r == p)
+        {
+          const double pivinv = 1.0 / f;
+          if (q == (c >> 4)) a[c & 15] = 1.0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j)
+            {
+              a[j] *= pivinv;
+              prow[buf][16 * q + j] = a[j];
+            }
+          used = true;
+          my_col = c;
         }
       __syncthreads();
+      if (r != p)
+        {
+          if (q == (c >> 4)) a[c & 15] = 0.0;
+#pragma unroll
+          for (int j = 0; j < 16; ++j) a[j] = fma(-f, prow[buf][16 * q + j], a[j]);
+        }
     }
+  __syncthreads();
+#pragma unroll
+  for (int j = 0; j < 16; ++j) Sout[my_col * LDP + row_of_col[16 * q + j]] = a[j];
+  __syncthreads();
 }
 
-// store a padded smem block to global, transposed (column-major): out[b*64 + a] = M[a][b]
-__device__ void store_block_T(double *__restrict__ out, const double *M)
-{
-  for (int idx = threadIdx.x; idx < BS2; idx += blockDim.x)
-    {
-      const int b = idx / BS, a = idx % BS;
-      out[idx] = M[a * LDS_ + b];
-    }
-}
-
+// ---------------------------------------------------------------------------------------
+// factorisation kernels (one level)
+// ---------------------------------------------------------------------------------------
+// eliminated position p = 2m+1: Dinv = D_p^-1 -> dinv_rm[m] (row-major, for k_bcr_update) and
+// DinvT (saved); L_p, U_p saved transposed.
 __global__ void __launch_bounds__(256, 1)
-  k_bt_factor(uint32_t N, uint32_t K, int band, const double *__restrict__ bandm,
-              double *__restrict__ SinvT, double *__restrict__ Lt, double *__restrict__ Ut, int *info)
+  k_bcr_invert(uint32_t n_elim, const double *__restrict__ Lw, const double *__restrict__ Dw,
+               const double *__restrict__ Uw, double *__restrict__ dinv_rm, double *__restrict__ dinvT,
+               double *__restrict__ lT, double *__restrict__ uT, int *info, int tag_base, int single)
 {
   extern __shared__ double sm[];
-  double *S = sm, *Bm = S + BS * LDS_, *Cm = Bm + BS * LDS_, *W = Cm + BS * LDS_;
-  __shared__ int piv[BS];
-  load_block(S, bandm, N, band, 0, 0);
+  double *S = sm, *R = sm + BS * LDP;
+  const uint32_t m = blockIdx.x;
+  const uint32_t p = single ? 0 : 2 * m + 1;
+  tile_load(S, Dw + (size_t)p * BS2);
   __syncthreads();
-  for (uint32_t k = 0; k < K; ++k)
+  invert64(S, R, info, tag_base + (int)m);
+  tile_store_T(dinvT + (size_t)m * BS2, R);
+  if (!single)
     {
-      invert64(S, piv, info, (int)k);
-      store_block_T(SinvT + (size_t)k * BS2, S);
-      if (k + 1 < K)
-        {
-          load_block(Bm, bandm, N, band, k + 1, k);
-          load_block(Cm, bandm, N, band, k, k + 1);
-          __syncthreads();
-          gemm64(W, S, Cm, nullptr); // U_k = S_k^{-1} C_k
-          __syncthreads();
-          store_block_T(Ut + (size_t)k * BS2, W);
-          __syncthreads();
-          gemm64(W, Bm, S, nullptr); // L_{k+1} = B_k S_k^{-1}
-          __syncthreads();
-          store_block_T(Lt + (size_t)(k + 1) * BS2, W);
-          load_block(Bm, bandm, N, band, k + 1, k + 1); // A_{k+1} (Bm is free: W holds L)
-          __syncthreads();
-          gemm64(S, W, Cm, Bm); // S_{k+1} = A_{k+1} - L_{k+1} C_k
-          __syncthreads();
-        }
+      tile_store(dinv_rm + (size_t)m * BS2, R);
+      __syncthreads();
+      tile_load(S, Lw + (size_t)p * BS2);
+      __syncthreads();
+      tile_store_T(lT + (size_t)m * BS2, S);
+      __syncthreads();
+      tile_load(S, Uw + (size_t)p * BS2);
+      __syncthreads();
+      tile_store_T(uT + (size_t)m * BS2, S);
     }
 }
 
-// ---- sequential sweeps --------------------------------------------------------------------
-__device__ __forceinline__ uint32_t p_smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
-__device__ __forceinline__ void p_mbar_init(uint64_t *bar, uint32_t count)
-{
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(p_smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void p_mbar_expect_tx(uint64_t *bar, uint32_t bytes)
-{
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(p_smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void p_bulk_g2s(void *dst, const void *src, uint32_t bytes, uint64_t *bar)
-{
-  asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
-                 p_smem_u32(dst)),
-               "l"(src), "r"(bytes), "r"(p_smem_u32(bar))
-               : "memory");
-}
-__device__ __forceinline__ void p_mbar_wait(uint64_t *bar, uint32_t parity)
-{
-  uint32_t done;
-  do
-    {
-      asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
-                   "selp.u32 %0, 1, 0, p;\n\t}"
-                   : "=r"(done)
-                   : "r"(p_smem_u32(bar)), "r"(parity)
-                   : "memory");
-    }
-  while (!done);
-}
-
-#define NSTAGE 3
-// forward (dir = +1):  v_0 = w_0,       v_k = w_k - M_k v_{k-1},  k = 1..K-1,   M = Lt
-// backward (dir = -1): v_{K-1}=w_{K-1}, v_k = w_k - M_k v_{k+1},  k = K-2..0,   M = Ut
-// Mt blocks are column-major: Mt[j*64 + r] = M[r][j].  w may alias v.
+// kept position q = 2t -> position t of the next level
 __global__ void __launch_bounds__(256, 1)
-  k_bt_sweep(uint32_t N, uint32_t K, int dir, const double *__restrict__ Mt, const double *w, double *v)
+  k_bcr_update(uint32_t n, const double *__restrict__ Lw, const double *__restrict__ Dw,
+               const double *__restrict__ Uw, const double *__restrict__ dinv_rm,
+               double *__restrict__ Ln, double *__restrict__ Dn, double *__restrict__ Un,
+               double *__restrict__ pmT, double *__restrict__ ppT)
 {
-  extern __shared__ __align__(128) double sm[];
-  double *buf = sm;                                   // [NSTAGE][4096]
-  double *vprev = buf + NSTAGE * BS2;                 // [2][64]
-  double *part = vprev + 2 * BS;                      // [4][64]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(part + 4 * BS); // [NSTAGE]
-  const int tid = threadIdx.x;
-  const uint32_t nsteps = K - 1;
-  auto blk_of = [&](uint32_t s) -> uint32_t { return dir > 0 ? s + 1 : K - 2 - s; };
-  if (tid == 0)
+  extern __shared__ double sm[];
+  double *Dt = sm, *X = Dt + BS * LDP, *Y = X + BS * LDP, *Z = Y + BS * LDP;
+  const uint32_t t = blockIdx.x, q = 2 * t;
+  tile_load(Dt, Dw + (size_t)q * BS2);
+  if (q >= 1)
     {
-      for (int s = 0; s < NSTAGE; ++s) p_mbar_init(&bar[s], 1);
-      asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
-    }
-  __syncthreads();
-  if (tid == 0)
-    for (uint32_t s = 0; s < NSTAGE && s < nsteps; ++s)
-      {
-        p_mbar_expect_tx(&bar[s], BS2 * sizeof(double));
-        p_bulk_g2s(buf + s * BS2, Mt + (size_t)blk_of(s) * BS2, BS2 * sizeof(double), &bar[s]);
-      }
-  // first block: copy through
-  {
-    const uint32_t k0 = dir > 0 ? 0 : K - 1;
-    if (tid < BS)
-      {
-        const size_t g = (size_t)k0 * BS + tid;
-        const double x = g < N ? w[g] : 0.0;
-        if (g < N) v[g] = x;
-        vprev[tid] = x;
-      }
-  }
-  __syncthreads();
-  const int g4 = tid >> 6, r = tid & 63;
-  for (uint32_t s = 0; s < nsteps; ++s)
-    {
-      const int stage = s % NSTAGE;
-      const uint32_t k = blk_of(s);
-      p_mbar_wait(&bar[stage], (s / NSTAGE) & 1);
-      const double *M = buf + stage * BS2;
-      const double *vp = vprev + (s & 1) * BS;
-      double a0 = 0, a1 = 0;
-#pragma unroll
-      for (int j = 0; j < 16; j += 2)
-        {
-          a0 = fma(M[(16 * g4 + j) * BS + r], vp[16 * g4 + j], a0);
-          a1 = fma(M[(16 * g4 + j + 1) * BS + r], vp[16 * g4 + j + 1], a1);
-        }
-      part[g4 * BS + r] = a0 + a1;
+      tile_load(X, Lw + (size_t)q * BS2);
+      tile_load(Y, dinv_rm + (size_t)(t - 1) * BS2);
       __syncthreads();
-      if (tid < BS)
-        {
-          const size_t g = (size_t)k * BS + tid;
-          const double x = (g < N ? w[g] : 0.0) - ((part[tid] + part[BS + tid]) + (part[2 * BS + tid] + part[3 * BS + tid]));
-          if (g < N) v[g] = x;
-          vprev[((s + 1) & 1) * BS + tid] = x;
-        }
-      // this stage's buffer is free for step s + NSTAGE (all threads passed the barrier above)
-      if (tid == 0 && s + NSTAGE < nsteps)
-        {
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          p_mbar_expect_tx(&bar[stage], BS2 * sizeof(double));
-          p_bulk_g2s(buf + stage * BS2, Mt + (size_t)blk_of(s + NSTAGE) * BS2, BS2 * sizeof(double), &bar[stage]);
-        }
+      gemm64(Z, X, Y, nullptr, 1.0); // P- = L_q Dinv_{q-1}
+      __syncthreads();
+      tile_store_T(pmT + (size_t)t * BS2, Z);
+      tile_load(X, Uw + (size_t)(q - 1) * BS2);
+      __syncthreads();
+      gemm64(Dt, Z, X, Dt, -1.0); // D' -= P- U_{q-1}
+      __syncthreads();
+      tile_load(X, Lw + (size_t)(q - 1) * BS2);
+      __syncthreads();
+      gemm64(Y, Z, X, nullptr, -1.0); // L' = -P- L_{q-1}
+      __syncthreads();
+      tile_store(Ln + (size_t)t * BS2, Y);
       __syncthreads();
     }
+  else
+    {
+      tile_zero_store(Ln + (size_t)t * BS2);
+      tile_zero_store(pmT + (size_t)t * BS2);
+    }
+  if (q + 1 < n)
+    {
+      tile_load(X, Uw + (size_t)q * BS2);
+      tile_load(Y, dinv_rm + (size_t)t * BS2);
+      __syncthreads();
+      gemm64(Z, X, Y, nullptr, 1.0); // P+ = U_q Dinv_{q+1}
+      __syncthreads();
+      tile_store_T(ppT + (size_t)t * BS2, Z);
+      tile_load(X, Lw + (size_t)(q + 1) * BS2);
+      __syncthreads();
+      gemm64(Dt, Z, X, Dt, -1.0); // D' -= P+ L_{q+1}
+      __syncthreads();
+      tile_load(X, Uw + (size_t)(q + 1) * BS2);
+      __syncthreads();
+      gemm64(Y, Z, X, nullptr, -1.0); // U' = -P+ U_{q+1}
+      __syncthreads();
+      tile_store(Un + (size_t)t * BS2, Y);
+    }
+  else
+    {
+      tile_zero_store(Un + (size_t)t * BS2);
+      tile_zero_store(ppT + (size_t)t * BS2);
+    }
+  __syncthreads();
+  tile_store(Dn + (size_t)t * BS2, Dt);
 }
 
-// z_k = S_k^{-1} y_k for every block (one CTA of 64 threads per block); y may alias z
-__global__ void __launch_bounds__(BS)
-  k_bt_diag(uint32_t N, const double *__restrict__ SinvT, const double *y, double *z)
-{
-  __shared__ double sy[BS];
-  const uint32_t k = blockIdx.x;
-  const int r = threadIdx.x;
-  const size_t g = (size_t)k * BS + r;
-  sy[r] = g < N ? y[g] : 0.0;
-  __syncthreads();
-  const double *M = SinvT + (size_t)k * BS2;
+// ---------------------------------------------------------------------------------------
+// solve kernels.  w[K*64] is indexed by ORIGINAL block (position p of level l = block p << l),
+// so the reduced right-hand sides and the solution all live in place.
+// Blocks are column-major: Mt[j*64 + r] = M[r][j]  ->  thread r reads coalesced.
+// ---------------------------------------------------------------------------------------
+__device__ __forceinline__ double gemv_half(const double *__restrict__ Mt, const double *v, int r, int j0)
+{ // sum_{j=j0}^{j0+31} M[r][j] v[j]
   double a0 = 0, a1 = 0, a2 = 0, a3 = 0;
-#pragma unroll 4
-  for (int j = 0; j < BS; j += 4)
+#pragma unroll 8
+  for (int j = j0; j < j0 + 32; j += 4)
     {
-      a0 = fma(M[(j + 0) * BS + r], sy[j + 0], a0);
-      a1 = fma(M[(j + 1) * BS + r], sy[j + 1], a1);
-      a2 = fma(M[(j + 2) * BS + r], sy[j + 2], a2);
-      a3 = fma(M[(j + 3) * BS + r], sy[j + 3], a3);
+      a0 = fma(Mt[(j + 0) * BS + r], v[j + 0], a0);
+      a1 = fma(Mt[(j + 1) * BS + r], v[j + 1], a1);
+      a2 = fma(Mt[(j + 2) * BS + r], v[j + 2], a2);
+      a3 = fma(Mt[(j + 3) * BS + r], v[j + 3], a3);
     }
-  if (g < N) z[g] = (a0 + a1) + (a2 + a3);
+  return (a0 + a1) + (a2 + a3);
 }
 
+// forward: kept q = 2t: w_q -= P-_q w_{q-1} + P+_q w_{q+1}.  256 threads = 64 rows x 4 parts
+// (part 0,1: halves of P-, part 2,3: halves of P+).
+__global__ void __launch_bounds__(256)
+  k_bcr_forward(uint32_t n, int shift, const double *__restrict__ pmT, const double *__restrict__ ppT,
+                double *w)
+{
+  __shared__ double vl[BS], vr[BS], part[4][BS];
+  const uint32_t t = blockIdx.x, q = 2 * t;
+  const int r = threadIdx.x & 63, part_id = threadIdx.x >> 6;
+  const bool has_l = q >= 1, has_r = q + 1 < n;
+  if (threadIdx.x < BS) vl[r] = has_l ? w[((size_t)(q - 1) << shift) * BS + r] : 0.0;
+  else if (threadIdx.x < 2 * BS) vr[r] = has_r ? w[((size_t)(q + 1) << shift) * BS + r] : 0.0;
+  __syncthreads();
+  double s = 0.0;
+  if (part_id < 2)
+    {
+      if (has_l) s = gemv_half(pmT + (size_t)t * BS2, vl, r, 32 * part_id);
+    }
+  else if (has_r)
+    s = gemv_half(ppT + (size_t)t * BS2, vr, r, 32 * (part_id - 2));
+  part[part_id][r] = s;
+  __syncthreads();
+  if (threadIdx.x < BS)
+    {
+      double *dst = w + ((size_t)q << shift) * BS + r;
+      *dst = *dst - ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r]));
+    }
+}
+
+// backward: eliminated p = 2m+1: w_p = Dinv_p (w_p - L_p w_{p-1} - U_p w_{p+1})
+__global__ void __launch_bounds__(256)
+  k_bcr_backward(uint32_t n, int shift, const double *__restrict__ dinvT, const double *__restrict__ lT,
+                 const double *__restrict__ uT, double *w)
+{
+  __shared__ double vl[BS], vr[BS], rhs[BS], part[4][BS];
+  const uint32_t m = blockIdx.x, p = 2 * m + 1;
+  const int r = threadIdx.x & 63, part_id = threadIdx.x >> 6;
+  const bool has_r = p + 1 < n;
+  if (threadIdx.x < BS) vl[r] = w[((size_t)(p - 1) << shift) * BS + r];
+  else if (threadIdx.x < 2 * BS) vr[r] = has_r ? w[((size_t)(p + 1) << shift) * BS + r] : 0.0;
+  __syncthreads();
+  double s = 0.0;
+  if (part_id < 2) s = gemv_half(lT + (size_t)m * BS2, vl, r, 32 * part_id);
+  else if (has_r) s = gemv_half(uT + (size_t)m * BS2, vr, r, 32 * (part_id - 2));
+  part[part_id][r] = s;
+  __syncthreads();
+  double *dst = w + ((size_t)p << shift) * BS;
+  if (threadIdx.x < BS) rhs[r] = dst[r] - ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r]));
+  __syncthreads();
+  if (part_id < 2) part[part_id][r] = gemv_half(dinvT + (size_t)m * BS2, rhs, r, 32 * part_id);
+  __syncthreads();
+  if (threadIdx.x < BS) dst[r] = part[0][r] + part[1][r];
+}
+
+// last block: w_0 = Dinv w_0 ; also used for K == 1
+__global__ void __launch_bounds__(128) k_bcr_last(const double *__restrict__ dinvT, double *w)
+{
+  __shared__ double rhs[BS], part[2][BS];
+  const int r = threadIdx.x & 63, part_id = threadIdx.x >> 6;
+  if (threadIdx.x < BS) rhs[r] = w[r];
+  __syncthreads();
+  part[part_id][r] = gemv_half(dinvT, rhs, r, 32 * part_id);
+  __syncthreads();
+  if (threadIdx.x < BS) w[r] = part[0][r] + part[1][r];
+}
+
+__global__ void k_pad_copy_in(uint32_t N, uint32_t Np, const double *__restrict__ in, double *__restrict__ w)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < Np) w[i] = i < N ? in[i] : 0.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// host side
+// ---------------------------------------------------------------------------------------
 static bool g_attr_done = false;
 
 int wbem_device_precond_factor(wbem_ctx *ctx)
@@ -351,30 +409,81 @@ int wbem_device_precond_factor(wbem_ctx *ctx)
       dp = new DevPrecond();
       dp->K = K;
       ctx->dev_precond = dp;
-      CUDA_OK(ctx, cudaMalloc((void **)&dp->SinvT, sizeof(double) * (size_t)K * BS2));
-      CUDA_OK(ctx, cudaMalloc((void **)&dp->Lt, sizeof(double) * (size_t)K * BS2));
-      CUDA_OK(ctx, cudaMalloc((void **)&dp->Ut, sizeof(double) * (size_t)K * BS2));
+      size_t blocks = 0;
+      for (uint32_t n = K; n > 1; n = (n + 1) / 2)
+        {
+          BcrLevel L;
+          L.n = n;
+          L.n_elim = n / 2;
+          L.n_kept = (n + 1) / 2;
+          L.off_dinvT = blocks;
+          blocks += L.n_elim;
+          L.off_lT = blocks;
+          blocks += L.n_elim;
+          L.off_uT = blocks;
+          blocks += L.n_elim;
+          L.off_pmT = blocks;
+          blocks += L.n_kept;
+          L.off_ppT = blocks;
+          blocks += L.n_kept;
+          dp->lev.push_back(L);
+        }
+      dp->off_last = blocks++;
+      dp->pool_blocks = blocks;
+      CUDA_OK(ctx, cudaMalloc((void **)&dp->pool, sizeof(double) * blocks * BS2));
+      for (int i = 0; i < 2; ++i)
+        {
+          const size_t nb = i == 0 ? K : (K + 1) / 2;
+          CUDA_OK(ctx, cudaMalloc((void **)&dp->Lw[i], sizeof(double) * nb * BS2));
+          CUDA_OK(ctx, cudaMalloc((void **)&dp->Dw[i], sizeof(double) * nb * BS2));
+          CUDA_OK(ctx, cudaMalloc((void **)&dp->Uw[i], sizeof(double) * nb * BS2));
+        }
+      CUDA_OK(ctx, cudaMalloc((void **)&dp->dinv_rm, sizeof(double) * (size_t)(K / 2 + 1) * BS2));
       CUDA_OK(ctx, cudaMalloc((void **)&dp->work, sizeof(double) * (size_t)K * BS));
       CUDA_OK(ctx, cudaMalloc((void **)&dp->info, sizeof(int)));
     }
   if (!g_attr_done)
     {
-      CUDA_OK(ctx, cudaFuncSetAttribute(k_bt_factor, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double) * 4 * BS * LDS_)));
-      CUDA_OK(ctx, cudaFuncSetAttribute(k_bt_sweep, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                        (int)(sizeof(double) * (NSTAGE * BS2 + 6 * BS) + 64)));
+      CUDA_OK(ctx, cudaFuncSetAttribute(k_bcr_invert, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(double) * 2 * BS * LDP)));
+      CUDA_OK(ctx, cudaFuncSetAttribute(k_bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                        (int)(sizeof(double) * 4 * BS * LDP)));
       g_attr_done = true;
     }
   cudaStream_t st = ctx->stream;
   CUDA_OK(ctx, cudaMemsetAsync(dp->info, 0, sizeof(int), st));
-  k_bt_factor<<<1, 256, sizeof(double) * 4 * BS * LDS_, st>>>(ctx->N, K, band, ctx->d_band, dp->SinvT,
-                                                             dp->Lt, dp->Ut, dp->info);
+  k_band_to_blocks<<<dim3(K, 3), 256, 0, st>>>(ctx->N, K, band, ctx->d_band, dp->Lw[0], dp->Dw[0], dp->Uw[0]);
+  ctx->launches++;
+  int cur = 0, tag = 0;
+  // level 0 works on the K-block arrays; from level 1 on the two half-size arrays alternate
+  double *Lc = dp->Lw[0], *Dc = dp->Dw[0], *Uc = dp->Uw[0];
+  for (size_t l = 0; l < dp->lev.size(); ++l)
+    {
+      const BcrLevel &L = dp->lev[l];
+      k_bcr_invert<<<L.n_elim, 256, sizeof(double) * 2 * BS * LDP, st>>>(
+        L.n_elim, Lc, Dc, Uc, dp->dinv_rm, dp->pool + L.off_dinvT * BS2, dp->pool + L.off_lT * BS2,
+        dp->pool + L.off_uT * BS2, dp->info, tag, 0);
+      tag += L.n_elim;
+      // next-level arrays: level 0 -> Lw[1]; afterwards alternate between Lw[1] and Lw[0]
+      const int nxt = (l == 0) ? 1 : 1 - cur;
+      k_bcr_update<<<L.n_kept, 256, sizeof(double) * 4 * BS * LDP, st>>>(
+        L.n, Lc, Dc, Uc, dp->dinv_rm, dp->Lw[nxt], dp->Dw[nxt], dp->Uw[nxt], dp->pool + L.off_pmT * BS2,
+        dp->pool + L.off_ppT * BS2);
+      ctx->launches += 2;
+      cur = nxt;
+      Lc = dp->Lw[cur];
+      Dc = dp->Dw[cur];
+      Uc = dp->Uw[cur];
+    }
+  k_bcr_invert<<<1, 256, sizeof(double) * 2 * BS * LDP, st>>>(1, Lc, Dc, Uc, dp->dinv_rm,
+                                                             dp->pool + dp->off_last * BS2, nullptr, nullptr,
+                                                             dp->info, tag, 1);
   ctx->launches++;
   int info = 0;
   CUDA_OK(ctx, cudaMemcpyAsync(&info, dp->info, sizeof(int), cudaMemcpyDeviceToHost, st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   CUDA_OK(ctx, cudaGetLastError());
-  if (info) WBEM_FAIL(ctx, -6, "band preconditioner: singular diagonal block at row %d", info - 1);
+  if (info) WBEM_FAIL(ctx, -6, "band preconditioner: singular diagonal block (code %d)", info);
   return 0;
 }
 
@@ -383,19 +492,26 @@ int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out)
   DevPrecond *dp = reinterpret_cast<DevPrecond *>(ctx->dev_precond);
   if (!dp) WBEM_FAIL(ctx, -3, "device preconditioner not factorised");
   cudaStream_t st = ctx->stream;
-  const size_t smem = sizeof(double) * (NSTAGE * BS2 + 6 * BS) + 64;
-  if (dp->K > 1)
+  const uint32_t Np = dp->K * BS;
+  k_pad_copy_in<<<(Np + 255) / 256, 256, 0, st>>>(ctx->N, Np, d_in, dp->work);
+  ctx->launches++;
+  for (size_t l = 0; l < dp->lev.size(); ++l)
     {
-      k_bt_sweep<<<1, 256, smem, st>>>(ctx->N, dp->K, +1, dp->Lt, d_in, d_out);
-      k_bt_diag<<<dp->K, BS, 0, st>>>(ctx->N, dp->SinvT, d_out, d_out);
-      k_bt_sweep<<<1, 256, smem, st>>>(ctx->N, dp->K, -1, dp->Ut, d_out, d_out);
-      ctx->launches += 3;
-    }
-  else
-    {
-      k_bt_diag<<<1, BS, 0, st>>>(ctx->N, dp->SinvT, d_in, d_out);
+      const BcrLevel &L = dp->lev[l];
+      k_bcr_forward<<<L.n_kept, 256, 0, st>>>(L.n, (int)l, dp->pool + L.off_pmT * BS2,
+                                             dp->pool + L.off_ppT * BS2, dp->work);
       ctx->launches++;
     }
+  k_bcr_last<<<1, 128, 0, st>>>(dp->pool + dp->off_last * BS2, dp->work);
+  ctx->launches++;
+  for (size_t l = dp->lev.size(); l-- > 0;)
+    {
+      const BcrLevel &L = dp->lev[l];
+      k_bcr_backward<<<L.n_elim, 256, 0, st>>>(L.n, (int)l, dp->pool + L.off_dinvT * BS2,
+                                              dp->pool + L.off_lT * BS2, dp->pool + L.off_uT * BS2, dp->work);
+      ctx->launches++;
+    }
+  CUDA_OK(ctx, cudaMemcpyAsync(d_out, dp->work, sizeof(double) * ctx->N, cudaMemcpyDeviceToDevice, st));
   CUDA_OK(ctx, cudaGetLastError());
   return 0;
 }
@@ -404,9 +520,14 @@ void wbem_device_precond_free(wbem_ctx *ctx)
 {
   DevPrecond *dp = reinterpret_cast<DevPrecond *>(ctx->dev_precond);
   if (!dp) return;
-  cudaFree(dp->SinvT);
-  cudaFree(dp->Lt);
-  cudaFree(dp->Ut);
+  cudaFree(dp->pool);
+  for (int i = 0; i < 2; ++i)
+    {
+      cudaFree(dp->Lw[i]);
+      cudaFree(dp->Dw[i]);
+      cudaFree(dp->Uw[i]);
+    }
+  cudaFree(dp->dinv_rm);
   cudaFree(dp->work);
   cudaFree(dp->info);
   delete dp;

@@ -69,14 +69,26 @@ def _patch(points_grid, outward_is_uxv=True):
     bnd[0, :] = bnd[-1, :] = True
     bnd[:, 0] = bnd[:, -1] = True
     dirf = np.full(cells.shape[0], 1 if outward_is_uxv else 0, dtype=np.uint8)
-    return xyz, cells, dirf, bnd.ravel()
+    return xyz, cells, dirf, bnd.ravel(), (nu1 - 1, nv1 - 1)
+
+
+def _morton(i, j):
+    """Interleave the bits of two index arrays (z-order)."""
+    code = np.zeros_like(i, dtype=np.int64)
+    for b in range(20):
+        code |= ((i >> b) & 1) << (2 * b)
+        code |= ((j >> b) & 1) << (2 * b + 1)
+    return code
 
 
 def _finish(patches, names, renumber=None, seed=0, flip_every=0):
     """Concatenate patches, optionally renumber dofs, build double-node sets."""
     xyz_l, cells_l, dir_l, bnd_l, cp_l, np_l = [], [], [], [], [], []
     off = 0
-    for p, (xyz, cells, dirf, bnd) in enumerate(patches):
+    morton_l = []
+    for p, (xyz, cells, dirf, bnd, (nu, nv)) in enumerate(patches):
+        k = np.arange(cells.shape[0])
+        morton_l.append(_morton(k % nu, k // nu))
         xyz_l.append(xyz)
         cells_l.append(cells + off)
         dir_l.append(dirf)
@@ -100,7 +112,24 @@ def _finish(patches, names, renumber=None, seed=0, flip_every=0):
         dirf = dirf.copy()
         dirf[sel] = 1 - dirf[sel]
 
-    if renumber == "random":
+    if renumber == "hierarchical":
+        # deal.II-like numbering: cells in z-order inside each patch (the order hierarchical
+        # refinement produces), dofs numbered at their first appearance in that cell sequence.
+        # A band |i-j| < 50 in this numbering covers a compact 2-D neighbourhood, as in the
+        # reference, instead of a strip of a lexicographic grid.
+        order = np.lexsort((np.concatenate(morton_l), cpatch))
+        cells, dirf, cpatch = cells[order], dirf[order], cpatch[order]
+        flat = cells.ravel()
+        _, first = np.unique(flat, return_index=True)
+        seq = flat[np.sort(first)]                  # old dof ids in order of first appearance
+        perm = np.empty(n, dtype=np.int64)           # old -> new
+        perm[seq] = np.arange(n)
+        inv = seq
+        xyz = xyz[inv]
+        bnd = bnd[inv]
+        npatch = npatch[inv]
+        cells = perm[cells]
+    elif renumber == "random":
         rng = np.random.default_rng(seed)
         perm = rng.permutation(n)            # old -> new
         inv = np.empty(n, dtype=np.int64)
@@ -290,6 +319,7 @@ def wigley_tank(nxm=24, nt=10, nxu=8, nxd=12, nz=6, nzh=6, grade=0.25, renumber=
 
 
 def wigley_tank_for_nodes(n_target, **kw):
+    kw.setdefault("renumber", "hierarchical")
     """Pick the resolution whose node count is closest to n_target (keeps the aspect of the
     default resolution: most nodes near the hull and on the free surface)."""
     best = None
