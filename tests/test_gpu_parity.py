@@ -322,7 +322,7 @@ def test_full_size_20k_properties_and_row_slab_parity(wb, orc):
     flat = np.isin(m.node_patch, [m.patch_names.index(k) for k in ("bottom", "fs_up", "fs_down")]) & \
         ~m.node_on_patch_boundary
     assert np.abs(alpha[flat] - 0.5).max() < 1e-3   # solid angle of a smooth point
-    assert alpha.min() > 0 and alpha.max() <= 1.0 + 1e-6
+    assert alpha.min() > 0 and alpha.max() <= 1.0 + 1e-4   # ~1 at the thin ends of the keel
     ctx.set_masks(m.surface_nodes, m.other_nodes)
     ctx.set_constraints(cl)
     x, y = np.cos(0.1 * np.arange(n)), np.sin(0.3 * np.arange(n))

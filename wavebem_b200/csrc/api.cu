@@ -326,7 +326,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_alloc(ctx, &ctx->d_rhs, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_sol, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_V, (size_t)(ntmp - 1) * ld))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_h, 1024))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_h, 2048 + 128 + (size_t)(N + 255) / 256 + 64))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_band, (size_t)ctx->chunk * P * band))) return rc;
   CUDA_OK(ctx, cudaMemsetAsync(ctx->d_xn, 0, sizeof(double) * ld, ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->d_xd, 0, sizeof(double) * ld, ctx->stream));
@@ -338,7 +338,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
       CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_Nm + N, ld * sizeof(double), 0, (ld - N) * sizeof(double), nloc, ctx->stream));
       CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_Dm + N, ld * sizeof(double), 0, (ld - N) * sizeof(double), nloc, ctx->stream));
     }
-  ctx->pinned_doubles = 8 * (size_t)ld + 1024;
+  ctx->pinned_doubles = 8 * (size_t)ld + 2048;
   CUDA_OK(ctx, cudaMallocHost((void **)&ctx->h_pinned, ctx->pinned_doubles * sizeof(double)));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->op_version++;

@@ -376,27 +376,28 @@ __global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs
           double *gD = a.Dm + (size_t)row_b * a.ld + col;
           if (cc >> 31)
             {
-              double on[8], od[8];
+              // ADD column: fire-and-forget reduction (RED.ADD.F64), no load on the SM side.
+              // Clusters of one colour never share a column and colours are separate
+              // launches, so each entry sees its additions in a fixed order: bitwise
+              // reproducible although the instruction is an atomic.
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                {
-                  on[i] = (i < nr) ? gN[(size_t)i * a.ld] : 0.0;
-                  od[i] = (i < nr) ? gD[(size_t)i * a.ld] : 0.0;
-                }
-#pragma unroll
-              for (int i = 0; i < 8; ++i)
-                {
-                  vn[i] += on[i];
-                  vd[i] += od[i];
-                }
+                if (i < nr)
+                  {
+                    atomicAdd(gN + (size_t)i * a.ld, vn[i]);
+                    atomicAdd(gD + (size_t)i * a.ld, vd[i]);
+                  }
             }
+          else
+            {
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
-            if (i < nr)
-              {
-                gN[(size_t)i * a.ld] = vn[i];
-                gD[(size_t)i * a.ld] = vd[i];
-              }
+              for (int i = 0; i < 8; ++i)
+                if (i < nr)
+                  {
+                    gN[(size_t)i * a.ld] = vn[i];
+                    gD[(size_t)i * a.ld] = vd[i];
+                  }
+            }
         }
     }
 }

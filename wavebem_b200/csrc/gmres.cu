@@ -17,22 +17,31 @@
 // ---------------------------------------------------------------------------------------
 // vector kernels
 // ---------------------------------------------------------------------------------------
-// h[i] = V[i] . w  for i < k  (one CTA per basis vector; fixed reduction order)
+#define DOT_SEGS 8
+// partial[seg*128 + i] = V[i] . w over segment seg of the vector  (grid = k x DOT_SEGS;
+// fixed reduction order inside a CTA, the segments are summed in order by the consumer)
 __global__ void __launch_bounds__(256)
   k_dots(uint32_t N, const double *__restrict__ V, size_t ldv, const double *__restrict__ w,
-         double *__restrict__ h)
+         double *__restrict__ partial)
 {
   __shared__ double red[8];
   const double *v = V + (size_t)blockIdx.x * ldv;
-  double s0 = 0, s1 = 0;
-  uint32_t i = threadIdx.x;
-  for (; i + 256 < N; i += 512)
+  const uint32_t seg = blockIdx.y;
+  const uint32_t len = (N + DOT_SEGS - 1) / DOT_SEGS;
+  const uint32_t b = seg * len, e = min(N, b + len);
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  uint32_t i = b + threadIdx.x;
+  for (; i + 768 < e; i += 1024)
     {
-      s0 = fma(v[i], w[i], s0);
-      s1 = fma(v[i + 256], w[i + 256], s1);
+      const double v0 = v[i], v1 = v[i + 256], v2 = v[i + 512], v3 = v[i + 768];
+      const double w0 = w[i], w1 = w[i + 256], w2 = w[i + 512], w3 = w[i + 768];
+      s0 = fma(v0, w0, s0);
+      s1 = fma(v1, w1, s1);
+      s2 = fma(v2, w2, s2);
+      s3 = fma(v3, w3, s3);
     }
-  if (i < N) s0 = fma(v[i], w[i], s0);
-  double s = s0 + s1;
+  for (; i < e; i += 256) s0 = fma(v[i], w[i], s0);
+  double s = (s0 + s1) + (s2 + s3);
 #pragma unroll
   for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
   if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = s;
@@ -42,28 +51,49 @@ __global__ void __launch_bounds__(256)
       double t = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) t += red[k];
-      h[blockIdx.x] = t;
+      partial[seg * 128 + blockIdx.x] = t;
     }
 }
 
-// w -= sum_i h[i] V[i] ; optionally hacc[i] += h[i] (block 0)
+// h[i] = sum_seg partial ; w -= sum_i h[i] V[i] ; hacc[i] (+)= h[i] (block 0) ;
+// nrm2[blockIdx.x] = sum over this CTA's entries of w_j^2 (after the update)
 __global__ void __launch_bounds__(256)
   k_project_out(uint32_t N, int k, const double *__restrict__ V, size_t ldv,
-                const double *__restrict__ h, double *__restrict__ w, double *__restrict__ hacc,
-                int accumulate)
+                const double *__restrict__ partial, double *__restrict__ w, double *__restrict__ hacc,
+                int accumulate, double *__restrict__ nrm2)
 {
   extern __shared__ double sh[];
-  for (int i = threadIdx.x; i < k; i += blockDim.x) sh[i] = h[i];
+  __shared__ double red[8];
+  for (int i = threadIdx.x; i < k; i += blockDim.x)
+    {
+      double t = 0;
+#pragma unroll
+      for (int sg = 0; sg < DOT_SEGS; ++sg) t += partial[sg * 128 + i];
+      sh[i] = t;
+    }
   __syncthreads();
   const uint32_t j = blockIdx.x * blockDim.x + threadIdx.x;
+  double s = 0.0;
   if (j < N)
     {
-      double s = w[j];
+      s = w[j];
       for (int i = 0; i < k; ++i) s = fma(-sh[i], V[(size_t)i * ldv + j], s);
       w[j] = s;
     }
   if (blockIdx.x == 0 && hacc)
     for (int i = threadIdx.x; i < k; i += blockDim.x) hacc[i] = accumulate ? hacc[i] + sh[i] : sh[i];
+  double q = s * s;
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) q += __shfl_xor_sync(0xffffffffu, q, off);
+  if ((threadIdx.x & 31) == 0) red[threadIdx.x >> 5] = q;
+  __syncthreads();
+  if (threadIdx.x == 0)
+    {
+      double t = 0;
+#pragma unroll
+      for (int kk = 0; kk < 8; ++kk) t += red[kk];
+      nrm2[blockIdx.x] = t;
+    }
 }
 
 // out[0] = ||v||_2   (single CTA, fixed order)
@@ -392,7 +422,9 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   const int max_steps = ctx->p.gmres_max_steps;
   const size_t ldv = ctx->ld;
   double *V = ctx->d_V, *p = ctx->d_tmp[0], *x = ctx->d_sol;
-  double *d_h = ctx->d_h;         // [0..ntmp) current pass, [128..) accumulated, [256] norm
+  double *d_h = ctx->d_h;            // [0,128) scratch, [256] initial norm, [512] pure-Neumann norm
+  double *d_part = ctx->d_h + 1024;  // [DOT_SEGS][128] dot-product partials
+  double *d_hacc = ctx->d_h + 2048;  // [0,128) accumulated h, [128, 128+nb) per-CTA |w|^2
   double *hp = ctx->h_pinned;
   CUDA_OK(ctx, cudaMemsetAsync(x, 0, sizeof(double) * N, st));
   std::vector<double> H((size_t)ntmp * ntmp, 0.0), gamma(ntmp + 1), ci(ntmp + 1), si(ntmp + 1),
@@ -446,17 +478,18 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
           // CGS2
           for (int pass = 0; pass < 2; ++pass)
             {
-              k_dots<<<dim, 256, 0, st>>>(N, V, ldv, vv, d_h);
-              k_project_out<<<nb, 256, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_h, vv, d_h + 128,
-                                                                  pass);
+              k_dots<<<dim3(dim, DOT_SEGS), 256, 0, st>>>(N, V, ldv, vv, d_part);
+              k_project_out<<<nb, 256, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_part, vv, d_hacc, pass,
+                                                                  d_hacc + 128);
               ctx->launches += 2;
             }
-          k_norm2<<<1, 1024, 0, st>>>(N, vv, d_h + 128 + dim);
-          ctx->launches++;
-          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_h + 128, sizeof(double) * (dim + 1),
-                                       cudaMemcpyDeviceToHost, st));
+          // one D2H: accumulated h[0..dim) and the per-CTA sums of squares of the new vector
+          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_hacc, sizeof(double) * (128 + nb), cudaMemcpyDeviceToHost, st));
           CUDA_OK(ctx, cudaStreamSynchronize(st));
-          for (int i = 0; i <= dim; ++i) h[i] = hp[i];
+          for (int i = 0; i < dim; ++i) h[i] = hp[i];
+          double ss = 0;
+          for (unsigned i = 0; i < nb; ++i) ss += hp[128 + i];
+          h[dim] = std::sqrt(ss);
           const double s = h[dim];
           k_scale<<<nb, 256, 0, st>>>(N, vv, 1.0 / s);
           ctx->launches++;
