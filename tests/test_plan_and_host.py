@@ -9,7 +9,7 @@ from wavebem_b200 import meshgen
 from wavebem_b200.constraints import compute_constraints
 
 
-def _plan_check(wb, mesh, w=48, mc=36):
+def _plan_check(wb, mesh, w=48, mc=64):
     st = np.zeros(8)
     rc = wb.lib().wbem_plan_check(C.c_uint32(mesh.n_nodes), C.c_uint32(mesh.n_cells),
                                   mesh.cells.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(mc),
@@ -26,7 +26,7 @@ def test_plan_invariants(wb, make):
     m = make()
     rc, st = _plan_check(wb, m)
     assert rc == 0, f"plan invariant {rc} violated"
-    assert st[2] <= 36 and st[3] <= 48 and st[6] == m.n_nodes
+    assert st[2] <= 64 and st[3] <= 48 and st[6] == m.n_nodes
 
 
 def test_plan_small_tiles_and_degenerate_cells(wb):

@@ -228,7 +228,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
     if (dn_idx[k] >= N) WBEM_FAIL(ctx, -1, "double_nodes_set entry out of range");
 
   // tiling plan (plan.cpp); W and the cell cap match k_assemble_tiled's shared-memory tile
-  int rc = wbem_build_plan(N, C, cell_dofs, 48, 36, &ctx->plan);
+  int rc = wbem_build_plan(N, C, cell_dofs, 48, 64, &ctx->plan);
   if (rc) WBEM_FAIL(ctx, -1, "wbem_build_plan failed (%d): cell dof out of range?", rc);
   const AssemblyPlan &pl = ctx->plan;
 

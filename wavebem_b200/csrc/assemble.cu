@@ -197,16 +197,27 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 
 // ---------------------------------------------------------------------------------------
 // Tiled regular-pair kernel, Gauss 4x4.
+//
+// One CTA = (128-row tile) x (one cell cluster), 256 threads: TWO threads per collocation
+// row, each integrating two of the four Gauss lines (8 of the 16 points) of every cell.
+// They swap their partial moments with one shuffle; thread 0 of the pair finishes the
+// Neumann sums, thread 1 the Dirichlet sums, and each adds its 4 values to per-column
+// accumulators in shared memory (acc[matrix][slot][row]).  Two CTAs are resident per SM
+// (4 warps per scheduler) so one CTA's prologue / flush overlaps the other's FP64 loop.
+// Panel data arrives in chunks of 8 cells through a double-buffered TMA bulk copy.
 // ---------------------------------------------------------------------------------------
-#define TILE_ROWS WBEM_TILE_ROWS
+#define TILE_ROWS WBEM_TILE_ROWS          // 128
+#define TILE_THREADS (2 * TILE_ROWS)      // 256
 #define TILE_W 48
-#define TILE_MAX_CELLS 36
+#define TILE_MAX_CELLS 64                 // bit mask of singular cells is 64 bits wide
+#define TILE_CHUNK 8
 #define ACC_STRIDE (TILE_ROWS + 1)
+#define ACC_MATOFF (TILE_W * ACC_STRIDE + 8) // +8 doubles: the two matrices hit disjoint banks
 
 struct TiledArgs
 {
-  const double *xyz;        // [N][3]
-  const double *geo;        // [C][7][16] processing order
+  const double *xyz;         // [N][3]
+  const double *geo;         // [C][7][16] processing order
   const uint8_t *cell_slots; // [C][4]
   const uint32_t *cl_cell_ptr, *cl_slot_ptr, *slot_col, *color_clusters;
   const uint32_t *sing_ptr, *sing_cellpos; // CSR by local row
@@ -217,39 +228,47 @@ struct TiledArgs
 
 constexpr size_t tiled_smem_bytes()
 {
-  return sizeof(double) * (2 * TILE_W * ACC_STRIDE + TILE_MAX_CELLS * 7 * 16) + 16 /*mbar*/ +
-         TILE_MAX_CELLS * 4 + TILE_W * 4;
+  return sizeof(double) * (2 * ACC_MATOFF + 2 * TILE_CHUNK * 7 * 16) + 32 /*mbar*/ + TILE_MAX_CELLS * 4 +
+         TILE_W * 4;
 }
 
-__global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs a)
+__global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *acc = reinterpret_cast<double *>(smem_raw);            // [2][W][ACC_STRIDE]
-  double *geo = acc + 2 * TILE_W * ACC_STRIDE;                   // [cells][7][16]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + TILE_MAX_CELLS * 7 * 16);
-  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 2);     // [cells] packed 4 x u8
-  uint32_t *s_col = s_slots + TILE_MAX_CELLS;                    // [W]
+  double *acc = reinterpret_cast<double *>(smem_raw);              // [2][ACC_MATOFF]
+  double *geo = acc + 2 * ACC_MATOFF;                              // [2][CHUNK][7][16]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * TILE_CHUNK * 112);
+  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 4);       // [cells] packed 4 x u8
+  uint32_t *s_col = s_slots + TILE_MAX_CELLS;                      // [W]
 
   const int tid = threadIdx.x;
+  const int row_l = tid >> 1, h = tid & 1;
   const uint32_t cluster = a.color_clusters[a.cluster_base + blockIdx.x];
   const uint32_t p0 = a.cl_cell_ptr[cluster], p1 = a.cl_cell_ptr[cluster + 1];
   const uint32_t s0 = a.cl_slot_ptr[cluster], s1 = a.cl_slot_ptr[cluster + 1];
   const int ncell = (int)(p1 - p0), nslot = (int)(s1 - s0);
+  const int nchunk = (ncell + TILE_CHUNK - 1) / TILE_CHUNK;
   const uint32_t lrow_base = blockIdx.y * TILE_ROWS;
-  const uint32_t lrow = lrow_base + tid;
-  const bool row_ok = lrow < a.nloc;
-  const uint32_t lrow_c = row_ok ? lrow : a.nloc - 1;
+  const uint32_t lrow = lrow_base + row_l;
+  const uint32_t lrow_c = lrow < a.nloc ? lrow : a.nloc - 1;
 
   if (tid == 0)
     {
-      mbar_init(bar, 1);
+      mbar_init(&bar[0], 1);
+      mbar_init(&bar[1], 1);
     }
   __syncthreads();
+  auto issue_chunk = [&](int c) {
+    const int nc = min(TILE_CHUNK, ncell - c * TILE_CHUNK);
+    const uint32_t bytes = (uint32_t)nc * 112 * sizeof(double);
+    mbar_expect_tx(&bar[c & 1], bytes);
+    bulk_copy_g2s(geo + (c & 1) * TILE_CHUNK * 112, a.geo + ((size_t)p0 + (size_t)c * TILE_CHUNK) * 112, bytes,
+                  &bar[c & 1]);
+  };
   if (tid == 0)
     {
-      const uint32_t bytes = (uint32_t)ncell * 7 * 16 * sizeof(double);
-      mbar_expect_tx(bar, bytes);
-      bulk_copy_g2s(geo, a.geo + (size_t)p0 * 7 * 16, bytes, bar);
+      issue_chunk(0);
+      if (nchunk > 1) issue_chunk(1);
     }
   // singular cells of this row inside the cluster -> bit mask (they are integrated by
   // k_assemble_singular only, reference :241/:261).  Most (row tile, cluster) pairs hold no
@@ -271,92 +290,108 @@ __global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs
   const double xi0 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 0];
   const double xi1 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 1];
   const double xi2 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 2];
-  for (int i = tid; i < ncell; i += TILE_ROWS)
+  for (int i = tid; i < ncell; i += TILE_THREADS)
     s_slots[i] = reinterpret_cast<const uint32_t *>(a.cell_slots)[p0 + i];
-  for (int i = tid; i < nslot; i += TILE_ROWS) s_col[i] = a.slot_col[s0 + i];
-  // zero the accumulators of the slots in use
-  for (int s = 0; s < nslot; ++s)
-    {
-      acc[s * ACC_STRIDE + tid] = 0.0;
-      acc[(TILE_W + s) * ACC_STRIDE + tid] = 0.0;
-    }
+  for (int i = tid; i < nslot; i += TILE_THREADS) s_col[i] = a.slot_col[s0 + i];
+  // zero the accumulators in use: thread (row, h) clears matrix h of its row
+  double *accM = acc + h * ACC_MATOFF + row_l;
+  for (int s = 0; s < nslot; ++s) accM[s * ACC_STRIDE] = 0.0;
   __syncthreads();
-  mbar_wait(bar, 0);
 
-  double *accN = acc + tid;
-  double *accD = acc + TILE_W * ACC_STRIDE + tid;
-  for (int k = 0; k < ncell; ++k)
+  const double vq0 = c_qt.g1_x[2 * h], vq1 = c_qt.g1_x[2 * h + 1];
+  for (int c = 0; c < nchunk; ++c)
     {
-      if ((smask >> k) & 1ull) continue;
-      const double *g = geo + k * 112;
-      double SN = 0, SuN = 0, SvN = 0, SuvN = 0;
-      double SD = 0, SuD = 0, SvD = 0, SuvD = 0;
-#pragma unroll
-      for (int qy = 0; qy < 4; ++qy)
+      mbar_wait(&bar[c & 1], (c >> 1) & 1);
+      const double *gc = geo + (c & 1) * TILE_CHUNK * 112 + 8 * h; // this thread's 8 points
+      const int kend = min(TILE_CHUNK, ncell - c * TILE_CHUNK);
+      for (int kk = 0; kk < kend; ++kk)
         {
-          double t0n = 0, t1n = 0, t0d = 0, t1d = 0;
+          const int k = c * TILE_CHUNK + kk;
+          const double *g = gc + kk * 112;
+          double SN, SuN, SvN, SuvN, SD, SuD, SvD, SuvD;
 #pragma unroll
-          for (int qx = 0; qx < 4; ++qx)
+          for (int j = 0; j < 2; ++j)
             {
-              const int q = qy * 4 + qx;
-              const double Rx = g[q] - xi0;
-              const double Ry = g[16 + q] - xi1;
-              const double Rz = g[32 + q] - xi2;
-              const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
-              const double ri = rsqrt_h3(r2);
-              const double ri2 = ri * ri;
-              const double ri3 = ri2 * ri;
-              const double Rn = fma(Rz, g[80 + q], fma(Ry, g[64 + q], Rx * g[48 + q]));
-              const double av = Rn * ri3;      // (D . n) JxW
-              const double bv = g[96 + q] * ri; // d JxW
-              const double uq = c_qt.g1_x[qx];
-              if (qx == 0)
+              double t0n = 0, t1n = 0, t0d = 0, t1d = 0;
+#pragma unroll
+              for (int qx = 0; qx < 4; ++qx)
                 {
-                  t0n = av;
-                  t1n = av * uq;
-                  t0d = bv;
-                  t1d = bv * uq;
+                  const int q = j * 4 + qx;
+                  const double Rx = g[q] - xi0;
+                  const double Ry = g[16 + q] - xi1;
+                  const double Rz = g[32 + q] - xi2;
+                  const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
+                  const double ri = rsqrt_h3(r2);
+                  const double ri2 = ri * ri;
+                  const double ri3 = ri2 * ri;
+                  const double Rn = fma(Rz, g[80 + q], fma(Ry, g[64 + q], Rx * g[48 + q]));
+                  const double av = Rn * ri3;       // (D . n) JxW
+                  const double bv = g[96 + q] * ri; // d JxW
+                  const double uq = c_qt.g1_x[qx];
+                  if (qx == 0)
+                    {
+                      t0n = av;
+                      t1n = av * uq;
+                      t0d = bv;
+                      t1d = bv * uq;
+                    }
+                  else
+                    {
+                      t0n += av;
+                      t1n = fma(av, uq, t1n);
+                      t0d += bv;
+                      t1d = fma(bv, uq, t1d);
+                    }
+                }
+              if (j == 0)
+                {
+                  SN = t0n;
+                  SuN = t1n;
+                  SvN = vq0 * t0n;
+                  SuvN = vq0 * t1n;
+                  SD = t0d;
+                  SuD = t1d;
+                  SvD = vq0 * t0d;
+                  SuvD = vq0 * t1d;
                 }
               else
                 {
-                  t0n += av;
-                  t1n = fma(av, uq, t1n);
-                  t0d += bv;
-                  t1d = fma(bv, uq, t1d);
+                  SN += t0n;
+                  SuN += t1n;
+                  SvN = fma(vq1, t0n, SvN);
+                  SuvN = fma(vq1, t1n, SuvN);
+                  SD += t0d;
+                  SuD += t1d;
+                  SvD = fma(vq1, t0d, SvD);
+                  SuvD = fma(vq1, t1d, SuvD);
                 }
             }
-          const double vq = c_qt.g1_x[qy];
-          SN += t0n;
-          SuN += t1n;
-          SvN = fma(vq, t0n, SvN);
-          SuvN = fma(vq, t1n, SuvN);
-          SD += t0d;
-          SuD += t1d;
-          SvD = fma(vq, t0d, SvD);
-          SuvD = fma(vq, t1d, SuvD);
+          // swap with the other thread of the row: h = 0 keeps Neumann, h = 1 keeps Dirichlet
+          const double o0 = __shfl_xor_sync(0xffffffffu, h ? SN : SD, 1);
+          const double o1 = __shfl_xor_sync(0xffffffffu, h ? SuN : SuD, 1);
+          const double o2 = __shfl_xor_sync(0xffffffffu, h ? SvN : SvD, 1);
+          const double o3 = __shfl_xor_sync(0xffffffffu, h ? SuvN : SuvD, 1);
+          const double m0 = (h ? SD : SN) + o0, m1 = (h ? SuD : SuN) + o1, m2 = (h ? SvD : SvN) + o2,
+                       m3 = (h ? SuvD : SuvN) + o3;
+          // moments -> the four Q1 shape-function sums
+          const double v3 = m3, v1 = m1 - m3, v2 = m2 - m3, v0 = (m0 - m1) - v2;
+          if (!((smask >> k) & 1ull))
+            {
+              const uint32_t sl = s_slots[k];
+              accM[(sl & 0xff) * ACC_STRIDE] += v0;
+              accM[((sl >> 8) & 0xff) * ACC_STRIDE] += v1;
+              accM[((sl >> 16) & 0xff) * ACC_STRIDE] += v2;
+              accM[(sl >> 24) * ACC_STRIDE] += v3;
+            }
         }
-      // moments -> the four Q1 shape-function sums
-      const double n3 = SuvN, n1 = SuN - SuvN, n2 = SvN - SuvN, n0 = (SN - SuN) - n2;
-      const double d3 = SuvD, d1 = SuD - SuvD, d2 = SvD - SuvD, d0 = (SD - SuD) - d2;
-      const uint32_t sl = s_slots[k];
-      const int sa = (sl & 0xff) * ACC_STRIDE, sb = ((sl >> 8) & 0xff) * ACC_STRIDE,
-                sc = ((sl >> 16) & 0xff) * ACC_STRIDE, sd = (sl >> 24) * ACC_STRIDE;
-      accN[sa] += n0;
-      accD[sa] += d0;
-      accN[sb] += n1;
-      accD[sb] += d1;
-      accN[sc] += n2;
-      accD[sc] += d2;
-      accN[sd] += n3;
-      accD[sd] += d3;
+      __syncthreads(); // every thread is done with this geometry buffer
+      if (tid == 0 && c + 2 < nchunk) issue_chunk(c + 2);
     }
-  __syncthreads();
 
-  // flush: warp w owns rows [32w, 32w+32) of the tile; lanes run over the cluster's column
-  // slots (coalesced row segments); 8 rows are in flight per lane so that the read-modify-
-  // write of ADD columns has 16 independent loads outstanding instead of one.
+  // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
+  // slots (coalesced row segments), 8 rows per lane in flight.
   const int warp = tid >> 5, lane = tid & 31;
-  for (int rb = warp * 32; rb < warp * 32 + 32; rb += 8)
+  for (int rb = warp * 16; rb < warp * 16 + 16; rb += 8)
     {
       const uint32_t row_b = lrow_base + rb;
       if (row_b >= a.nloc) break;
@@ -370,7 +405,7 @@ __global__ void __launch_bounds__(TILE_ROWS, 1) k_assemble_tiled(const TiledArgs
           for (int i = 0; i < 8; ++i)
             {
               vn[i] = acc[s * ACC_STRIDE + rb + i];
-              vd[i] = acc[(TILE_W + s) * ACC_STRIDE + rb + i];
+              vd[i] = acc[ACC_MATOFF + s * ACC_STRIDE + rb + i];
             }
           double *gN = a.Nm + (size_t)row_b * a.ld + col;
           double *gD = a.Dm + (size_t)row_b * a.ld + col;
@@ -637,7 +672,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
           if (nclu == 0) continue;
           a.cluster_base = pl.color_ptr[c];
           dim3 grid(nclu, row_tiles);
-          k_assemble_tiled<<<grid, TILE_ROWS, tiled_smem_bytes(), st>>>(a);
+          k_assemble_tiled<<<grid, TILE_THREADS, tiled_smem_bytes(), st>>>(a);
           ctx->launches++;
         }
       CUDA_OK(ctx, cudaGetLastError());
