@@ -74,7 +74,7 @@ ABI_SYMBOLS = [
     "wbem_get_system_rhs", "wbem_get_sol", "wbem_get_timings", "wbem_reset_counters",
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
-    "wbem_timer_start", "wbem_timer_stop",
+    "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe",
 ]
 
 
@@ -301,6 +301,11 @@ class Context:
     def measure_fp64_peak(self):
         v = C.c_double(0)
         self._chk(lib().wbem_measure_fp64_peak(self._h, C.byref(v)))
+        return v.value
+
+    def issue_probe(self, n_int):
+        v = C.c_double(0)
+        self._chk(lib().wbem_issue_probe(self._h, int(n_int), C.byref(v)))
         return v.value
 
     def measure_copy_bw(self):

@@ -42,6 +42,38 @@ static int dev_upload(wbem_ctx *ctx, T **p, const std::vector<T> &v)
     }                   \
   while (0)
 
+// issue-port probe: 8 independent DFMA chains + NI integer/LDS-free ALU ops per iteration
+template <int NI>
+__global__ void k_issue_probe(double *out, int *iout, int iters)
+{
+  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
+         a6 = a0 + 6, a7 = a0 + 7;
+  const double b = 1.0000001, c = 1e-7;
+  int x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
+  for (int i = 0; i < iters; ++i)
+    {
+      a0 = fma(a0, b, c);
+      a1 = fma(a1, b, c);
+      a2 = fma(a2, b, c);
+      a3 = fma(a3, b, c);
+      a4 = fma(a4, b, c);
+      a5 = fma(a5, b, c);
+      a6 = fma(a6, b, c);
+      a7 = fma(a7, b, c);
+#pragma unroll
+      for (int k = 0; k < NI; ++k)
+        {
+          if ((k & 3) == 0) x0 = (x0 ^ i) + 0x9e37;
+          if ((k & 3) == 1) x1 = (x1 ^ i) + 0x79b9;
+          if ((k & 3) == 2) x2 = (x2 ^ i) + 0x7f4a;
+          if ((k & 3) == 3) x3 = (x3 ^ i) + 0x7c15;
+        }
+    }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+  iout[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3;
+}
+
+
 extern "C" {
 
 int wbem_version(void) { return 100; }
@@ -227,6 +259,11 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   for (uint32_t k = 0; k < dn_ptr[N]; ++k)
     if (dn_idx[k] >= N) WBEM_FAIL(ctx, -1, "double_nodes_set entry out of range");
 
+  ctx->has_degenerate_cells = false;
+  for (uint32_t c = 0; c < C && !ctx->has_degenerate_cells; ++c)
+    for (int j = 1; j < 4; ++j)
+      for (int i = 0; i < j; ++i)
+        if (cell_dofs[4 * (size_t)c + i] == cell_dofs[4 * (size_t)c + j]) ctx->has_degenerate_cells = true;
   // tiling plan (plan.cpp); W and the cell cap match k_assemble_tiled's shared-memory tile
   int rc = wbem_build_plan(N, C, cell_dofs, 48, 64, &ctx->plan);
   if (rc) WBEM_FAIL(ctx, -1, "wbem_build_plan failed (%d): cell dof out of range?", rc);
@@ -842,6 +879,43 @@ __global__ void k_dfma_peak(double *out, int iters)
       a7 = fma(a7, b, c);
     }
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
+}
+
+// diagnostic: DFMA TFLOP/s when n_int integer ALU ops are interleaved with every 8 DFMAs
+int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops)
+{
+  CHECK_CTX(ctx);
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  const int blocks = 148 * 4, threads = 512, iters = 1 << 14;
+  double *d = nullptr;
+  int *di = nullptr;
+  CUDA_OK(ctx, cudaMalloc((void **)&d, sizeof(double) * blocks * threads));
+  CUDA_OK(ctx, cudaMalloc((void **)&di, sizeof(int) * blocks * threads));
+  cudaStream_t st = ctx->stream;
+  float best = 1e30f;
+  for (int rep = 0; rep < 4; ++rep)
+    {
+      CUDA_OK(ctx, cudaEventRecord(ctx->ev[8], st));
+      switch (n_int)
+        {
+        case 0: k_issue_probe<0><<<blocks, threads, 0, st>>>(d, di, iters); break;
+        case 2: k_issue_probe<2><<<blocks, threads, 0, st>>>(d, di, iters); break;
+        case 4: k_issue_probe<4><<<blocks, threads, 0, st>>>(d, di, iters); break;
+        case 8: k_issue_probe<8><<<blocks, threads, 0, st>>>(d, di, iters); break;
+        case 16: k_issue_probe<16><<<blocks, threads, 0, st>>>(d, di, iters); break;
+        default: cudaFree(d); cudaFree(di); WBEM_FAIL(ctx, -1, "n_int must be 0,2,4,8,16");
+        }
+      ctx->launches++;
+      CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], st));
+      CUDA_OK(ctx, cudaStreamSynchronize(st));
+      float ms = 0;
+      cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+      if (rep >= 1 && ms < best) best = ms;
+    }
+  cudaFree(d);
+  cudaFree(di);
+  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  return 0;
 }
 
 int wbem_measure_fp64_peak(wbem_ctx *ctx, double *tflops)

@@ -180,6 +180,10 @@ __device__ __forceinline__ void bulk_copy_g2s(void *dst, const void *src, uint32
     "l"(src), "r"(bytes), "r"(smem_u32(bar))
     : "memory");
 }
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
   uint32_t done;
@@ -254,8 +258,10 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
 
   if (tid == 0)
     {
-      mbar_init(&bar[0], 1);
+      mbar_init(&bar[0], 1);                 // "full": TMA bytes landed
       mbar_init(&bar[1], 1);
+      mbar_init(&bar[2], TILE_THREADS / 32); // "empty": every warp is done reading the buffer
+      mbar_init(&bar[3], TILE_THREADS / 32);
     }
   __syncthreads();
   auto issue_chunk = [&](int c) {
@@ -308,6 +314,12 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
         {
           const int k = c * TILE_CHUNK + kk;
           const double *g = gc + kk * 112;
+          // accumulator slots of this cell: loaded now, added to after the integration (the
+          // host routes meshes whose cells repeat a dof to the simple kernel)
+          const uint32_t sl = s_slots[k];
+          double *const pa = accM + (sl & 0xff) * ACC_STRIDE, *const pb = accM + ((sl >> 8) & 0xff) * ACC_STRIDE,
+                        *const pc = accM + ((sl >> 16) & 0xff) * ACC_STRIDE, *const pd = accM + (sl >> 24) * ACC_STRIDE;
+          const double oa = *pa, ob = *pb, oc = *pc, od = *pd;
           double SN, SuN, SvN, SuvN, SD, SuD, SvD, SuvD;
 #pragma unroll
           for (int j = 0; j < 2; ++j)
@@ -377,16 +389,26 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
           const double v3 = m3, v1 = m1 - m3, v2 = m2 - m3, v0 = (m0 - m1) - v2;
           if (!((smask >> k) & 1ull))
             {
-              const uint32_t sl = s_slots[k];
-              accM[(sl & 0xff) * ACC_STRIDE] += v0;
-              accM[((sl >> 8) & 0xff) * ACC_STRIDE] += v1;
-              accM[((sl >> 16) & 0xff) * ACC_STRIDE] += v2;
-              accM[(sl >> 24) * ACC_STRIDE] += v3;
+              *pa = oa + v0;
+              *pb = ob + v1;
+              *pc = oc + v2;
+              *pd = od + v3;
             }
         }
-      __syncthreads(); // every thread is done with this geometry buffer
-      if (tid == 0 && c + 2 < nchunk) issue_chunk(c + 2);
+      // release the geometry buffer: one arrival per warp on its "empty" barrier; only the
+      // producer thread waits for all 8 before refilling it (no CTA-wide barrier per chunk)
+      if (c + 2 < nchunk)
+        {
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&bar[2 + (c & 1)]);
+          if (tid == 0)
+            {
+              mbar_wait(&bar[2 + (c & 1)], (c >> 1) & 1);
+              issue_chunk(c + 2);
+            }
+        }
     }
+  __syncthreads();
 
   // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
   // slots (coalesced row segments), 8 rows per lane in flight.
@@ -627,7 +649,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
   cudaStream_t st = ctx->stream;
   const int nq = ctx->qt.nq;
   if (ctx->nloc == 0 || ctx->C == 0) return 0;
-  const bool tiled = (ctx->p.assemble_variant == 0) && (ctx->qt.n1 == 4);
+  const bool tiled = (ctx->p.assemble_variant == 0) && (ctx->qt.n1 == 4) && !ctx->has_degenerate_cells;
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
   if (tiled)
     {

@@ -145,6 +145,7 @@ struct wbem_ctx
   double *d_xyz = nullptr;     // [N][3]
   double *d_cellgeo = nullptr; // [C][7][nq] in processing order
   bool have_geometry = false, assembled = false, have_alpha = false;
+  bool has_degenerate_cells = false; // a cell lists the same dof twice -> simple kernel
 
   // matrices: nloc x ld, row-major, columns in storage order (colperm)
   double *d_Nm = nullptr, *d_Dm = nullptr;

@@ -44,6 +44,8 @@ struct DevPrecond
   double *dinv_rm = nullptr;  // [K/2] row-major inverses of the level being processed
   double *work = nullptr;     // [K*64] right-hand side / solution, indexed by original block
   int *info = nullptr;
+  unsigned int *barrier = nullptr;
+  int fused_grid = 0; // 0 = fused kernel unavailable
 };
 
 // ---------------------------------------------------------------------------------------
@@ -393,6 +395,122 @@ __global__ void k_pad_copy_in(uint32_t N, uint32_t Np, const double *__restrict_
 }
 
 // ---------------------------------------------------------------------------------------
+// Fused application of M^-1: one cooperative kernel walks all levels, with a grid-wide
+// barrier between levels instead of one launch per level (the per-level work is a few
+// microseconds, so launch gaps dominated the un-fused version).
+// ---------------------------------------------------------------------------------------
+#define BCR_MAX_LEVELS 24
+struct BcrSolveArgs
+{
+  uint32_t N, K, nlev;
+  uint32_t n[BCR_MAX_LEVELS];
+  const double *pmT[BCR_MAX_LEVELS], *ppT[BCR_MAX_LEVELS], *dinvT[BCR_MAX_LEVELS], *lT[BCR_MAX_LEVELS],
+    *uT[BCR_MAX_LEVELS];
+  const double *lastT;
+  const double *in;
+  double *out, *w;
+  unsigned int *barrier; // zeroed before every launch
+};
+
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int &epoch)
+{
+  __syncthreads();
+  if (threadIdx.x == 0)
+    {
+      ++epoch;
+      __threadfence();
+      atomicAdd(counter, 1u);
+      const unsigned int target = epoch * gridDim.x;
+      unsigned int v;
+      do
+        {
+          asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
+        }
+      while (v < target);
+      __threadfence();
+    }
+  __syncthreads();
+}
+
+__global__ void __launch_bounds__(256, 1) k_bcr_solve_fused(const BcrSolveArgs a)
+{
+  __shared__ double vl[BS], vr[BS], rhs[BS], part[4][BS];
+  unsigned int epoch = 0;
+  const int r = threadIdx.x & 63, part_id = threadIdx.x >> 6;
+  double *w = a.w;
+  const uint32_t Np = a.K * BS;
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x)
+    w[i] = i < a.N ? a.in[i] : 0.0;
+  grid_barrier(a.barrier, epoch);
+  // forward reduction of the right-hand side
+  for (uint32_t l = 0; l < a.nlev; ++l)
+    {
+      const uint32_t n = a.n[l], n_kept = (n + 1) / 2;
+      for (uint32_t t = blockIdx.x; t < n_kept; t += gridDim.x)
+        {
+          const uint32_t q = 2 * t;
+          const bool has_l = q >= 1, has_r = q + 1 < n;
+          if (threadIdx.x < BS) vl[r] = has_l ? w[((size_t)(q - 1) << l) * BS + r] : 0.0;
+          else if (threadIdx.x < 2 * BS) vr[r] = has_r ? w[((size_t)(q + 1) << l) * BS + r] : 0.0;
+          __syncthreads();
+          double s = 0.0;
+          if (part_id < 2)
+            {
+              if (has_l) s = gemv_half(a.pmT[l] + (size_t)t * BS2, vl, r, 32 * part_id);
+            }
+          else if (has_r)
+            s = gemv_half(a.ppT[l] + (size_t)t * BS2, vr, r, 32 * (part_id - 2));
+          part[part_id][r] = s;
+          __syncthreads();
+          if (threadIdx.x < BS)
+            {
+              double *dst = w + ((size_t)q << l) * BS + r;
+              *dst = *dst - ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r]));
+            }
+          __syncthreads();
+        }
+      grid_barrier(a.barrier, epoch);
+    }
+  // last block
+  if (blockIdx.x == 0)
+    {
+      if (threadIdx.x < BS) rhs[r] = w[r];
+      __syncthreads();
+      if (part_id < 2) part[part_id][r] = gemv_half(a.lastT, rhs, r, 32 * part_id);
+      __syncthreads();
+      if (threadIdx.x < BS) w[r] = part[0][r] + part[1][r];
+    }
+  grid_barrier(a.barrier, epoch);
+  // back substitution
+  for (uint32_t l = a.nlev; l-- > 0;)
+    {
+      const uint32_t n = a.n[l], n_elim = n / 2;
+      for (uint32_t m = blockIdx.x; m < n_elim; m += gridDim.x)
+        {
+          const uint32_t p = 2 * m + 1;
+          const bool has_r = p + 1 < n;
+          if (threadIdx.x < BS) vl[r] = w[((size_t)(p - 1) << l) * BS + r];
+          else if (threadIdx.x < 2 * BS) vr[r] = has_r ? w[((size_t)(p + 1) << l) * BS + r] : 0.0;
+          __syncthreads();
+          double s = 0.0;
+          if (part_id < 2) s = gemv_half(a.lT[l] + (size_t)m * BS2, vl, r, 32 * part_id);
+          else if (has_r) s = gemv_half(a.uT[l] + (size_t)m * BS2, vr, r, 32 * (part_id - 2));
+          part[part_id][r] = s;
+          __syncthreads();
+          double *dst = w + ((size_t)p << l) * BS;
+          if (threadIdx.x < BS) rhs[r] = dst[r] - ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r]));
+          __syncthreads();
+          if (part_id < 2) part[part_id][r] = gemv_half(a.dinvT[l] + (size_t)m * BS2, rhs, r, 32 * part_id);
+          __syncthreads();
+          if (threadIdx.x < BS) dst[r] = part[0][r] + part[1][r];
+          __syncthreads();
+        }
+      grid_barrier(a.barrier, epoch);
+    }
+  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += gridDim.x * blockDim.x) a.out[i] = w[i];
+}
+
+// ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
 static bool g_attr_done = false;
@@ -441,6 +559,12 @@ int wbem_device_precond_factor(wbem_ctx *ctx)
       CUDA_OK(ctx, cudaMalloc((void **)&dp->dinv_rm, sizeof(double) * (size_t)(K / 2 + 1) * BS2));
       CUDA_OK(ctx, cudaMalloc((void **)&dp->work, sizeof(double) * (size_t)K * BS));
       CUDA_OK(ctx, cudaMalloc((void **)&dp->info, sizeof(int)));
+      CUDA_OK(ctx, cudaMalloc((void **)&dp->barrier, sizeof(unsigned int)));
+      int coop = 0, n_sm = 0, per_sm = 0;
+      cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, ctx->dev);
+      cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->dev);
+      cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bcr_solve_fused, 256, 0);
+      dp->fused_grid = (coop && per_sm >= 1 && dp->lev.size() <= BCR_MAX_LEVELS) ? n_sm : 0;
     }
   if (!g_attr_done)
     {
@@ -493,6 +617,36 @@ int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out)
   if (!dp) WBEM_FAIL(ctx, -3, "device preconditioner not factorised");
   cudaStream_t st = ctx->stream;
   const uint32_t Np = dp->K * BS;
+  if (dp->fused_grid > 0)
+    {
+      BcrSolveArgs a;
+      a.N = ctx->N;
+      a.K = dp->K;
+      a.nlev = (uint32_t)dp->lev.size();
+      for (size_t l = 0; l < dp->lev.size(); ++l)
+        {
+          const BcrLevel &L = dp->lev[l];
+          a.n[l] = L.n;
+          a.pmT[l] = dp->pool + L.off_pmT * BS2;
+          a.ppT[l] = dp->pool + L.off_ppT * BS2;
+          a.dinvT[l] = dp->pool + L.off_dinvT * BS2;
+          a.lT[l] = dp->pool + L.off_lT * BS2;
+          a.uT[l] = dp->pool + L.off_uT * BS2;
+        }
+      a.lastT = dp->pool + dp->off_last * BS2;
+      a.in = d_in;
+      a.out = d_out;
+      a.w = dp->work;
+      a.barrier = dp->barrier;
+      CUDA_OK(ctx, cudaMemsetAsync(dp->barrier, 0, sizeof(unsigned int), st));
+      void *args[] = {(void *)&a};
+      int grid = dp->fused_grid;
+      const int most = (int)((dp->K + 1) / 2);
+      if (grid > most) grid = most < 1 ? 1 : most;
+      CUDA_OK(ctx, cudaLaunchCooperativeKernel((void *)k_bcr_solve_fused, dim3(grid), dim3(256), args, 0, st));
+      ctx->launches++;
+      return 0;
+    }
   k_pad_copy_in<<<(Np + 255) / 256, 256, 0, st>>>(ctx->N, Np, d_in, dp->work);
   ctx->launches++;
   for (size_t l = 0; l < dp->lev.size(); ++l)
@@ -530,6 +684,7 @@ void wbem_device_precond_free(wbem_ctx *ctx)
   cudaFree(dp->dinv_rm);
   cudaFree(dp->work);
   cudaFree(dp->info);
+  cudaFree(dp->barrier);
   delete dp;
   ctx->dev_precond = nullptr;
 }
