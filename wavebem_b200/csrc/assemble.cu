@@ -395,20 +395,9 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
               *pd = od + v3;
             }
         }
-      // release the geometry buffer: one arrival per warp on its "empty" barrier; only the
-      // producer thread waits for all 8 before refilling it (no CTA-wide barrier per chunk)
-      if (c + 2 < nchunk)
-        {
-          __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&bar[2 + (c & 1)]);
-          if (tid == 0)
-            {
-              mbar_wait(&bar[2 + (c & 1)], (c >> 1) & 1);
-              issue_chunk(c + 2);
-            }
-        }
+      __syncthreads(); // every thread is done with this geometry buffer
+      if (tid == 0 && c + 2 < nchunk) issue_chunk(c + 2);
     }
-  __syncthreads();
 
   // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
   // slots (coalesced row segments), 8 rows per lane in flight.
