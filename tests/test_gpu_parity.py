@@ -337,3 +337,24 @@ def test_full_size_20k_properties_and_row_slab_parity(wb, orc):
     phi2, dphi2, it2, _ = ctx.solve_system(z, z, bc)
     assert it2 == it and np.array_equal(phi2, phi)
     ctx.close()
+
+
+def test_pure_neumann_with_constraints(wb, orc):
+    """All-Neumann cube: the -||dst|| shift uses the norm over ALL rows of the raw product
+    (bem_problem.cc:667-668) even though constrained rows are overwritten afterwards."""
+    from wavebem_b200.constraints import compute_constraints
+    m = meshgen.cube(5)
+    n = m.n_nodes
+    s, o = np.zeros(n), np.ones(n)
+    bc = np.sin(0.3 * np.arange(n))
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, s, bc)
+    ctx = _ctx(wb, m)
+    ctx.assemble()
+    ctx.set_masks(s, o)
+    ctx.set_constraints(cl)
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    alpha = orc.compute_alpha(on)
+    x = np.cos(0.2 * np.arange(n))
+    ref = orc.constrained_vmult(on, od, alpha, s, o, _orc_con(orc, cl), x)
+    assert np.abs(ctx.constrained_vmult(x) - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
+    ctx.close()

@@ -186,6 +186,7 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_surf);
   FREE_DEV(ctx->d_other);
   FREE_DEV(ctx->d_con_line_of);
+  FREE_DEV(ctx->d_free_rows);
   FREE_DEV(ctx->d_con_lines);
   FREE_DEV(ctx->d_con_ptr);
   FREE_DEV(ctx->d_con_col);
@@ -591,6 +592,11 @@ int wbem_set_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t *lines,
     vc(col, col + nnz);
   std::vector<double> vv(val, val + nnz), vi(inhom, inhom + n_lines);
   if (!n_lines) vp.assign(1, 0);
+  std::vector<uint32_t> free_rows;
+  for (uint32_t r = 0; r < ctx->nloc; ++r)
+    if (line_of[ctx->row0 + r] < 0) free_rows.push_back(r);
+  ctx->n_free_rows = (uint32_t)free_rows.size();
+  if ((rc = dev_upload(ctx, &ctx->d_free_rows, free_rows))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_con_line_of, line_of))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_con_lines, vl))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_con_ptr, vp))) return rc;

@@ -160,6 +160,8 @@ struct wbem_ctx
   uint32_t *d_con_lines = nullptr, *d_con_ptr = nullptr, *d_con_col = nullptr;
   double *d_con_val = nullptr, *d_con_inhom = nullptr;
   std::vector<int32_t> h_con_line_of;
+  uint32_t *d_free_rows = nullptr; // local rows without a constraint line
+  uint32_t n_free_rows = 0;
   uint64_t op_version = 0, precond_version = ~0ull; // preconditioner cache key
 
   // work vectors (device, length N or chunk*world)

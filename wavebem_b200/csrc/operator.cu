@@ -30,9 +30,11 @@ __device__ __forceinline__ double2 ld_stream(const double *p)
 template <int NR>
 __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const double *__restrict__ x,
                                           const uint32_t *__restrict__ list, int n, uint32_t ld,
-                                          uint32_t row0, int lane, double acc[GEMV_MAXR])
+                                          const uint32_t rows[GEMV_MAXR], int lane, double acc[GEMV_MAXR])
 {
-  const double *base = M + (size_t)row0 * ld + lane * 2;
+  const double *base[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) base[r] = M + (size_t)rows[r] * ld + lane * 2;
   int i = 0;
   for (; i + 1 < n; i += 2)
     {
@@ -41,8 +43,8 @@ __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const do
 #pragma unroll
       for (int r = 0; r < NR; ++r)
         {
-          m0[r] = ld_stream(base + (size_t)r * ld + c0);
-          m1[r] = ld_stream(base + (size_t)r * ld + c1);
+          m0[r] = ld_stream(base[r] + c0);
+          m1[r] = ld_stream(base[r] + c1);
         }
       const double2 x0 = *reinterpret_cast<const double2 *>(x + c0 + lane * 2);
       const double2 x1 = *reinterpret_cast<const double2 *>(x + c1 + lane * 2);
@@ -62,7 +64,7 @@ __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const do
 #pragma unroll
       for (int r = 0; r < NR; ++r)
         {
-          const double2 m0 = ld_stream(base + (size_t)r * ld + c0);
+          const double2 m0 = ld_stream(base[r] + c0);
           acc[r] = fma(m0.x, x0.x, acc[r]);
           acc[r] = fma(m0.y, x0.y, acc[r]);
         }
@@ -76,6 +78,8 @@ struct GemvArgs
   int n1, n2;
   double s1, s2, sdiag;
   uint32_t ld, nloc, row0;
+  const uint32_t *row_list; // local rows to compute (constrained rows are skipped), or null
+  uint32_t n_rows;          // entries of row_list (= nloc when null)
   double *y;
 };
 
@@ -85,8 +89,11 @@ __device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int la
   double a1[GEMV_MAXR], a2[GEMV_MAXR];
 #pragma unroll
   for (int r = 0; r < GEMV_MAXR; ++r) a1[r] = a2[r] = 0.0;
-  gemv_pass<NR>(a.M1, a.x1, a.list1, a.n1, a.ld, r0, lane, a1);
-  gemv_pass<NR>(a.M2, a.x2, a.list2, a.n2, a.ld, r0, lane, a2);
+  uint32_t rows[GEMV_MAXR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) rows[r] = a.row_list ? a.row_list[r0 + r] : r0 + r;
+  gemv_pass<NR>(a.M1, a.x1, a.list1, a.n1, a.ld, rows, lane, a1);
+  gemv_pass<NR>(a.M2, a.x2, a.list2, a.n2, a.ld, rows, lane, a2);
 #pragma unroll
   for (int r = 0; r < NR; ++r)
     {
@@ -95,8 +102,8 @@ __device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int la
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
       if (lane == 0)
         {
-          const uint32_t g = a.row0 + r0 + r;
-          a.y[r0 + r] = v + a.sdiag * a.alpha[g] * a.xdiag[g];
+          const uint32_t g = a.row0 + rows[r];
+          a.y[rows[r]] = v + a.sdiag * a.alpha[g] * a.xdiag[g];
         }
     }
 }
@@ -108,7 +115,7 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
 {
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t G = gridDim.x, c = blockIdx.x;
-  const uint32_t cr0 = (uint32_t)((uint64_t)a.nloc * c / G), cr1 = (uint32_t)((uint64_t)a.nloc * (c + 1) / G);
+  const uint32_t cr0 = (uint32_t)((uint64_t)a.n_rows * c / G), cr1 = (uint32_t)((uint64_t)a.n_rows * (c + 1) / G);
   const uint32_t nr = cr1 - cr0;
   uint32_t r0 = cr0 + nr * warp / GEMV_WARPS;
   const uint32_t r1 = cr0 + nr * (warp + 1) / GEMV_WARPS;
@@ -246,6 +253,11 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
       ga.nloc = ctx->nloc;
       ga.row0 = ctx->row0;
       ga.y = yloc;
+      // rows a constraint line overwrites afterwards need not be streamed at all
+      // (the pure-Neumann shift needs the norm over ALL rows of the raw product, :667-668)
+      const bool skip = constrained && ctx->n_lines > 0 && ctx->d_free_rows && !(mode == 0 && ctx->pure_neumann);
+      ga.row_list = skip ? ctx->d_free_rows : nullptr;
+      ga.n_rows = skip ? ctx->n_free_rows : ctx->nloc;
       if (mode == 0)
         {
           ga.list1 = list_o; ga.n1 = n_o; ga.s1 = 1.0;
@@ -259,13 +271,17 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
           ga.sdiag = -1.0;
         }
       uint32_t grid = (uint32_t)(n_sm * ctas_per_sm);
-      const uint32_t max_useful = (ctx->nloc + GEMV_WARPS - 1) / GEMV_WARPS; // >= 1 row per warp
+      const uint32_t max_useful = (ga.n_rows + GEMV_WARPS - 1) / GEMV_WARPS; // >= 1 row per warp
+      if (ga.n_rows == 0) grid = 0;
       if (grid > max_useful) grid = max_useful;
-      k_bem_gemv<<<grid, GEMV_WARPS * 32, 0, st>>>(ga);
-      ctx->launches++;
+      if (grid)
+        {
+          k_bem_gemv<<<grid, GEMV_WARPS * 32, 0, st>>>(ga);
+          ctx->launches++;
+        }
+      ctx->tm.gemv_bytes_last = 8.0 * 64.0 * (double)(n_o + n_s) * (double)ga.n_rows;
       ctx->timer.end();
     }
-  ctx->tm.gemv_bytes_last = 8.0 * 64.0 * (double)(n_o + n_s) * (double)ctx->nloc;
   if (ctx->p.world_size > 1) ctx->timer.begin(T_ALLGATHER);
   int rc = wbem_allgather_rows(ctx, ctx->d_yloc);
   if (ctx->p.world_size > 1) ctx->timer.end();
