@@ -52,5 +52,18 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     return LIB
 
 
+def build_cpp_test() -> str:
+    """Compile tests/cpp/host_mirror_test.cc (the C++ host mirror of BEMProblem<3>) against libwbem.so."""
+    build()
+    root = os.path.dirname(HERE)
+    src = os.path.join(root, "tests", "cpp", "host_mirror_test.cc")
+    exe = os.path.join(OUT, "host_mirror_test")
+    hdr = os.path.join(CSRC, "bem_problem_b200.h")
+    if _stale(exe, [src, hdr, LIB]):
+        subprocess.check_call([HOST_CXX, "-O2", "-std=c++17", src, "-o", exe, "-L", OUT, "-lwbem",
+                               "-Wl,-rpath,$ORIGIN"])
+    return exe
+
+
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))

@@ -1,0 +1,174 @@
+// bem_problem_b200.h -- header-only C++ host side above the C ABI (include/wbem.h).
+//
+// Mirrors the public interface of the reference's BEMProblem<3>
+// (include/bem_problem.h:87-180): reinit, assemble_system, compute_alpha, vmult, compute_rhs,
+// compute_constraints (taken as flattened lines), assemble_preconditioner, solve_system,
+// solve, residual -- same names, argument meaning and error behaviour (a GMRES that reaches
+// "Max steps" throws NoConvergence like deal.II's SolverControl; every other failure throws
+// std::runtime_error with wbem_last_error()).
+//
+// deal.II is not available in this image, so the role of ComputationalDomain<3> is played by
+// the plain struct FlatDomain below; INTEGRATION.md shows the 40-line adapter that fills it
+// from comp_dom.dh / mapping / double_nodes_set inside the real WaveBEM.
+#pragma once
+#include <cstdint>
+#include <stdexcept>
+#include <string>
+#include <vector>
+
+#include "../../include/wbem.h"
+
+namespace wbem
+{
+struct NoConvergence : public std::runtime_error
+{ // SolverControl::NoConvergence
+  unsigned int last_step;
+  double last_residual;
+  NoConvergence(unsigned int s, double r)
+    : std::runtime_error("GMRES did not converge"), last_step(s), last_residual(r)
+  {}
+};
+
+struct FlatDomain
+{ // what BEMProblem reads from ComputationalDomain<3> (source/bem_problem.cc:58, 117-120, 133,
+  // 169, 225, 643-644): dofs, cells, mapping (as support points), double nodes, masks
+  std::vector<double> support_points;     // [N][3]   DoFTools::map_dofs_to_support_points
+  std::vector<uint32_t> cell_dofs;        // [C][4]   cell->get_dof_indices, deal.II vertex order
+  std::vector<uint8_t> cell_direction;    // [C]      cell->direction_flag()
+  std::vector<uint32_t> dn_ptr, dn_idx;   // CSR      comp_dom.double_nodes_set
+  std::vector<double> surface_nodes, other_nodes; // [N]
+  unsigned int n_dofs() const { return (unsigned int)(support_points.size() / 3); }
+  unsigned int n_cells() const { return (unsigned int)(cell_dofs.size() / 4); }
+};
+
+struct ConstraintLines
+{ // flattened ConstraintMatrix (compute_constraints, source/bem_problem.cc:990-1105)
+  std::vector<uint32_t> lines, ptr{0}, col;
+  std::vector<double> val, inhom;
+};
+
+class BEMProblem
+{
+public:
+  explicit BEMProblem(FlatDomain &comp_dom, const wbem_params *params = nullptr) : comp_dom(comp_dom)
+  {
+    wbem_params p;
+    if (params)
+      p = *params;
+    else
+      wbem_default_params(&p);
+    if (wbem_create(&p, &ctx) != 0) throw std::runtime_error(std::string("wbem_create: ") + wbem_last_error(nullptr));
+  }
+  ~BEMProblem()
+  {
+    if (ctx) wbem_destroy(ctx);
+  }
+  BEMProblem(const BEMProblem &) = delete;
+  BEMProblem &operator=(const BEMProblem &) = delete;
+
+  // source/bem_problem.cc:55-71
+  void reinit()
+  {
+    check(wbem_set_topology(ctx, comp_dom.n_dofs(), comp_dom.n_cells(), comp_dom.cell_dofs.data(),
+                            comp_dom.cell_direction.data(), comp_dom.dn_ptr.data(), comp_dom.dn_idx.data()));
+    const unsigned int n = comp_dom.n_dofs();
+    system_rhs.assign(n, 0.0);
+    sol.assign(n, 0.0);
+    alpha.assign(n, 0.0);
+  }
+  // source/bem_problem.cc:106-590
+  void assemble_system()
+  {
+    check(wbem_set_geometry(ctx, comp_dom.support_points.data()));
+    check(wbem_assemble(ctx));
+    check(wbem_get_alpha(ctx, alpha.data()));
+  }
+  // source/bem_problem.cc:594-618
+  void compute_alpha()
+  {
+    check(wbem_compute_alpha(ctx));
+    check(wbem_get_alpha(ctx, alpha.data()));
+  }
+  // source/bem_problem.cc:620-670
+  void vmult(std::vector<double> &dst, const std::vector<double> &src)
+  {
+    masks();
+    dst.resize(src.size());
+    check(wbem_vmult(ctx, dst.data(), src.data()));
+  }
+  // source/bem_problem.cc:673-707
+  void compute_rhs(std::vector<double> &dst, const std::vector<double> &src)
+  {
+    masks();
+    dst.resize(src.size());
+    check(wbem_compute_rhs(ctx, dst.data(), src.data()));
+  }
+  // the ConstraintMatrix produced by the reference's own compute_constraints (host code)
+  void set_constraints(const ConstraintLines &c)
+  {
+    check(wbem_set_constraints(ctx, (uint32_t)c.lines.size(), c.lines.data(), c.ptr.data(), c.col.data(),
+                               c.val.data(), c.inhom.data()));
+  }
+  // source/bem_problem.cc:1107-1149
+  void assemble_preconditioner()
+  {
+    masks();
+    check(wbem_assemble_preconditioner(ctx));
+  }
+  // source/bem_problem.cc:821-895
+  void solve_system(std::vector<double> &phi, std::vector<double> &dphi_dn, const std::vector<double> &tmp_rhs)
+  {
+    masks();
+    int iters = 0;
+    double res = 0;
+    const int rc = wbem_solve_system(ctx, phi.data(), dphi_dn.data(), tmp_rhs.data(), &iters, &res);
+    finish(rc, iters, res);
+  }
+  // source/bem_problem.cc:969-987
+  void solve(std::vector<double> &phi, std::vector<double> &dphi_dn, const std::vector<double> &tmp_rhs)
+  {
+    masks();
+    int iters = 0;
+    double res = 0;
+    const int rc = wbem_solve(ctx, comp_dom.support_points.data(), phi.data(), dphi_dn.data(), tmp_rhs.data(),
+                              &iters, &res);
+    finish(rc, iters, res);
+  }
+  // source/bem_problem.cc:903-961
+  void residual(std::vector<double> &res, const std::vector<double> &phi, const std::vector<double> &dphi_dn)
+  {
+    masks();
+    res.resize(phi.size());
+    check(wbem_residual(ctx, res.data(), phi.data(), dphi_dn.data()));
+  }
+  // neumann_matrix(i, j) / dirichlet_matrix(i, j) rows (public members of the reference class)
+  void matrix_rows(int which, uint32_t r0, uint32_t r1, std::vector<double> &out)
+  {
+    out.resize((size_t)(r1 - r0) * comp_dom.n_dofs());
+    check(wbem_get_rows(ctx, which, r0, r1, out.data()));
+  }
+
+  FlatDomain &comp_dom;
+  std::vector<double> system_rhs, sol, alpha; // include/bem_problem.h:155-158
+  unsigned int last_step = 0;
+  double last_residual = 0;
+  wbem_ctx *ctx = nullptr;
+
+private:
+  void masks() { check(wbem_set_masks(ctx, comp_dom.surface_nodes.data(), comp_dom.other_nodes.data())); }
+  void check(int rc)
+  {
+    if (rc < 0) throw std::runtime_error(std::string("libwbem: ") + wbem_last_error(ctx));
+  }
+  void finish(int rc, int iters, double res)
+  {
+    check(rc);
+    last_step = (unsigned int)iters;
+    last_residual = res;
+    check(wbem_get_alpha(ctx, alpha.data()));
+    check(wbem_get_system_rhs(ctx, system_rhs.data()));
+    check(wbem_get_sol(ctx, sol.data()));
+    if (rc > 0) throw NoConvergence(last_step, last_residual);
+  }
+};
+} // namespace wbem
