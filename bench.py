@@ -166,6 +166,7 @@ def run_ours(args):
     ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=args.max_steps)
     ctx.set_topology(n, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
     wd.init_comm(ctx)
+    p2p = (not args.no_p2p) and wd.init_peer_gather(ctx)
     ctx.set_masks(m.surface_nodes, m.other_nodes)
     ctx.set_constraints(cl)
 
@@ -276,6 +277,8 @@ def run_ours(args):
                                    f"cells, Gauss 4x4 + QGaussOneOverR(5), GMRES tol {args.tol:g}/max {args.max_steps}, "
                                    "band-100 preconditioner",
                        "nodes": n, "cells": m.n_cells, "rows_per_gpu": nloc, "parallelism": f"rows/{world}",
+                       "gather": ("fused peer-to-peer stores in k_bem_gemv (CUDA IPC over NVLink)" if p2p else
+                                  ("ncclAllGather" if world > 1 else "none")),
                        "l2_policy": "inputs larger than L2 (both matrices, 16 N^2 bytes >> 126 MB)"},
             "gmres_iters": iters, "gmres_last_residual": res, "gmres_converged": rc == 0,
             "assembly_entries_per_s": entries / (acc["asm"] / K * 1e-3),
@@ -331,6 +334,7 @@ def main():
     ap.add_argument("--ref-slab-rows", type=int, default=1024)
     ap.add_argument("--ref-gmres-iters", type=int, default=100)
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-p2p", action="store_true", help="use ncclAllGather instead of the fused peer-to-peer gather")
     args = ap.parse_args()
     if args.impl == "reference":
         run_reference(args)

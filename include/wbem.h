@@ -158,6 +158,13 @@ int wbem_reset_counters(wbem_ctx *ctx);
  * ...) broadcasts it, every rank calls wbem_comm_init. */
 int wbem_comm_unique_id(void *id128);
 int wbem_comm_init(wbem_ctx *ctx, const void *id128);
+/* Optional, after every wbem_set_topology: CUDA-IPC exchange of the gather buffers.  Each rank
+ * exports 64 bytes, the launcher all-gathers them, each rank imports world_size*64 bytes.  With
+ * it the mat-vec kernel stores its result rows straight into every rank's gather buffer over
+ * NVLink (one fused kernel); without it each mat-vec is followed by ncclAllGather. */
+int wbem_comm_ipc_export(wbem_ctx *ctx, void *handle64);
+int wbem_comm_ipc_import(wbem_ctx *ctx, const void *handles);
+int wbem_comm_ipc_close(wbem_ctx *ctx); /* back to the ncclAllGather path */
 
 /* Diagnostics used by bench.py: measured FP64 FMA peak (TFLOP/s) and copy bandwidth (GB/s)
  * of this device; one operator application timed alone. */

@@ -11,6 +11,13 @@ python -c "import __graft_entry__ as g; g.build()" > $OUT/multi_build.log 2>&1
 echo "== pytest multi" | tee $OUT/multi_summary.log
 timeout 900 python -m pytest tests/test_gpu_multi.py -q -m gpu > $OUT/pytest_multi.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/multi_summary.log
 tail -15 $OUT/pytest_multi.log | tee -a $OUT/multi_summary.log
+if [ "$NG" != "1" ]; then
+  echo "== bench --gpus $NG --no-p2p (ncclAllGather)" | tee -a $OUT/multi_summary.log
+  NCCL_DEBUG=WARN timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $NG --master-addr 127.0.0.1 --master-port 29516 \
+      bench.py --gpus $NG --no-p2p > $OUT/bench_g${NG}_nccl.json 2> $OUT/bench_g${NG}_nccl.err
+  echo "rc=$?" | tee -a $OUT/multi_summary.log
+  tail -1 $OUT/bench_g${NG}_nccl.json | cut -c1-1500 | tee -a $OUT/multi_summary.log
+fi
 for n in 1 $NG; do
   echo "== bench --gpus $n" | tee -a $OUT/multi_summary.log
   if [ "$n" = "1" ]; then

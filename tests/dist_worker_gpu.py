@@ -29,6 +29,9 @@ def main():
     ctx.set_topology(m.n_nodes, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
     assert (ctx.row0, ctx.row1) == wd.row_block(m.n_nodes, rank, world)
     wd.init_comm(ctx)
+    use_p2p = len(sys.argv) > 2 and sys.argv[2] == "p2p"
+    if use_p2p:
+        assert wd.init_peer_gather(ctx), "CUDA IPC peer gather unavailable"
     ctx.set_geometry(m.xyz)
     ctx.assemble()
     ctx.set_masks(m.surface_nodes, m.other_nodes)

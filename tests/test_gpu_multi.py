@@ -11,7 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-def test_two_gpus_match_one(wb, tmp_path):
+@pytest.mark.parametrize("gather", ["nccl", "p2p"])
+def test_two_gpus_match_one(wb, tmp_path, gather):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -23,7 +24,7 @@ def test_two_gpus_match_one(wb, tmp_path):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "dist_worker_gpu.py"), str(tmp_path)]
+           os.path.join(ROOT, "tests", "dist_worker_gpu.py"), str(tmp_path), gather]
     subprocess.run(cmd, check=True, timeout=600)
     m = meshgen.wigley_tank(nxm=14, nt=6, nxu=5, nxd=7, nz=3, nzh=4)
     bc = meshgen.towing_tank_bc(m)

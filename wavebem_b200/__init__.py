@@ -74,7 +74,8 @@ ABI_SYMBOLS = [
     "wbem_get_system_rhs", "wbem_get_sol", "wbem_get_timings", "wbem_reset_counters",
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
-    "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe",
+    "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
+    "wbem_comm_ipc_close",
 ]
 
 
@@ -296,6 +297,18 @@ class Context:
     def comm_init(self, uid: bytes):
         assert len(uid) == 128
         self._chk(lib().wbem_comm_init(self._h, C.c_char_p(uid)))
+
+    def ipc_export(self) -> bytes:
+        buf = C.create_string_buffer(64)
+        self._chk(lib().wbem_comm_ipc_export(self._h, buf))
+        return buf.raw
+
+    def ipc_import(self, handles: bytes):
+        assert len(handles) == 64 * self.params.world_size
+        self._chk(lib().wbem_comm_ipc_import(self._h, C.c_char_p(handles)))
+
+    def ipc_close(self):
+        self._chk(lib().wbem_comm_ipc_close(self._h))
 
     # --- diagnostics ---
     def measure_fp64_peak(self):

@@ -162,8 +162,24 @@ int wbem_create(const wbem_params *p, wbem_ctx **out)
   return 0;
 }
 
+} // extern "C"
+void wbem_p2p_close(wbem_ctx *ctx)
+{
+  for (int q = 0; q < WBEM_MAX_PEERS; ++q)
+    {
+      if (ctx->peer_opened[q] && ctx->peer_base[q]) cudaIpcCloseMemHandle(ctx->peer_base[q]);
+      ctx->peer_opened[q] = false;
+      ctx->peer_base[q] = nullptr;
+    }
+  ctx->p2p_ready = false;
+}
+extern "C" {
+
 static void free_topology(wbem_ctx *ctx)
 {
+  wbem_p2p_close(ctx);
+  FREE_DEV(ctx->d_p2p);
+  FREE_DEV(ctx->d_done_counter);
   FREE_DEV(ctx->d_cell_dofs);
   FREE_DEV(ctx->d_dir);
   FREE_DEV(ctx->d_cell_order);
@@ -359,6 +375,16 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_alloc(ctx, &ctx->d_list_o, ld / 64))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_list_s, ld / 64))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_yloc, (size_t)ctx->chunk * P + 64))) return rc;
+  if (P > 1)
+    {
+      const size_t nd = 2 * (size_t)ctx->chunk * P + WBEM_MAX_PEERS;
+      if ((rc = dev_alloc(ctx, &ctx->d_p2p, nd))) return rc;
+      if ((rc = dev_alloc(ctx, &ctx->d_done_counter, 1))) return rc;
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_p2p, 0, sizeof(double) * nd, ctx->stream));
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_done_counter, 0, sizeof(unsigned long long), ctx->stream));
+      ctx->p2p_epoch = 0;
+      ctx->gemv_done_total = 0;
+    }
   for (auto &t : ctx->d_tmp)
     if ((rc = dev_alloc(ctx, &t, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_rhs, ld))) return rc;
@@ -858,6 +884,62 @@ int wbem_comm_unique_id(void *id128)
   if (rc) g_create_error = err;
   return rc;
 }
+// CUDA-IPC exchange of the gather buffers (after wbem_set_topology, on every rank):
+// export -> the launcher all-gathers the 64-byte handles -> import.  Enables the fused
+// GEMV + all-gather over NVLink peer memory; without it mat-vecs fall back to ncclAllGather.
+int wbem_comm_ipc_export(wbem_ctx *ctx, void *handle64)
+{
+  CHECK_CTX(ctx);
+  if (ctx->p.world_size <= 1 || !ctx->d_p2p) WBEM_FAIL(ctx, -3, "ipc_export needs world_size > 1 and wbem_set_topology");
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  cudaIpcMemHandle_t h;
+  CUDA_OK(ctx, cudaIpcGetMemHandle(&h, ctx->d_p2p));
+  static_assert(sizeof(h) == 64, "cudaIpcMemHandle_t is 64 bytes");
+  memcpy(handle64, &h, 64);
+  return 0;
+}
+int wbem_comm_ipc_import(wbem_ctx *ctx, const void *handles)
+{
+  CHECK_CTX(ctx);
+  const int P = ctx->p.world_size;
+  if (P <= 1 || !ctx->d_p2p) WBEM_FAIL(ctx, -3, "ipc_import needs world_size > 1 and wbem_set_topology");
+  if (P > WBEM_MAX_PEERS) WBEM_FAIL(ctx, -1, "at most %d ranks for the peer-to-peer gather", WBEM_MAX_PEERS);
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  wbem_p2p_close(ctx);
+  for (int q = 0; q < P; ++q)
+    {
+      if (q == ctx->p.rank)
+        {
+          ctx->peer_base[q] = ctx->d_p2p;
+          continue;
+        }
+      cudaIpcMemHandle_t h;
+      memcpy(&h, (const char *)handles + 64 * (size_t)q, 64);
+      void *ptr = nullptr;
+      cudaError_t e = cudaIpcOpenMemHandle(&ptr, h, cudaIpcMemLazyEnablePeerAccess);
+      if (e != cudaSuccess)
+        {
+          cudaGetLastError();
+          wbem_p2p_close(ctx);
+          WBEM_FAIL(ctx, -5, "cudaIpcOpenMemHandle(rank %d): %s", q, cudaGetErrorString(e));
+        }
+      ctx->peer_base[q] = (double *)ptr;
+      ctx->peer_opened[q] = true;
+    }
+  ctx->p2p_ready = true;
+  return 0;
+}
+
+int wbem_comm_ipc_close(wbem_ctx *ctx)
+{
+  CHECK_CTX(ctx);
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  wbem_p2p_close(ctx);
+  return 0;
+}
+
 int wbem_comm_init(wbem_ctx *ctx, const void *id128)
 {
   CHECK_CTX(ctx);

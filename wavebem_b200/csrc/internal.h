@@ -9,6 +9,7 @@
 
 #define WBEM_MAX_NQ 64   // regular rule: up to 8 x 8
 #define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
+#define WBEM_MAX_PEERS 16
 #define WBEM_TILE_ROWS 128 // rows per CTA of the tiled regular-pair kernel
 
 struct QuadTables
@@ -188,6 +189,14 @@ struct wbem_ctx
   // comm
   NcclApi *nccl = nullptr;
   void *nccl_comm = nullptr;
+  // peer-to-peer gather fused into k_bem_gemv: every rank's gather buffer mapped through
+  // CUDA IPC.  d_p2p = [2][chunk*P] doubles (double-buffered by epoch) + WBEM_MAX_PEERS flags
+  double *d_p2p = nullptr;
+  double *peer_base[WBEM_MAX_PEERS] = {};
+  bool peer_opened[WBEM_MAX_PEERS] = {};
+  bool p2p_ready = false;
+  unsigned long long p2p_epoch = 0, gemv_done_total = 0;
+  unsigned long long *d_done_counter = nullptr;
 
   wbem_timings tm = {};
   long long launches = 0;
@@ -232,6 +241,8 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn,
 int wbem_device_precond_factor(wbem_ctx *ctx);
 int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out);
 void wbem_device_precond_free(wbem_ctx *ctx);
+// api.cu
+void wbem_p2p_close(wbem_ctx *ctx);
 // comm.cpp
 int wbem_nccl_unique_id(void *id128, std::string *err);
 int wbem_nccl_init(wbem_ctx *ctx, const void *id128);

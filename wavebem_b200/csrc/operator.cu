@@ -24,10 +24,10 @@ __device__ __forceinline__ double2 ld_stream(const double *p)
   return r;
 }
 
-// acc[r] += sum over the listed 64-column chunks of M[row0+r, :] . x   (NR rows per pass:
-// the x chunk is loaded once and reused for NR streamed 128-bit matrix loads per lane; two
-// chunks are in flight per iteration)
-template <int NR>
+// acc[r] += sum over the listed 64-column chunks of M[rows[r], :] . x.  NR rows share every x
+// chunk; NC chunks are in flight per iteration, NR * NC ~ 8..10 independent 128-bit loads per
+// lane whatever the number of rows a warp owns (few rows per warp on row-sharded runs).
+template <int NR, int NC>
 __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const double *__restrict__ x,
                                           const uint32_t *__restrict__ list, int n, uint32_t ld,
                                           const uint32_t rows[GEMV_MAXR], int lane, double acc[GEMV_MAXR])
@@ -36,28 +36,29 @@ __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const do
 #pragma unroll
   for (int r = 0; r < NR; ++r) base[r] = M + (size_t)rows[r] * ld + lane * 2;
   int i = 0;
-  for (; i + 1 < n; i += 2)
+  for (; i + NC <= n; i += NC)
     {
-      const uint32_t c0 = list[i] * 64, c1 = list[i + 1] * 64;
-      double2 m0[NR], m1[NR];
+      uint32_t c[NC];
 #pragma unroll
-      for (int r = 0; r < NR; ++r)
-        {
-          m0[r] = ld_stream(base[r] + c0);
-          m1[r] = ld_stream(base[r] + c1);
-        }
-      const double2 x0 = *reinterpret_cast<const double2 *>(x + c0 + lane * 2);
-      const double2 x1 = *reinterpret_cast<const double2 *>(x + c1 + lane * 2);
+      for (int k = 0; k < NC; ++k) c[k] = list[i + k] * 64;
+      double2 m[NC][NR];
 #pragma unroll
-      for (int r = 0; r < NR; ++r)
-        {
-          acc[r] = fma(m0[r].x, x0.x, acc[r]);
-          acc[r] = fma(m0[r].y, x0.y, acc[r]);
-          acc[r] = fma(m1[r].x, x1.x, acc[r]);
-          acc[r] = fma(m1[r].y, x1.y, acc[r]);
-        }
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) m[k][r] = ld_stream(base[r] + c[k]);
+      double2 xv[NC];
+#pragma unroll
+      for (int k = 0; k < NC; ++k) xv[k] = *reinterpret_cast<const double2 *>(x + c[k] + lane * 2);
+#pragma unroll
+      for (int k = 0; k < NC; ++k)
+#pragma unroll
+        for (int r = 0; r < NR; ++r)
+          {
+            acc[r] = fma(m[k][r].x, xv[k].x, acc[r]);
+            acc[r] = fma(m[k][r].y, xv[k].y, acc[r]);
+          }
     }
-  if (i < n)
+  for (; i < n; ++i)
     {
       const uint32_t c0 = list[i] * 64;
       const double2 x0 = *reinterpret_cast<const double2 *>(x + c0 + lane * 2);
@@ -81,9 +82,16 @@ struct GemvArgs
   const uint32_t *row_list; // local rows to compute (constrained rows are skipped), or null
   uint32_t n_rows;          // entries of row_list (= nloc when null)
   double *y;
+  // fused all-gather over NVLink peer memory (n_peers > 1): every result row is stored straight
+  // into the gather buffer of every rank; the last CTA to finish raises this rank's flag there
+  int n_peers, rank;
+  double *peer_base[WBEM_MAX_PEERS];
+  size_t buf_off, flag_off; // in doubles from peer_base: this epoch's buffer / the flag array
+  unsigned long long epoch, done_target;
+  unsigned long long *done_counter;
 };
 
-template <int NR>
+template <int NR, int NC>
 __device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int lane)
 {
   double a1[GEMV_MAXR], a2[GEMV_MAXR];
@@ -92,19 +100,22 @@ __device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int la
   uint32_t rows[GEMV_MAXR];
 #pragma unroll
   for (int r = 0; r < NR; ++r) rows[r] = a.row_list ? a.row_list[r0 + r] : r0 + r;
-  gemv_pass<NR>(a.M1, a.x1, a.list1, a.n1, a.ld, rows, lane, a1);
-  gemv_pass<NR>(a.M2, a.x2, a.list2, a.n2, a.ld, rows, lane, a2);
+  gemv_pass<NR, NC>(a.M1, a.x1, a.list1, a.n1, a.ld, rows, lane, a1);
+  gemv_pass<NR, NC>(a.M2, a.x2, a.list2, a.n2, a.ld, rows, lane, a2);
 #pragma unroll
   for (int r = 0; r < NR; ++r)
     {
       double v = a.s1 * a1[r] + a.s2 * a2[r];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      if (lane == 0)
+      const uint32_t g = a.row0 + rows[r];
+      v += a.sdiag * a.alpha[g] * a.xdiag[g];
+      if (a.n_peers > 1)
         {
-          const uint32_t g = a.row0 + rows[r];
-          a.y[rows[r]] = v + a.sdiag * a.alpha[g] * a.xdiag[g];
+          if (lane < a.n_peers) a.peer_base[lane][a.buf_off + g] = v; // lane q -> rank q (NVLink store)
         }
+      else if (lane == 0)
+        a.y[rows[r]] = v;
     }
 }
 
@@ -127,13 +138,32 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
       const uint32_t take = (left + passes - 1) / passes;
       switch (take)
         {
-        case 1: gemv_rows<1>(a, r0, lane); break;
-        case 2: gemv_rows<2>(a, r0, lane); break;
-        case 3: gemv_rows<3>(a, r0, lane); break;
-        case 4: gemv_rows<4>(a, r0, lane); break;
-        default: gemv_rows<5>(a, r0, lane); break;
+        case 1: gemv_rows<1, 8>(a, r0, lane); break;
+        case 2: gemv_rows<2, 4>(a, r0, lane); break;
+        case 3: gemv_rows<3, 3>(a, r0, lane); break;
+        case 4: gemv_rows<4, 2>(a, r0, lane); break;
+        default: gemv_rows<5, 2>(a, r0, lane); break;
         }
       r0 += take;
+    }
+  if (a.n_peers > 1)
+    { // completion: the last CTA of this launch publishes "rank's rows of epoch e are in place"
+      __shared__ bool s_last;
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          __threadfence_system();
+          const unsigned long long prev = atomicAdd(a.done_counter, 1ull);
+          s_last = (prev + 1ull == a.done_target);
+        }
+      __syncthreads();
+      if (s_last && threadIdx.x < a.n_peers)
+        {
+          __threadfence_system();
+          unsigned long long *flag =
+            reinterpret_cast<unsigned long long *>(a.peer_base[threadIdx.x] + a.flag_off) + a.rank;
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.epoch) : "memory");
+        }
     }
 }
 
@@ -154,11 +184,25 @@ __global__ void k_prep_multipliers(uint32_t N, const double *__restrict__ src,
 }
 
 // dst = gathered rows, with constrained rows replaced by src_i - sum c_ik src_k
-__global__ void k_epilogue(uint32_t N, const double *__restrict__ y, const double *__restrict__ src,
+__global__ void k_epilogue(uint32_t N, const double *y, const double *__restrict__ src,
                            const int32_t *__restrict__ line_of, const uint32_t *__restrict__ cptr,
                            const uint32_t *__restrict__ ccol, const double *__restrict__ cval,
-                           double shift, double *__restrict__ dst)
+                           double shift, double *__restrict__ dst, const unsigned long long *flags, int n_peers,
+                           unsigned long long epoch)
 {
+  if (flags)
+    { // fused gather: wait until every rank has raised its flag for this epoch
+      if (threadIdx.x < n_peers)
+        {
+          unsigned long long v;
+          do
+            {
+              asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+            }
+          while (v < epoch);
+        }
+      __syncthreads();
+    }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double v = y[i] + shift;
@@ -232,7 +276,12 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
                                                      ctx->d_xd, ctx->d_xdiag);
   ctx->launches++;
   double *yloc = ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk;
-  if (ctx->nloc)
+  const int P = ctx->p.world_size;
+  const bool use_p2p = P > 1 && ctx->p2p_ready && !((mode == 0) && ctx->pure_neumann);
+  const size_t p2p_len = (size_t)ctx->chunk * P;
+  if (use_p2p) ctx->p2p_epoch++;
+  const double *ygather = use_p2p ? ctx->d_p2p + (ctx->p2p_epoch & 1ull) * p2p_len : ctx->d_yloc;
+  if (ctx->nloc || use_p2p)
     {
       ctx->timer.begin(T_GEMV);
       static int ctas_per_sm = 0, n_sm = 0;
@@ -274,6 +323,20 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
       const uint32_t max_useful = (ga.n_rows + GEMV_WARPS - 1) / GEMV_WARPS; // >= 1 row per warp
       if (ga.n_rows == 0) grid = 0;
       if (grid > max_useful) grid = max_useful;
+      ga.n_peers = 1;
+      ga.rank = ctx->p.rank;
+      if (use_p2p)
+        {
+          if (grid == 0) grid = 1; // a rank without rows still has to raise its flag
+          ga.n_peers = P;
+          for (int q = 0; q < P; ++q) ga.peer_base[q] = ctx->peer_base[q];
+          ga.buf_off = (ctx->p2p_epoch & 1ull) * p2p_len;
+          ga.flag_off = 2 * p2p_len;
+          ga.epoch = ctx->p2p_epoch;
+          ctx->gemv_done_total += grid;
+          ga.done_target = ctx->gemv_done_total;
+          ga.done_counter = ctx->d_done_counter;
+        }
       if (grid)
         {
           k_bem_gemv<<<grid, GEMV_WARPS * 32, 0, st>>>(ga);
@@ -282,10 +345,13 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
       ctx->tm.gemv_bytes_last = 8.0 * 64.0 * (double)(n_o + n_s) * (double)ga.n_rows;
       ctx->timer.end();
     }
-  if (ctx->p.world_size > 1) ctx->timer.begin(T_ALLGATHER);
-  int rc = wbem_allgather_rows(ctx, ctx->d_yloc);
-  if (ctx->p.world_size > 1) ctx->timer.end();
-  if (rc) return rc;
+  if (P > 1 && !use_p2p)
+    {
+      ctx->timer.begin(T_ALLGATHER);
+      int rc = wbem_allgather_rows(ctx, ctx->d_yloc);
+      ctx->timer.end();
+      if (rc) return rc;
+    }
   const bool shift = (mode == 0) && ctx->pure_neumann;
   if (shift)
     {
@@ -295,9 +361,9 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
       ctx->launches++;
     }
   const bool con = constrained && ctx->n_lines > 0;
-  k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->d_yloc, d_src, con ? ctx->d_con_line_of : nullptr,
-                                             ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0,
-                                             d_dst);
+  k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(
+    N, ygather, d_src, con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0, d_dst,
+    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_len) : nullptr, P, ctx->p2p_epoch);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return 0;

@@ -46,6 +46,42 @@ def init_comm(ctx):
     ctx.comm_init(uid)
 
 
+def init_peer_gather(ctx) -> bool:
+    """After ctx.set_topology on every rank: exchange CUDA-IPC handles of the gather buffers so
+    that the mat-vec kernel writes its rows straight into every peer (fused GEMV + all-gather).
+    Returns False (and leaves the NCCL all-gather path active) when IPC is unavailable."""
+    import torch
+    import torch.distributed as dist
+    if ctx.params.world_size <= 1:
+        return False
+    world = dist.get_world_size()
+    ok = 1
+    try:
+        mine = ctx.ipc_export()
+    except Exception:
+        mine, ok = bytes(64), 0
+    dev = "cuda" if dist.get_backend() == "nccl" else "cpu"
+    t = torch.frombuffer(bytearray(mine), dtype=torch.uint8).to(dev)
+    out = [torch.empty_like(t) for _ in range(world)]
+    dist.all_gather(out, t)
+    flag = torch.tensor([ok], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        return False
+    handles = b"".join(bytes(o.cpu().numpy().tobytes()) for o in out)
+    try:
+        ctx.ipc_import(handles)
+        ok = 1
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], device=dev)
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        ctx.ipc_close()   # some rank failed: nobody may use the peer path
+        return False
+    return True
+
+
 def allgather_rows(local: np.ndarray, n: int) -> np.ndarray:
     """Host-side gather of per-rank row blocks (tests / diagnostics): (row1-row0, ...) -> (n, ...)."""
     import torch
