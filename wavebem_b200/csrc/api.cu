@@ -282,7 +282,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
       for (int i = 0; i < j; ++i)
         if (cell_dofs[4 * (size_t)c + i] == cell_dofs[4 * (size_t)c + j]) ctx->has_degenerate_cells = true;
   // tiling plan (plan.cpp); W and the cell cap match k_assemble_tiled's shared-memory tile
-  int rc = wbem_build_plan(N, C, cell_dofs, 48, 64, &ctx->plan);
+  int rc = wbem_build_plan(N, C, cell_dofs, WBEM_TILE_W, 64, &ctx->plan);
   if (rc) WBEM_FAIL(ctx, -1, "wbem_build_plan failed (%d): cell dof out of range?", rc);
   const AssemblyPlan &pl = ctx->plan;
 

@@ -212,11 +212,13 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // ---------------------------------------------------------------------------------------
 #define TILE_ROWS WBEM_TILE_ROWS          // 128
 #define TILE_THREADS (2 * TILE_ROWS)      // 256
-#define TILE_W 48
+#define TILE_W WBEM_TILE_W
 #define TILE_MAX_CELLS 64                 // bit mask of singular cells is 64 bits wide
 #define TILE_CHUNK 8
 #define ACC_STRIDE (TILE_ROWS + 1)
-#define ACC_MATOFF (TILE_W * ACC_STRIDE + 8) // +8 doubles: the two matrices hit disjoint banks
+// offset between the two matrices' accumulators: = 8 (mod 16) doubles, so that the N-thread and
+// the D-thread of a row hit disjoint shared-memory banks
+#define ACC_MATOFF (TILE_W * ACC_STRIDE + ((8 - (TILE_W * ACC_STRIDE) % 16) + 16) % 16)
 
 struct TiledArgs
 {
@@ -236,7 +238,14 @@ constexpr size_t tiled_smem_bytes()
          TILE_W * 4;
 }
 
-__global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledArgs a)
+#define TILE_BLOCK (TILE_THREADS + 32) // + one producer warp that only drives the TMA pipeline
+
+__device__ __forceinline__ void consumer_barrier()
+{ // named barrier 1: the TILE_THREADS consumer threads only
+  asm volatile("bar.sync 1, %0;" ::"n"(TILE_THREADS) : "memory");
+}
+
+__global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *acc = reinterpret_cast<double *>(smem_raw);              // [2][ACC_MATOFF]
@@ -271,10 +280,21 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
     bulk_copy_g2s(geo + (c & 1) * TILE_CHUNK * 112, a.geo + ((size_t)p0 + (size_t)c * TILE_CHUNK) * 112, bytes,
                   &bar[c & 1]);
   };
-  if (tid == 0)
-    {
-      issue_chunk(0);
-      if (nchunk > 1) issue_chunk(1);
+  if (tid >= TILE_THREADS)
+    { // producer warp: fill the two buffers, then refill each one as soon as all consumer
+      // warps have released it ("empty" barrier); consumers never meet a CTA-wide barrier
+      // inside the integration loop
+      if (tid == TILE_THREADS)
+        {
+          issue_chunk(0);
+          if (nchunk > 1) issue_chunk(1);
+          for (int c = 2; c < nchunk; ++c)
+            {
+              mbar_wait(&bar[2 + (c & 1)], ((c - 2) >> 1) & 1);
+              issue_chunk(c);
+            }
+        }
+      return;
     }
   // singular cells of this row inside the cluster -> bit mask (they are integrated by
   // k_assemble_singular only, reference :241/:261).  Most (row tile, cluster) pairs hold no
@@ -302,7 +322,7 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
   // zero the accumulators in use: thread (row, h) clears matrix h of its row
   double *accM = acc + h * ACC_MATOFF + row_l;
   for (int s = 0; s < nslot; ++s) accM[s * ACC_STRIDE] = 0.0;
-  __syncthreads();
+  consumer_barrier();
 
   const double vq0 = c_qt.g1_x[2 * h], vq1 = c_qt.g1_x[2 * h + 1];
   for (int c = 0; c < nchunk; ++c)
@@ -395,9 +415,13 @@ __global__ void __launch_bounds__(TILE_THREADS, 2) k_assemble_tiled(const TiledA
               *pd = od + v3;
             }
         }
-      __syncthreads(); // every thread is done with this geometry buffer
-      if (tid == 0 && c + 2 < nchunk) issue_chunk(c + 2);
+      if (c + 2 < nchunk)
+        { // release this geometry buffer to the producer warp
+          __syncwarp();
+          if ((tid & 31) == 0) mbar_arrive(&bar[2 + (c & 1)]);
+        }
     }
+  consumer_barrier();
 
   // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
   // slots (coalesced row segments), 8 rows per lane in flight.
@@ -683,7 +707,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
           if (nclu == 0) continue;
           a.cluster_base = pl.color_ptr[c];
           dim3 grid(nclu, row_tiles);
-          k_assemble_tiled<<<grid, TILE_THREADS, tiled_smem_bytes(), st>>>(a);
+          k_assemble_tiled<<<grid, TILE_BLOCK, tiled_smem_bytes(), st>>>(a);
           ctx->launches++;
         }
       CUDA_OK(ctx, cudaGetLastError());

@@ -10,7 +10,8 @@
 #define WBEM_MAX_NQ 64   // regular rule: up to 8 x 8
 #define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
 #define WBEM_MAX_PEERS 16
-#define WBEM_TILE_ROWS 128 // rows per CTA of the tiled regular-pair kernel
+#define WBEM_TILE_W 56      // column slots (dofs) per cell cluster
+#define WBEM_TILE_ROWS 64 // rows per CTA of the tiled regular-pair kernel
 
 struct QuadTables
 { // host copies of the reference-cell tables (uploaded to __constant__ memory)
