@@ -358,3 +358,80 @@ def test_pure_neumann_with_constraints(wb, orc):
     ref = orc.constrained_vmult(on, od, alpha, s, o, _orc_con(orc, cl), x)
     assert np.abs(ctx.constrained_vmult(x) - ref).max() < 1e-12 * max(1.0, np.abs(ref).max())
     ctx.close()
+
+
+@pytest.mark.parametrize("n_tmp,band", [(12, 100), (100, 0), (30, 40)])
+def test_gmres_restart_and_preconditioner_options(wb, orc, tank_case, n_tmp, band):
+    """Short restart cycles (AdditionalData(n_tmp)) and other band widths, incl. no preconditioner."""
+    t = tank_case
+    m = t["m"]
+    n = m.n_nodes
+    tol, steps = 1e-9, 3000
+    ctx = _ctx(wb, m, gmres_tol=tol, gmres_max_steps=steps, gmres_n_tmp_vectors=n_tmp, preconditioner_band=band)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(t["cl"])
+    z = np.zeros(n)
+    try:
+        phi, dphi, it, res = ctx.solve_system(z, z, t["bc"])
+        conv = True
+    except wb.NoConvergence:
+        conv = False
+    ref = orc.solve_system(t["on"], t["od"], m.surface_nodes, m.other_nodes, t["bc"], t["con"], z, z, tol=tol,
+                           max_steps=steps, n_tmp_vectors=n_tmp, band=max(band, 2), use_precond=band > 0)
+    assert conv == ref["converged"]
+    if conv:
+        assert abs(it - ref["iters"]) <= max(5, ref["iters"] // 5)
+        assert np.linalg.norm(ctx.get_sol() - ref["sol"]) <= 1e-6 * np.linalg.norm(ref["sol"])
+    ctx.close()
+
+
+def test_tiny_and_ragged_sizes(wb, orc):
+    """N far below one tile / one 64-block, N not a multiple of anything, a single cell."""
+    xyz = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0.3]], dtype=float)
+    cells = np.array([[0, 1, 2, 3]], dtype=np.uint32)
+    ptr, idx = np.arange(5, dtype=np.uint32), np.arange(4, dtype=np.uint32)
+    ctx = wb.Context()
+    ctx.set_topology(4, cells, np.ones(1, np.uint8), ptr, idx)
+    ctx.set_geometry(xyz)
+    ctx.assemble()
+    on, od = orc.assemble_rows(xyz, cells, np.ones(1, np.uint8), ptr, idx)
+    assert rel_err_rowscaled(ctx.get_rows(0), on, diag=np.ones(4)) < ENTRY_TOL
+    assert rel_err_rowscaled(ctx.get_rows(1), od) < ENTRY_TOL
+    ctx.close()
+    for make in (lambda: meshgen.cube(2), lambda: meshgen.sphere(3), lambda: meshgen.wigley_tank(nxm=7, nt=3, nxu=2, nxd=3, nz=2, nzh=2)):
+        m = make()
+        bc, nn, cl = make_problem(m, bc=np.cos(np.arange(m.n_nodes) * 0.4)) if m.surface_nodes is not None else (None, None, None)
+        s = m.surface_nodes if m.surface_nodes is not None else (m.node_patch == 0).astype(float)
+        o = 1.0 - s
+        if cl is None:
+            from wavebem_b200.constraints import compute_constraints
+            bc = np.cos(np.arange(m.n_nodes) * 0.4)
+            cl = compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=meshgen.cell_normals_at_nodes(m))
+        ctx = _ctx(wb, m, gmres_tol=1e-11, gmres_max_steps=500)
+        ctx.assemble()
+        ctx.set_masks(s, o)
+        ctx.set_constraints(cl)
+        on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+        z = np.zeros(m.n_nodes)
+        _, _, it, _ = ctx.solve_system(z, z, bc)
+        ref = orc.solve_system(on, od, s, o, bc, _orc_con(orc, cl), z, z, tol=1e-11, max_steps=500)
+        assert np.linalg.norm(ctx.get_sol() - ref["sol"]) <= 1e-8 * max(1.0, np.linalg.norm(ref["sol"]))
+        ctx.close()
+
+
+def test_reinit_with_another_mesh_and_moving_geometry(wb, orc):
+    """reinit() after a remesh (free_surface.cc:1674) and re-assembly after the nodes moved
+    (free_surface.cc:5306-5307) on the same context."""
+    ctx = wb.Context()
+    for m in (meshgen.cube(3), meshgen.wigley_tank(nxm=10, nt=5, nxu=4, nxd=5, nz=3, nzh=3)):
+        ctx.set_topology(m.n_nodes, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+        for amp in (0.0, 0.03):
+            xyz = m.xyz.copy()
+            xyz[:, 2] += amp * np.sin(xyz[:, 0]) * np.cos(xyz[:, 1])
+            ctx.set_geometry(xyz)
+            ctx.assemble()
+            on, od = orc.assemble_rows(xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+            assert rel_err_rowscaled(ctx.get_rows(0), on, diag=orc.compute_alpha(on)) < ENTRY_TOL
+            assert rel_err_rowscaled(ctx.get_rows(1), od) < ENTRY_TOL
+    ctx.close()
