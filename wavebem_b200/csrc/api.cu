@@ -390,7 +390,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_alloc(ctx, &ctx->d_rhs, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_sol, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_V, (size_t)(ntmp - 1) * ld))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_h, 2048 + 128 + (size_t)(N + 255) / 256 + 64))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_h, 2048 + 128 + (size_t)(N + 127) / 128 + 64))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_band, (size_t)ctx->chunk * P * band))) return rc;
   CUDA_OK(ctx, cudaMemsetAsync(ctx->d_xn, 0, sizeof(double) * ld, ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->d_xd, 0, sizeof(double) * ld, ctx->stream));

@@ -57,13 +57,13 @@ __global__ void __launch_bounds__(256)
 
 // h[i] = sum_seg partial ; w -= sum_i h[i] V[i] ; hacc[i] (+)= h[i] (block 0) ;
 // nrm2[blockIdx.x] = sum over this CTA's entries of w_j^2 (after the update)
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(128)
   k_project_out(uint32_t N, int k, const double *__restrict__ V, size_t ldv,
                 const double *__restrict__ partial, double *__restrict__ w, double *__restrict__ hacc,
                 int accumulate, double *__restrict__ nrm2)
 {
   extern __shared__ double sh[];
-  __shared__ double red[8];
+  __shared__ double red[4];
   for (int i = threadIdx.x; i < k; i += blockDim.x)
     {
       double t = 0;
@@ -76,8 +76,26 @@ __global__ void __launch_bounds__(256)
   double s = 0.0;
   if (j < N)
     {
-      s = w[j];
-      for (int i = 0; i < k; ++i) s = fma(-sh[i], V[(size_t)i * ldv + j], s);
+      // four independent partial sums: the k loads per element are issued in batches of 8
+      double p0 = 0, p1 = 0, p2 = 0, p3 = 0;
+      const double *vj = V + j;
+      int i = 0;
+      for (; i + 8 <= k; i += 8)
+        {
+          double v[8];
+#pragma unroll
+          for (int u = 0; u < 8; ++u) v[u] = vj[(size_t)(i + u) * ldv];
+          p0 = fma(sh[i + 0], v[0], p0);
+          p1 = fma(sh[i + 1], v[1], p1);
+          p2 = fma(sh[i + 2], v[2], p2);
+          p3 = fma(sh[i + 3], v[3], p3);
+          p0 = fma(sh[i + 4], v[4], p0);
+          p1 = fma(sh[i + 5], v[5], p1);
+          p2 = fma(sh[i + 6], v[6], p2);
+          p3 = fma(sh[i + 7], v[7], p3);
+        }
+      for (; i < k; ++i) p0 = fma(sh[i], vj[(size_t)i * ldv], p0);
+      s = w[j] - ((p0 + p1) + (p2 + p3));
       w[j] = s;
     }
   if (blockIdx.x == 0 && hacc)
@@ -91,7 +109,7 @@ __global__ void __launch_bounds__(256)
     {
       double t = 0;
 #pragma unroll
-      for (int kk = 0; kk < 8; ++kk) t += red[kk];
+      for (int kk = 0; kk < 4; ++kk) t += red[kk];
       nrm2[blockIdx.x] = t;
     }
 }
@@ -381,7 +399,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
 {
   cudaStream_t st = ctx->stream;
   const uint32_t N = ctx->N;
-  const unsigned nb = (N + 255) / 256;
+  const unsigned nb = (N + 255) / 256, nb128 = (N + 127) / 128;
   if (!ctx->assembled) WBEM_FAIL(ctx, -3, "solve_system before assemble_system");
   if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "solve_system before wbem_set_masks");
   EvTimer &g_timer = ctx->timer;
@@ -479,16 +497,16 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
           for (int pass = 0; pass < 2; ++pass)
             {
               k_dots<<<dim3(dim, DOT_SEGS), 256, 0, st>>>(N, V, ldv, vv, d_part);
-              k_project_out<<<nb, 256, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_part, vv, d_hacc, pass,
-                                                                  d_hacc + 128);
+              k_project_out<<<nb128, 128, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_part, vv, d_hacc, pass,
+                                                                     d_hacc + 128);
               ctx->launches += 2;
             }
           // one D2H: accumulated h[0..dim) and the per-CTA sums of squares of the new vector
-          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_hacc, sizeof(double) * (128 + nb), cudaMemcpyDeviceToHost, st));
+          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_hacc, sizeof(double) * (128 + nb128), cudaMemcpyDeviceToHost, st));
           CUDA_OK(ctx, cudaStreamSynchronize(st));
           for (int i = 0; i < dim; ++i) h[i] = hp[i];
           double ss = 0;
-          for (unsigned i = 0; i < nb; ++i) ss += hp[128 + i];
+          for (unsigned i = 0; i < nb128; ++i) ss += hp[128 + i];
           h[dim] = std::sqrt(ss);
           const double s = h[dim];
           k_scale<<<nb, 256, 0, st>>>(N, vv, 1.0 / s);

@@ -408,7 +408,7 @@ struct BcrSolveArgs
     *uT[BCR_MAX_LEVELS];
   const double *lastT;
   const double *in;
-  double *out, *w;
+  double *out; // also the work array: must hold K*64 doubles
   unsigned int *barrier; // zeroed before every launch
 };
 
@@ -437,11 +437,18 @@ __global__ void __launch_bounds__(256, 1) k_bcr_solve_fused(const BcrSolveArgs a
   __shared__ double vl[BS], vr[BS], rhs[BS], part[4][BS];
   unsigned int epoch = 0;
   const int r = threadIdx.x & 63, part_id = threadIdx.x >> 6;
-  double *w = a.w;
-  const uint32_t Np = a.K * BS;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < Np; i += gridDim.x * blockDim.x)
-    w[i] = i < a.N ? a.in[i] : 0.0;
-  grid_barrier(a.barrier, epoch);
+  // The output vector doubles as the work array (every caller's buffer holds K*64 doubles);
+  // level 0 reads the input directly, so there is no separate copy-in pass or barrier.
+  double *w = a.out;
+  auto in_val = [&](size_t blk, int r) -> double {
+    const size_t g = blk * BS + r;
+    return g < a.N ? a.in[g] : 0.0;
+  };
+  if (a.nlev == 0)
+    {
+      if (blockIdx.x == 0 && threadIdx.x < BS) w[r] = in_val(0, r);
+      __syncthreads();
+    }
   // forward reduction of the right-hand side
   for (uint32_t l = 0; l < a.nlev; ++l)
     {
@@ -450,8 +457,23 @@ __global__ void __launch_bounds__(256, 1) k_bcr_solve_fused(const BcrSolveArgs a
         {
           const uint32_t q = 2 * t;
           const bool has_l = q >= 1, has_r = q + 1 < n;
-          if (threadIdx.x < BS) vl[r] = has_l ? w[((size_t)(q - 1) << l) * BS + r] : 0.0;
-          else if (threadIdx.x < 2 * BS) vr[r] = has_r ? w[((size_t)(q + 1) << l) * BS + r] : 0.0;
+          double own = 0.0;
+          if (l == 0)
+            {
+              if (threadIdx.x < BS) vl[r] = has_l ? in_val(q - 1, r) : 0.0;
+              else if (threadIdx.x < 2 * BS)
+                {
+                  vr[r] = has_r ? in_val(q + 1, r) : 0.0;
+                  if (has_r) w[(size_t)(q + 1) * BS + r] = vr[r]; // odd blocks: plain copy
+                }
+              if (threadIdx.x < BS) own = in_val(q, r);
+            }
+          else
+            {
+              if (threadIdx.x < BS) vl[r] = has_l ? w[((size_t)(q - 1) << l) * BS + r] : 0.0;
+              else if (threadIdx.x < 2 * BS) vr[r] = has_r ? w[((size_t)(q + 1) << l) * BS + r] : 0.0;
+              if (threadIdx.x < BS) own = w[((size_t)q << l) * BS + r];
+            }
           __syncthreads();
           double s = 0.0;
           if (part_id < 2)
@@ -463,10 +485,7 @@ __global__ void __launch_bounds__(256, 1) k_bcr_solve_fused(const BcrSolveArgs a
           part[part_id][r] = s;
           __syncthreads();
           if (threadIdx.x < BS)
-            {
-              double *dst = w + ((size_t)q << l) * BS + r;
-              *dst = *dst - ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r]));
-            }
+            w[((size_t)q << l) * BS + r] = own - ((part[0][r] + part[1][r]) + (part[2][r] + part[3][r]));
           __syncthreads();
         }
       grid_barrier(a.barrier, epoch);
@@ -505,9 +524,8 @@ __global__ void __launch_bounds__(256, 1) k_bcr_solve_fused(const BcrSolveArgs a
           if (threadIdx.x < BS) dst[r] = part[0][r] + part[1][r];
           __syncthreads();
         }
-      grid_barrier(a.barrier, epoch);
+      if (l > 0) grid_barrier(a.barrier, epoch);
     }
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < a.N; i += gridDim.x * blockDim.x) a.out[i] = w[i];
 }
 
 // ---------------------------------------------------------------------------------------
@@ -636,7 +654,6 @@ int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out)
       a.lastT = dp->pool + dp->off_last * BS2;
       a.in = d_in;
       a.out = d_out;
-      a.w = dp->work;
       a.barrier = dp->barrier;
       CUDA_OK(ctx, cudaMemsetAsync(dp->barrier, 0, sizeof(unsigned int), st));
       void *args[] = {(void *)&a};
