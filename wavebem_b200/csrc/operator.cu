@@ -11,6 +11,7 @@
 // Each warp owns 4 rows: the x chunk is loaded once and reused for 4 streamed 128-bit
 // matrix loads per lane.
 #include <cstdio>
+#include <cstdlib>
 
 #include "internal.h"
 
@@ -91,6 +92,8 @@ struct GemvArgs
   unsigned long long *done_counter;
 };
 
+__device__ __forceinline__ void gemv_store_fwd(const GemvArgs &a, uint32_t lrow, double v, int lane);
+
 template <int NR, int NC>
 __device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int lane)
 {
@@ -108,28 +111,67 @@ __device__ __forceinline__ void gemv_rows(const GemvArgs &a, uint32_t r0, int la
       double v = a.s1 * a1[r] + a.s2 * a2[r];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
-      const uint32_t g = a.row0 + rows[r];
-      v += a.sdiag * a.alpha[g] * a.xdiag[g];
-      if (a.n_peers > 1)
-        {
-          if (lane < a.n_peers) a.peer_base[lane][a.buf_off + g] = v; // lane q -> rank q (NVLink store)
-        }
-      else if (lane == 0)
-        a.y[rows[r]] = v;
+      gemv_store_fwd(a, rows[r], v, lane);
     }
 }
 
+__device__ __forceinline__ void gemv_store(const GemvArgs &a, uint32_t lrow, double v, int lane);
+__device__ __forceinline__ void gemv_store_fwd(const GemvArgs &a, uint32_t lrow, double v, int lane)
+{
+  gemv_store(a, lrow, v, lane);
+}
+__device__ __forceinline__ void gemv_store(const GemvArgs &a, uint32_t lrow, double v, int lane)
+{
+  const uint32_t g = a.row0 + lrow;
+  v += a.sdiag * a.alpha[g] * a.xdiag[g];
+  if (a.n_peers > 1)
+    {
+      if (lane < a.n_peers) a.peer_base[lane][a.buf_off + g] = v; // lane q -> rank q (NVLink store)
+    }
+  else if (lane == 0)
+    a.y[lrow] = v;
+}
+
+// one row, its column chunks split over the 8 warps of the CTA (used for the remainder rows)
+__device__ __forceinline__ void gemv_row_split(const GemvArgs &a, uint32_t idx, int warp, int lane, double *red)
+{
+  double a1[GEMV_MAXR], a2[GEMV_MAXR];
+  a1[0] = a2[0] = 0.0;
+  uint32_t rows[GEMV_MAXR];
+  rows[0] = a.row_list ? a.row_list[idx] : idx;
+  const int b1 = a.n1 * warp / GEMV_WARPS, e1 = a.n1 * (warp + 1) / GEMV_WARPS;
+  const int b2 = a.n2 * warp / GEMV_WARPS, e2 = a.n2 * (warp + 1) / GEMV_WARPS;
+  gemv_pass<1, 8>(a.M1, a.x1, a.list1 + b1, e1 - b1, a.ld, rows, lane, a1);
+  gemv_pass<1, 8>(a.M2, a.x2, a.list2 + b2, e2 - b2, a.ld, rows, lane, a2);
+  double v = a.s1 * a1[0] + a.s2 * a2[0];
+#pragma unroll
+  for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0)
+    {
+      double t = 0.0;
+#pragma unroll
+      for (int w = 0; w < GEMV_WARPS; ++w) t += red[w]; // fixed order: deterministic
+      gemv_store(a, rows[0], t, lane);
+    }
+  __syncthreads();
+}
+
 // y[r] = s1 * (M1[r,:] . x1) + s2 * (M2[r,:] . x2) + sdiag * alpha[row0+r] * xdiag[row0+r]
-// One resident wave of CTAs (grid = SMs x occupancy); the rows are split evenly over CTAs and
-// then over the warps of a CTA, so every SM streams the same number of bytes (no tail wave).
+// One resident wave of CTAs (grid = SMs x occupancy).  Every warp streams the same number q of
+// whole rows; the n_rows - q*warps remainder rows are split column-wise over the 8 warps of a
+// CTA, so all warps finish together whatever the row count (no tail wave, no 3-rows-vs-2 skew
+// on row-sharded runs).
 __global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
 {
+  __shared__ double red[GEMV_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t G = gridDim.x, c = blockIdx.x;
-  const uint32_t cr0 = (uint32_t)((uint64_t)a.n_rows * c / G), cr1 = (uint32_t)((uint64_t)a.n_rows * (c + 1) / G);
-  const uint32_t nr = cr1 - cr0;
-  uint32_t r0 = cr0 + nr * warp / GEMV_WARPS;
-  const uint32_t r1 = cr0 + nr * (warp + 1) / GEMV_WARPS;
+  const uint32_t Wt = G * GEMV_WARPS;
+  const uint32_t q = a.n_rows / Wt, rem = a.n_rows - q * Wt;
+  uint32_t r0 = (c * GEMV_WARPS + warp) * q;
+  const uint32_t r1 = r0 + q;
   while (r0 < r1)
     {
       const uint32_t left = r1 - r0;
@@ -146,6 +188,7 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
         }
       r0 += take;
     }
+  for (uint32_t j = c; j < rem; j += G) gemv_row_split(a, q * Wt + j, warp, lane, red);
   if (a.n_peers > 1)
     { // completion: the last CTA of this launch publishes "rank's rows of epoch e are in place"
       __shared__ bool s_last;
@@ -253,7 +296,11 @@ int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank)
 {
   if (ctx->p.world_size <= 1) return 0;
   if (!ctx->nccl_comm)
-    WBEM_FAIL(ctx, -5, "world_size=%d but wbem_comm_init was not called", ctx->p.world_size);
+    {
+      // diagnostics only: time one rank's share of a sharded run on a single GPU
+      if (getenv("WBEM_DIAG_NO_COMM")) return 0;
+      WBEM_FAIL(ctx, -5, "world_size=%d but wbem_comm_init was not called", ctx->p.world_size);
+    }
   const char *base = (const char *)d_buf;
   return wbem_nccl_allgather(ctx, base + bytes_per_rank * ctx->p.rank, d_buf, bytes_per_rank);
 }
@@ -320,9 +367,8 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
           ga.sdiag = -1.0;
         }
       uint32_t grid = (uint32_t)(n_sm * ctas_per_sm);
-      const uint32_t max_useful = (ga.n_rows + GEMV_WARPS - 1) / GEMV_WARPS; // >= 1 row per warp
       if (ga.n_rows == 0) grid = 0;
-      if (grid > max_useful) grid = max_useful;
+      if (grid > ga.n_rows && ga.n_rows > 0) grid = ga.n_rows; // tiny problems: one split row per CTA
       ga.n_peers = 1;
       ga.rank = ctx->p.rank;
       if (use_p2p)
