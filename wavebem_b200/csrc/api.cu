@@ -199,6 +199,7 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_Nm);
   FREE_DEV(ctx->d_Dm);
   FREE_DEV(ctx->d_alpha);
+  FREE_DEV(ctx->d_alpha_part);
   FREE_DEV(ctx->d_surf);
   FREE_DEV(ctx->d_other);
   FREE_DEV(ctx->d_con_line_of);
@@ -367,6 +368,8 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_alloc(ctx, &ctx->d_Nm, nloc * ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_Dm, nloc * ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_alpha, ld))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_alpha_part, ((size_t)pl.n_clusters + 1) * nloc))) return rc;
+  ctx->alpha_parts_valid = false;
   if ((rc = dev_alloc(ctx, &ctx->d_surf, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_other, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_xn, ld))) return rc;
@@ -490,7 +493,7 @@ int wbem_compute_alpha(wbem_ctx *ctx)
   CHECK_CTX(ctx);
   if (!ctx->assembled) WBEM_FAIL(ctx, -3, "wbem_compute_alpha before wbem_assemble");
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
-  int rc = wbem_launch_alpha(ctx);
+  int rc = wbem_launch_alpha(ctx, true); // the literal N * (-1) of the reference
   if (rc) return rc;
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;

@@ -229,6 +229,7 @@ struct TiledArgs
   const uint32_t *sing_ptr, *sing_cellpos; // CSR by local row
   const uint8_t *tile_sing;                // [row tiles][clusters]: any singular pair inside?
   double *Nm, *Dm;
+  double *alpha_part; // [n_clusters + 1][nloc]: per-cluster partial of sum_j N_ij (row sum = sum of moments S)
   uint32_t ld, row0, nloc, cluster_base, n_clusters;
 };
 
@@ -325,6 +326,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
   consumer_barrier();
 
   const double vq0 = c_qt.g1_x[2 * h], vq1 = c_qt.g1_x[2 * h + 1];
+  double row_sum = 0.0; // sum over this cluster's regular cells of the zeroth moment (h = 0: Neumann)
   for (int c = 0; c < nchunk; ++c)
     {
       mbar_wait(&bar[c & 1], (c >> 1) & 1);
@@ -409,6 +411,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
           const double v3 = m3, v1 = m1 - m3, v2 = m2 - m3, v0 = (m0 - m1) - v2;
           if (!((smask >> k) & 1ull))
             {
+              row_sum += m0; // sum_j phi_j = 1: the row sum of the cell's four entries is its S moment
               *pa = oa + v0;
               *pb = ob + v1;
               *pc = oc + v2;
@@ -422,6 +425,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
         }
     }
   consumer_barrier();
+  if (h == 0 && lrow < a.nloc) a.alpha_part[(size_t)cluster * a.nloc + lrow] = row_sum;
 
   // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
   // slots (coalesced row segments), 8 rows per lane in flight.
@@ -559,11 +563,12 @@ __global__ void __launch_bounds__(256)
                       const uint32_t *__restrict__ sing_ptr,
                       const uint32_t *__restrict__ sing_cellpos,
                       const uint8_t *__restrict__ sing_idx, double *Nm, double *Dm, uint32_t ld,
-                      uint32_t row0, uint32_t nloc)
+                      uint32_t row0, uint32_t nloc, double *__restrict__ alpha_sing)
 {
   const int lane = threadIdx.x & 31;
   const uint32_t lrow = (blockIdx.x * blockDim.x + threadIdx.x) >> 5;
   if (lrow >= nloc) return;
+  double row_sum = 0.0;
   const double *px = xyz + 3 * (size_t)(row0 + lrow);
   const double xi[3] = {px[0], px[1], px[2]};
   const int ns = c_qt.ns;
@@ -602,6 +607,7 @@ __global__ void __launch_bounds__(256)
 #pragma unroll
           for (int off = 16; off > 0; off >>= 1) v8[j] += __shfl_xor_sync(0xffffffffu, v8[j], off);
         }
+      row_sum += (v8[0] + v8[1]) + (v8[2] + v8[3]);
       // lanes 0..3 -> Neumann, 4..7 -> Dirichlet; sequential over j for repeated dofs
       double mine = 0;
 #pragma unroll
@@ -620,6 +626,26 @@ __global__ void __launch_bounds__(256)
         }
       __syncwarp();
     }
+  if (lane == 0 && alpha_sing) alpha_sing[lrow] = row_sum;
+}
+
+// alpha_loc[r] = -(sum over clusters of the partial row sums + singular part), fixed order
+__global__ void __launch_bounds__(256)
+  k_alpha_from_parts(const double *__restrict__ part, uint32_t n_parts, uint32_t nloc, double *__restrict__ out)
+{
+  const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= nloc) return;
+  double s0 = 0, s1 = 0, s2 = 0, s3 = 0;
+  uint32_t k = 0;
+  for (; k + 4 <= n_parts; k += 4)
+    {
+      s0 += part[(size_t)(k + 0) * nloc + r];
+      s1 += part[(size_t)(k + 1) * nloc + r];
+      s2 += part[(size_t)(k + 2) * nloc + r];
+      s3 += part[(size_t)(k + 3) * nloc + r];
+    }
+  for (; k < n_parts; ++k) s0 += part[(size_t)k * nloc + r];
+  out[r] = -((s0 + s1) + (s2 + s3));
 }
 
 // alpha_loc[r] = - sum_j N[r][j]   (one warp per local row, 128-bit loads)
@@ -697,6 +723,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       a.n_clusters = pl.n_clusters;
       a.Nm = ctx->d_Nm;
       a.Dm = ctx->d_Dm;
+      a.alpha_part = ctx->d_alpha_part;
       a.ld = ctx->ld;
       a.row0 = ctx->row0;
       a.nloc = ctx->nloc;
@@ -738,18 +765,31 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       const uint32_t warps_per_block = 8;
       k_assemble_singular<<<(ctx->nloc + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
         ctx->d_xyz, ctx->d_cell_dofs, ctx->d_dir, ctx->d_colpos, ctx->d_sing_ptr,
-        ctx->d_sing_cellpos, ctx->d_sing_idx, ctx->d_Nm, ctx->d_Dm, ctx->ld, ctx->row0, ctx->nloc);
+        ctx->d_sing_cellpos, ctx->d_sing_idx, ctx->d_Nm, ctx->d_Dm, ctx->ld, ctx->row0, ctx->nloc,
+        tiled ? ctx->d_alpha_part + (size_t)ctx->plan.n_clusters * ctx->nloc : nullptr);
       ctx->launches++;
       CUDA_OK(ctx, cudaGetLastError());
     }
+  else if (tiled)
+    CUDA_OK(ctx, cudaMemsetAsync(ctx->d_alpha_part + (size_t)ctx->plan.n_clusters * ctx->nloc, 0,
+                                 sizeof(double) * ctx->nloc, st));
+  ctx->alpha_parts_valid = tiled;
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[2], st));
   return 0;
 }
 
-int wbem_launch_alpha(wbem_ctx *ctx)
+int wbem_launch_alpha(wbem_ctx *ctx, bool from_matrix)
 {
   cudaStream_t st = ctx->stream;
-  if (ctx->nloc)
+  if (ctx->nloc && ctx->alpha_parts_valid && !from_matrix)
+    {
+      k_alpha_from_parts<<<(ctx->nloc + 255) / 256, 256, 0, st>>>(ctx->d_alpha_part, ctx->plan.n_clusters + 1,
+                                                                 ctx->nloc,
+                                                                 ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+    }
+  else if (ctx->nloc)
     {
       k_alpha_rowsum<<<(ctx->nloc + 7) / 8, 256, 0, st>>>(ctx->d_Nm, ctx->ld, ctx->nloc,
                                                          ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk);

@@ -152,6 +152,8 @@ struct wbem_ctx
   // matrices: nloc x ld, row-major, columns in storage order (colperm)
   double *d_Nm = nullptr, *d_Dm = nullptr;
   double *d_alpha = nullptr; // [N] replicated
+  double *d_alpha_part = nullptr; // [n_clusters + 1][nloc] partial row sums written by the assembly
+  bool alpha_parts_valid = false;
 
   // masks / constraints (replicated)
   double *d_surf = nullptr, *d_other = nullptr;
@@ -227,7 +229,7 @@ struct wbem_ctx
 int wbem_upload_tables(wbem_ctx *ctx);
 int wbem_launch_geometry(wbem_ctx *ctx);
 int wbem_launch_assemble(wbem_ctx *ctx);
-int wbem_launch_alpha(wbem_ctx *ctx);
+int wbem_launch_alpha(wbem_ctx *ctx, bool from_matrix = false);
 // operator.cu
 int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double *d_src,
                         double *d_dst, bool constrained);
