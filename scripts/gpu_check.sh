@@ -14,6 +14,9 @@ if [ "$MODE" != "quick" ]; then
   echo "== compute-sanitizer memcheck (smoke)" | tee -a $OUT/summary.log
   timeout 900 compute-sanitizer --tool memcheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/memcheck.log 2>&1; echo "memcheck rc=$?" | tee -a $OUT/summary.log
   grep -E "ERROR SUMMARY|Invalid|out of bounds" $OUT/memcheck.log | head -5 | tee -a $OUT/summary.log
+  echo "== compute-sanitizer racecheck (smoke)" | tee -a $OUT/summary.log
+  timeout 900 compute-sanitizer --tool racecheck --error-exitcode 9 python -c "import __graft_entry__ as g; g.smoke()" > $OUT/racecheck.log 2>&1; echo "racecheck rc=$?" | tee -a $OUT/summary.log
+  grep -E "RACECHECK SUMMARY|hazard|ERROR" $OUT/racecheck.log | head -8 | tee -a $OUT/summary.log
 fi
 echo "== pytest -m gpu" | tee -a $OUT/summary.log
 timeout 1500 python -m pytest tests -q -m gpu > $OUT/pytest_gpu.log 2>&1; echo "pytest rc=$?" | tee -a $OUT/summary.log

@@ -292,6 +292,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
           for (int c = 2; c < nchunk; ++c)
             {
               mbar_wait(&bar[2 + (c & 1)], ((c - 2) >> 1) & 1);
+              // consumers' generic-proxy reads of this buffer are ordered before the
+              // async-proxy refill
+              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
               issue_chunk(c);
             }
         }
