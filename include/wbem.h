@@ -45,7 +45,10 @@ typedef struct wbem_params
   int world_size;          /* number of row blocks (GPUs) */
   int assemble_variant;    /* 0 = default (tiled, deterministic), 1 = simple atomic kernel */
   int precond_on_host;     /* 1 = band LU + solves on the host (debug), 0 = on the device */
-  int reserved[5];
+  int precond_kind;        /* 0 = the reference's band preconditioner (default); 1 = local-inverse
+                              sparse approximate inverse (spai.cu): same solution within the solver
+                              tolerance, ~4x fewer GMRES iterations, no dependence on the numbering */
+  int reserved[4];
 } wbem_params;
 
 typedef struct wbem_timings
@@ -125,6 +128,15 @@ int wbem_assemble_preconditioner(wbem_ctx *ctx);
 int wbem_precond_vmult(wbem_ctx *ctx, double *dst, const double *src);
 /* the band_system entries of this context's rows: out[(r-row0)*band + (i-(r-band/2+1))] */
 int wbem_get_band(wbem_ctx *ctx, double *out);
+/* precond_kind = 1: the assembled sparse approximate inverse M (row i = k entries at columns
+ * nbr[i*k .. i*k+k), 0xffffffff = unused slot), and the number of local systems that were
+ * singular (those rows fall back to 1/a_ii).  Any output pointer may be NULL. */
+int wbem_get_spai(wbem_ctx *ctx, uint32_t *k, uint32_t *nbr, double *val, int *n_singular);
+/* host-only check of its sparsity-pattern builder (no GPU): 0 = all invariants hold;
+ * stats4 = k, widest / mean near-field row, rows with fewer than k dofs in reach */
+int wbem_spai_pattern_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *cell_dofs,
+                            const uint32_t *dn_ptr, const uint32_t *dn_idx, const double *xyz,
+                            uint32_t *nbr_out, double *stats4);
 
 /* BEMProblem<3>::solve_system (source/bem_problem.cc:821-895).  phi / dphi_dn are in-out:
  * only the unknown half is overwritten (:869-879).  iters / last_res may be NULL.

@@ -435,3 +435,98 @@ def test_reinit_with_another_mesh_and_moving_geometry(wb, orc):
             assert rel_err_rowscaled(ctx.get_rows(0), on, diag=orc.compute_alpha(on)) < ENTRY_TOL
             assert rel_err_rowscaled(ctx.get_rows(1), od) < ENTRY_TOL
     ctx.close()
+
+
+def _dense_constrained_operator(t):
+    """The matrix GMRES sees: merged operator (bem_problem.cc:620-670 with 0/1 masks) with the
+    constrained rows of ConstrainedOperator::vmult (constrained_matrix.h:73-86)."""
+    m, cl = t["m"], t["cl"]
+    s, o = m.surface_nodes, m.other_nodes
+    n = m.n_nodes
+    A = t["on"] * o[None, :] - t["od"] * s[None, :]
+    A[np.arange(n), np.arange(n)] += t["alpha"] * o
+    for k, line in enumerate(cl.lines):
+        A[line, :] = 0.0
+        A[line, line] = 1.0
+        for c, v in zip(cl.col[cl.ptr[k]:cl.ptr[k + 1]], cl.val[cl.ptr[k]:cl.ptr[k + 1]]):
+            A[line, c] -= v
+    return A
+
+
+def test_spai_preconditioner_rows_and_solve(wb, orc, tank_case):
+    """precond_kind = 1 (spai.cu): every row of M solves its local system A[S,S]^T m = e_i; the
+    GMRES solution agrees with the oracle's (band-preconditioned) within the solver tolerance
+    and needs far fewer iterations."""
+    t = tank_case
+    m = t["m"]
+    n = m.n_nodes
+    tol = 1e-10
+    ctx = _ctx(wb, m, precond_kind=1, gmres_tol=tol, gmres_max_steps=400)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(t["cl"])
+    ctx.assemble_preconditioner()
+    nbr, val, n_sing = ctx.get_spai()
+    assert n_sing == 0 and nbr.shape == (n, 32)
+    A = _dense_constrained_operator(t)
+    M = np.zeros((n, n))
+    for i in range(n):
+        S = nbr[i][nbr[i] != 0xFFFFFFFF].astype(np.int64)
+        assert i in S and np.all(np.diff(S) > 0)
+        ref = np.linalg.solve(A[np.ix_(S, S)].T, (S == i).astype(float))
+        got = val[i][: len(S)]
+        assert np.abs(got - ref).max() <= 1e-9 * np.abs(ref).max(), i
+        M[i, S] = got
+    # row i of M A is e_i on S_i
+    i = n // 2
+    S = nbr[i].astype(np.int64)
+    assert np.abs((M[i] @ A)[S] - (S == i)).max() < 1e-10
+    v = np.sin(0.11 * np.arange(n))
+    assert np.abs(ctx.precond_vmult(v) - M @ v).max() <= 1e-12 * np.abs(M @ v).max()
+    phi0 = np.where(m.surface_nodes == 1, t["bc"], 0.0)
+    dphi0 = np.where(m.surface_nodes == 1, 0.0, t["bc"])
+    phi, dphi, iters, res = ctx.solve_system(phi0, dphi0, t["bc"])
+    ref = orc.solve_system(t["on"], t["od"], m.surface_nodes, m.other_nodes, t["bc"], t["con"], phi0, dphi0,
+                           tol=tol, max_steps=400)
+    assert ref["converged"] and res <= tol
+    assert iters <= ref["iters"] // 2, (iters, ref["iters"])
+    scale = np.linalg.norm(ref["sol"])
+    assert np.linalg.norm(ctx.get_sol() - ref["sol"]) <= 50 * tol * max(scale, 1.0)
+    vinf = np.array([0.28 * np.sqrt(9.81 * 2.5), 0, 0])
+    s = m.surface_nodes == 1
+    fg, pg = hull_pressure_force(m, phi, dphi, vinf)
+    fo, po = hull_pressure_force(m, np.where(s, phi0, ref["phi"]), np.where(s, ref["dphi_dn"], dphi0), vinf)
+    assert abs(fg[0] - fo[0]) <= 1e-8 * abs(fo[0]) and abs(pg - po) <= 1e-8 * abs(po)
+    # the preconditioner is rebuilt when the operator changes (masks), reused otherwise
+    t0 = ctx.timings()["precond_setup_ms"]
+    ctx.solve_system(phi0, dphi0, t["bc"])
+    assert ctx.timings()["precond_setup_ms"] <= t0
+    ctx.close()
+
+
+@pytest.mark.parametrize("mesh", ["cube1", "cube4_random_flipped"])
+def test_spai_on_tiny_and_randomly_numbered_meshes(wb, orc, mesh):
+    """Fewer dofs than K (padding slots) and a random numbering (the band preconditioner depends
+    on the numbering, the local inverse does not)."""
+    m = MESHES[mesh]()
+    n = m.n_nodes
+    from wavebem_b200.constraints import compute_constraints
+    s = (m.node_patch == 1).astype(float)            # one Dirichlet face, five Neumann faces
+    m.surface_nodes, m.other_nodes = s, 1.0 - s
+    bc = np.cos(np.arange(n) * 0.4)
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=meshgen.cell_normals_at_nodes(m))
+    sols = {}
+    for kind in (0, 1):
+        ctx = _ctx(wb, m, precond_kind=kind, gmres_tol=1e-12, gmres_max_steps=300)
+        ctx.assemble()
+        ctx.set_masks(m.surface_nodes, m.other_nodes)
+        ctx.set_constraints(cl)
+        z = np.zeros(n)
+        _, _, it, res = ctx.solve_system(z, z, bc)
+        sols[kind] = (ctx.get_sol(), it)
+        if kind == 1:
+            nbr, val, n_sing = ctx.get_spai()
+            assert n_sing == 0
+            assert np.all((nbr != 0xFFFFFFFF).sum(axis=1) == min(32, n))
+        ctx.close()
+    assert np.linalg.norm(sols[0][0] - sols[1][0]) <= 1e-9 * max(1.0, np.linalg.norm(sols[0][0]))

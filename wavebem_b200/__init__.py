@@ -24,7 +24,8 @@ from . import constraints as _constraints
 from . import meshgen  # noqa: F401
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libwbem.so")
+# WBEM_LIB: development override (kernel tuning variants built by build.build_variant)
+LIB_PATH = os.environ.get("WBEM_LIB") or os.path.join(_HERE, "lib", "libwbem.so")
 _lib = None
 
 
@@ -46,7 +47,7 @@ class Params(C.Structure):
                 ("gmres_max_steps", C.c_int), ("gmres_n_tmp_vectors", C.c_int),
                 ("preconditioner_band", C.c_int), ("device", C.c_int), ("rank", C.c_int),
                 ("world_size", C.c_int), ("assemble_variant", C.c_int), ("precond_on_host", C.c_int),
-                ("reserved", C.c_int * 5)]
+                ("precond_kind", C.c_int), ("reserved", C.c_int * 4)]
 
 
 class Timings(C.Structure):
@@ -75,7 +76,7 @@ ABI_SYMBOLS = [
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
     "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
-    "wbem_comm_ipc_close",
+    "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check",
 ]
 
 
@@ -219,6 +220,16 @@ class Context:
         out = np.empty((self.row1 - self.row0, band))
         self._chk(lib().wbem_get_band(self._h, _dp(out)))
         return out
+
+    def get_spai(self):
+        """precond_kind = 1: (nbr[N,k] uint32 with 0xffffffff pads, val[N,k], n_singular)."""
+        k = C.c_uint32(0)
+        self._chk(lib().wbem_get_spai(self._h, C.byref(k), None, None, None))
+        nbr = np.empty((self.n, k.value), dtype=np.uint32)
+        val = np.empty((self.n, k.value))
+        ns = C.c_int(0)
+        self._chk(lib().wbem_get_spai(self._h, C.byref(k), _dp(nbr), _dp(val), C.byref(ns)))
+        return nbr, val, ns.value
 
     def solve_system(self, phi, dphi_dn, tmp_rhs, raise_on_no_convergence=True):
         phi, dphi_dn, tmp_rhs = np.array(phi, dtype=np.float64), np.array(dphi_dn, dtype=np.float64), _f64(tmp_rhs)

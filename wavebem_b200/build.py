@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT, "libwbem.so")
-SOURCES = ["api.cu", "assemble.cu", "operator.cu", "gmres.cu", "precond.cu", "plan.cpp",
+SOURCES = ["api.cu", "assemble.cu", "operator.cu", "gmres.cu", "precond.cu", "spai.cu", "plan.cpp",
            "quadrature.cpp", "comm.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -50,6 +50,21 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     if force or jobs or _stale(LIB, objs):
         run([NVCC] + ARCH + ["-shared", "-ccbin", HOST_CXX, "-o", LIB] + objs + ["-ldl"])
     return LIB
+
+
+def build_variant(tag: str, defines: list[str]) -> str:
+    """Development helper: lib/libwbem_<tag>.so compiled with extra -D flags (kernel tuning
+    experiments; select it with the environment variable WBEM_LIB)."""
+    vdir = os.path.join(OUT, "variant_" + tag)
+    os.makedirs(vdir, exist_ok=True)
+    objs = []
+    for s in SOURCES:
+        obj = os.path.join(vdir, os.path.splitext(s)[0] + ".o")
+        objs.append(obj)
+        subprocess.check_call([NVCC] + ARCH + FLAGS + defines + ["-c", os.path.join(CSRC, s), "-o", obj])
+    lib = os.path.join(OUT, f"libwbem_{tag}.so")
+    subprocess.check_call([NVCC] + ARCH + ["-shared", "-ccbin", HOST_CXX, "-o", lib] + objs + ["-ldl"])
+    return lib
 
 
 def build_cpp_test() -> str:

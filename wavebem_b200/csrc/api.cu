@@ -92,6 +92,7 @@ void wbem_default_params(wbem_params *p)
   p->world_size = 1;
   p->assemble_variant = 0;
   p->precond_on_host = 0;
+  p->precond_kind = 0;
 }
 
 const char *wbem_last_error(const wbem_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -129,10 +130,10 @@ int wbem_create(const wbem_params *p, wbem_ctx **out)
       return -2;
     }
   if (p->world_size < 1 || p->rank < 0 || p->rank >= p->world_size || p->gmres_n_tmp_vectors < 3 ||
-      p->gmres_n_tmp_vectors > 120 || p->preconditioner_band < 0 || (p->preconditioner_band & 1) ||
-      p->preconditioner_band > 128)
+      p->gmres_n_tmp_vectors > WBEM_GMRES_KMAX || p->preconditioner_band < 0 || (p->preconditioner_band & 1) ||
+      p->preconditioner_band > 128 || p->precond_kind < 0 || p->precond_kind > 1)
     {
-      g_create_error = "bad wbem_params (world/rank, 3 <= n_tmp_vectors <= 120, even band <= 128)";
+      g_create_error = "bad wbem_params (world/rank, 3 <= n_tmp_vectors <= 1024, even band <= 128, precond_kind 0/1)";
       return -1;
     }
   wbem_ctx *ctx = new wbem_ctx();
@@ -224,6 +225,7 @@ static void free_topology(wbem_ctx *ctx)
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   ctx->h_pinned = nullptr;
   wbem_device_precond_free(ctx);
+  wbem_spai_free(ctx);
   ctx->have_geometry = ctx->assembled = ctx->have_alpha = ctx->have_masks = false;
   ctx->precond_ready = false;
   ctx->n_lines = 0;
@@ -393,7 +395,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_alloc(ctx, &ctx->d_rhs, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_sol, ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_V, (size_t)(ntmp - 1) * ld))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_h, 2048 + 128 + (size_t)(N + 127) / 128 + 64))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_h, 1024 + (size_t)(10 * WBEM_GMRES_KMAX) + (size_t)(N + 127) / 128 + 64))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_band, (size_t)ctx->chunk * P * band))) return rc;
   CUDA_OK(ctx, cudaMemsetAsync(ctx->d_xn, 0, sizeof(double) * ld, ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(ctx->d_xd, 0, sizeof(double) * ld, ctx->stream));

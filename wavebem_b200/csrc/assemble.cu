@@ -202,19 +202,29 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 // ---------------------------------------------------------------------------------------
 // Tiled regular-pair kernel, Gauss 4x4.
 //
-// One CTA = (128-row tile) x (one cell cluster), 256 threads: TWO threads per collocation
+// One CTA = (64-row tile) x (one cell cluster), 128 threads: TWO threads per collocation
 // row, each integrating two of the four Gauss lines (8 of the 16 points) of every cell.
 // They swap their partial moments with one shuffle; thread 0 of the pair finishes the
 // Neumann sums, thread 1 the Dirichlet sums, and each adds its 4 values to per-column
-// accumulators in shared memory (acc[matrix][slot][row]).  Two CTAs are resident per SM
-// (4 warps per scheduler) so one CTA's prologue / flush overlaps the other's FP64 loop.
-// Panel data arrives in chunks of 8 cells through a double-buffered TMA bulk copy.
+// accumulators in shared memory (acc[matrix][slot][row]).  TILE_MIN_CTAS CTAs are resident
+// per SM (one warp of every CTA on every scheduler) so one CTA's prologue / flush overlaps
+// the others' FP64 loops.  Panel data arrives in chunks of TILE_CHUNK cells through a
+// double-buffered TMA bulk copy; the LAST warp to finish a chunk (shared-memory counter)
+// re-arms the barrier and issues the refill, so no warp ever spins and the integration loop
+// has no CTA-wide barrier.
 // ---------------------------------------------------------------------------------------
-#define TILE_ROWS WBEM_TILE_ROWS          // 128
-#define TILE_THREADS (2 * TILE_ROWS)      // 256
+#define TILE_ROWS WBEM_TILE_ROWS          // 64
+#define TILE_THREADS (2 * TILE_ROWS)      // 128
+#define TILE_WARPS (TILE_THREADS / 32)
 #define TILE_W WBEM_TILE_W
 #define TILE_MAX_CELLS 64                 // bit mask of singular cells is 64 bits wide
-#define TILE_CHUNK 8
+#ifndef WBEM_TILE_CHUNK
+#define WBEM_TILE_CHUNK 8
+#endif
+#ifndef WBEM_TILE_MIN_CTAS
+#define WBEM_TILE_MIN_CTAS 3
+#endif
+#define TILE_CHUNK WBEM_TILE_CHUNK
 #define ACC_STRIDE (TILE_ROWS + 1)
 // offset between the two matrices' accumulators: = 8 (mod 16) doubles, so that the N-thread and
 // the D-thread of a row hit disjoint shared-memory banks
@@ -235,23 +245,32 @@ struct TiledArgs
 
 constexpr size_t tiled_smem_bytes()
 {
-  return sizeof(double) * (2 * ACC_MATOFF + 2 * TILE_CHUNK * 7 * 16) + 32 /*mbar*/ + TILE_MAX_CELLS * 4 +
-         TILE_W * 4;
+  return sizeof(double) * (2 * ACC_MATOFF + 2 * TILE_CHUNK * 7 * 16) + 32 /*mbar + counters*/ + TILE_MAX_CELLS * 4 +
+         ((TILE_W + 3) / 4) * 16;
 }
 
-#define TILE_BLOCK (TILE_THREADS + 32) // + one producer warp that only drives the TMA pipeline
+#define TILE_BLOCK TILE_THREADS
 
-__device__ __forceinline__ void consumer_barrier()
-{ // named barrier 1: the TILE_THREADS consumer threads only
-  asm volatile("bar.sync 1, %0;" ::"n"(TILE_THREADS) : "memory");
+// one column value of the flush: STORE for the first writer of a column, RED.ADD.F64 for later
+// ones -- both predicated, so a warp with mixed lanes runs one instruction stream
+__device__ __forceinline__ void flush_value(double *p, double v, uint32_t is_add, uint32_t is_store)
+{
+  asm volatile("{\n\t.reg .pred pa, ps;\n\t"
+               "setp.ne.u32 pa, %2, 0;\n\t"
+               "setp.ne.u32 ps, %3, 0;\n\t"
+               "@pa red.global.add.f64 [%0], %1;\n\t"
+               "@ps st.global.f64 [%0], %1;\n\t}" ::"l"(p),
+               "d"(v), "r"(is_add), "r"(is_store)
+               : "memory");
 }
 
-__global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArgs a)
+__global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_tiled(const TiledArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *acc = reinterpret_cast<double *>(smem_raw);              // [2][ACC_MATOFF]
   double *geo = acc + 2 * ACC_MATOFF;                              // [2][CHUNK][7][16]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * TILE_CHUNK * 112);
+  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * TILE_CHUNK * 112); // [2] "full" barriers
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(bar + 2);         // [2] warps done with a buffer
   uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 4);       // [cells] packed 4 x u8
   uint32_t *s_col = s_slots + TILE_MAX_CELLS;                      // [W]
 
@@ -266,14 +285,6 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
   const uint32_t lrow = lrow_base + row_l;
   const uint32_t lrow_c = lrow < a.nloc ? lrow : a.nloc - 1;
 
-  if (tid == 0)
-    {
-      mbar_init(&bar[0], 1);                 // "full": TMA bytes landed
-      mbar_init(&bar[1], 1);
-      mbar_init(&bar[2], TILE_THREADS / 32); // "empty": every warp is done reading the buffer
-      mbar_init(&bar[3], TILE_THREADS / 32);
-    }
-  __syncthreads();
   auto issue_chunk = [&](int c) {
     const int nc = min(TILE_CHUNK, ncell - c * TILE_CHUNK);
     const uint32_t bytes = (uint32_t)nc * 112 * sizeof(double);
@@ -281,24 +292,14 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
     bulk_copy_g2s(geo + (c & 1) * TILE_CHUNK * 112, a.geo + ((size_t)p0 + (size_t)c * TILE_CHUNK) * 112, bytes,
                   &bar[c & 1]);
   };
-  if (tid >= TILE_THREADS)
-    { // producer warp: fill the two buffers, then refill each one as soon as all consumer
-      // warps have released it ("empty" barrier); consumers never meet a CTA-wide barrier
-      // inside the integration loop
-      if (tid == TILE_THREADS)
-        {
-          issue_chunk(0);
-          if (nchunk > 1) issue_chunk(1);
-          for (int c = 2; c < nchunk; ++c)
-            {
-              mbar_wait(&bar[2 + (c & 1)], ((c - 2) >> 1) & 1);
-              // consumers' generic-proxy reads of this buffer are ordered before the
-              // async-proxy refill
-              asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-              issue_chunk(c);
-            }
-        }
-      return;
+  if (tid == 0)
+    {
+      mbar_init(&bar[0], 1); // "full": TMA bytes landed
+      mbar_init(&bar[1], 1);
+      s_cnt[0] = 0;
+      s_cnt[1] = 0;
+      issue_chunk(0);
+      if (nchunk > 1) issue_chunk(1);
     }
   // singular cells of this row inside the cluster -> bit mask (they are integrated by
   // k_assemble_singular only, reference :241/:261).  Most (row tile, cluster) pairs hold no
@@ -326,7 +327,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
   // zero the accumulators in use: thread (row, h) clears matrix h of its row
   double *accM = acc + h * ACC_MATOFF + row_l;
   for (int s = 0; s < nslot; ++s) accM[s * ACC_STRIDE] = 0.0;
-  consumer_barrier();
+  __syncthreads(); // barriers initialised, slot tables visible
 
   const double vq0 = c_qt.g1_x[2 * h], vq1 = c_qt.g1_x[2 * h + 1];
   double row_sum = 0.0; // sum over this cluster's regular cells of the zeroth moment (h = 0: Neumann)
@@ -422,60 +423,69 @@ __global__ void __launch_bounds__(TILE_BLOCK, 3) k_assemble_tiled(const TiledArg
             }
         }
       if (c + 2 < nchunk)
-        { // release this geometry buffer to the producer warp
+        { // this warp is done with the buffer; the last of the CTA's warps refills it
           __syncwarp();
-          if ((tid & 31) == 0) mbar_arrive(&bar[2 + (c & 1)]);
+          if ((tid & 31) == 0)
+            {
+              __threadfence_block();
+              if (atomicAdd(&s_cnt[c & 1], 1u) == TILE_WARPS - 1)
+                {
+                  s_cnt[c & 1] = 0;
+                  __threadfence_block();
+                  // the warps' generic-proxy reads of this buffer are ordered before the
+                  // async-proxy refill
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                  issue_chunk(c + 2);
+                }
+            }
         }
     }
-  consumer_barrier();
   if (h == 0 && lrow < a.nloc) a.alpha_part[(size_t)cluster * a.nloc + lrow] = row_sum;
+  __syncwarp(); // a warp flushes exactly the 16 rows its own lanes accumulated
 
   // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
-  // slots (coalesced row segments), 8 rows per lane in flight.
+  // slots (STORE slots first: one coalesced row segment), 8 rows per lane in flight.
   const int warp = tid >> 5, lane = tid & 31;
-  for (int rb = warp * 16; rb < warp * 16 + 16; rb += 8)
+  const uint32_t row_w = lrow_base + warp * 16;
+  if (row_w >= a.nloc) return;
+  const int nrw = min(16, (int)(a.nloc - row_w));
+  for (int s = lane; s < nslot; s += 32)
     {
-      const uint32_t row_b = lrow_base + rb;
-      if (row_b >= a.nloc) break;
-      const int nr = min(8, (int)(a.nloc - row_b));
-      for (int s = lane; s < nslot; s += 32)
+      const uint32_t cc = s_col[s];
+      const uint32_t is_add = cc >> 31, is_store = is_add ^ 1u;
+      double *gN = a.Nm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
+      double *gD = a.Dm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
+      const double *an = acc + s * ACC_STRIDE + warp * 16;
+      if (nrw == 16)
         {
-          const uint32_t cc = s_col[s];
-          const uint32_t col = cc & 0x7fffffffu;
-          double vn[8], vd[8];
 #pragma unroll
-          for (int i = 0; i < 8; ++i)
+          for (int rb = 0; rb < 16; rb += 8)
             {
-              vn[i] = acc[s * ACC_STRIDE + rb + i];
-              vd[i] = acc[ACC_MATOFF + s * ACC_STRIDE + rb + i];
-            }
-          double *gN = a.Nm + (size_t)row_b * a.ld + col;
-          double *gD = a.Dm + (size_t)row_b * a.ld + col;
-          if (cc >> 31)
-            {
-              // ADD column: fire-and-forget reduction (RED.ADD.F64), no load on the SM side.
-              // Clusters of one colour never share a column and colours are separate
-              // launches, so each entry sees its additions in a fixed order: bitwise
-              // reproducible although the instruction is an atomic.
+              double vn[8], vd[8];
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                if (i < nr)
-                  {
-                    atomicAdd(gN + (size_t)i * a.ld, vn[i]);
-                    atomicAdd(gD + (size_t)i * a.ld, vd[i]);
-                  }
-            }
-          else
-            {
+                {
+                  vn[i] = an[rb + i];
+                  vd[i] = an[ACC_MATOFF + rb + i];
+                }
 #pragma unroll
               for (int i = 0; i < 8; ++i)
-                if (i < nr)
-                  {
-                    gN[(size_t)i * a.ld] = vn[i];
-                    gD[(size_t)i * a.ld] = vd[i];
-                  }
+                {
+                  flush_value(gN, vn[i], is_add, is_store);
+                  flush_value(gD, vd[i], is_add, is_store);
+                  gN += a.ld;
+                  gD += a.ld;
+                }
             }
         }
+      else
+        for (int i = 0; i < nrw; ++i)
+          {
+            flush_value(gN, an[i], is_add, is_store);
+            flush_value(gD, an[ACC_MATOFF + i], is_add, is_store);
+            gN += a.ld;
+            gD += a.ld;
+          }
     }
 }
 

@@ -18,7 +18,8 @@
 // vector kernels
 // ---------------------------------------------------------------------------------------
 #define DOT_SEGS 8
-// partial[seg*128 + i] = V[i] . w over segment seg of the vector  (grid = k x DOT_SEGS;
+#define GM_KMAX WBEM_GMRES_KMAX // largest Krylov basis (row stride of the small device work arrays)
+// partial[seg*GM_KMAX + i] = V[i] . w over segment seg of the vector  (grid = k x DOT_SEGS;
 // fixed reduction order inside a CTA, the segments are summed in order by the consumer)
 __global__ void __launch_bounds__(256)
   k_dots(uint32_t N, const double *__restrict__ V, size_t ldv, const double *__restrict__ w,
@@ -51,7 +52,7 @@ __global__ void __launch_bounds__(256)
       double t = 0;
 #pragma unroll
       for (int k = 0; k < 8; ++k) t += red[k];
-      partial[seg * 128 + blockIdx.x] = t;
+      partial[seg * GM_KMAX + blockIdx.x] = t;
     }
 }
 
@@ -68,7 +69,7 @@ __global__ void __launch_bounds__(128)
     {
       double t = 0;
 #pragma unroll
-      for (int sg = 0; sg < DOT_SEGS; ++sg) t += partial[sg * 128 + i];
+      for (int sg = 0; sg < DOT_SEGS; ++sg) t += partial[sg * GM_KMAX + i];
       sh[i] = t;
     }
   __syncthreads();
@@ -287,6 +288,14 @@ int wbem_build_preconditioner(wbem_ctx *ctx)
       return 0;
     }
   if (ctx->precond_ready && ctx->precond_version == ctx->op_version) return 0;
+  if (ctx->p.precond_kind == 1)
+    { // local-inverse sparse approximate inverse (spai.cu) instead of the band LU
+      const int rc = wbem_spai_setup(ctx);
+      if (rc) return rc;
+      ctx->precond_ready = true;
+      ctx->precond_version = ctx->op_version;
+      return 0;
+    }
   cudaStream_t st = ctx->stream;
   const uint32_t N = ctx->N;
   double *loc = ctx->d_band + (size_t)ctx->p.rank * ctx->chunk * band;
@@ -352,6 +361,7 @@ int wbem_apply_preconditioner(wbem_ctx *ctx, const double *d_in, double *d_out)
       return 0;
     }
   if (!ctx->precond_ready) WBEM_FAIL(ctx, -3, "preconditioner applied before it was assembled");
+  if (ctx->p.precond_kind == 1) return wbem_spai_apply(ctx, d_in, d_out);
   if (ctx->p.precond_on_host)
     {
       CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, d_in, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
@@ -440,9 +450,10 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   const int max_steps = ctx->p.gmres_max_steps;
   const size_t ldv = ctx->ld;
   double *V = ctx->d_V, *p = ctx->d_tmp[0], *x = ctx->d_sol;
-  double *d_h = ctx->d_h;            // [0,128) scratch, [256] initial norm, [512] pure-Neumann norm
-  double *d_part = ctx->d_h + 1024;  // [DOT_SEGS][128] dot-product partials
-  double *d_hacc = ctx->d_h + 2048;  // [0,128) accumulated h, [128, 128+nb) per-CTA |w|^2
+  double *d_h = ctx->d_h + 1024;     // ctx->d_h[256] initial norm, [512] pure-Neumann norm; d_h: [0,KMAX) y
+  double *d_part = d_h + GM_KMAX;    // [DOT_SEGS][KMAX] dot-product partials
+  double *d_nrm = d_part + DOT_SEGS * GM_KMAX;  // [0,nb128) per-CTA |w|^2, directly followed by
+  double *d_hacc = d_nrm + nb128;               // [0,KMAX) the accumulated Hessenberg column
   double *hp = ctx->h_pinned;
   CUDA_OK(ctx, cudaMemsetAsync(x, 0, sizeof(double) * N, st));
   std::vector<double> H((size_t)ntmp * ntmp, 0.0), gamma(ntmp + 1), ci(ntmp + 1), si(ntmp + 1),
@@ -469,9 +480,9 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
       rc = wbem_apply_preconditioner(ctx, p, v0);
       g_timer.end();
       if (rc) return rc;
-      k_norm2<<<1, 1024, 0, st>>>(N, v0, d_h + 256);
+      k_norm2<<<1, 1024, 0, st>>>(N, v0, ctx->d_h + 256);
       ctx->launches++;
-      CUDA_OK(ctx, cudaMemcpyAsync(hp, d_h + 256, sizeof(double), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaMemcpyAsync(hp, ctx->d_h + 256, sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_OK(ctx, cudaStreamSynchronize(st));
       rho = hp[0];
       state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
@@ -498,15 +509,15 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
             {
               k_dots<<<dim3(dim, DOT_SEGS), 256, 0, st>>>(N, V, ldv, vv, d_part);
               k_project_out<<<nb128, 128, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_part, vv, d_hacc, pass,
-                                                                     d_hacc + 128);
+                                                                     d_nrm);
               ctx->launches += 2;
             }
           // one D2H: accumulated h[0..dim) and the per-CTA sums of squares of the new vector
-          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_hacc, sizeof(double) * (128 + nb128), cudaMemcpyDeviceToHost, st));
+          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_nrm, sizeof(double) * (nb128 + dim), cudaMemcpyDeviceToHost, st));
           CUDA_OK(ctx, cudaStreamSynchronize(st));
-          for (int i = 0; i < dim; ++i) h[i] = hp[i];
+          for (int i = 0; i < dim; ++i) h[i] = hp[nb128 + i];
           double ss = 0;
-          for (unsigned i = 0; i < nb128; ++i) ss += hp[128 + i];
+          for (unsigned i = 0; i < nb128; ++i) ss += hp[i];
           h[dim] = std::sqrt(ss);
           const double s = h[dim];
           k_scale<<<nb, 256, 0, st>>>(N, vv, 1.0 / s);

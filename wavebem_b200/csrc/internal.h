@@ -10,7 +10,10 @@
 #define WBEM_MAX_NQ 64   // regular rule: up to 8 x 8
 #define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
 #define WBEM_MAX_PEERS 16
+#define WBEM_GMRES_KMAX 1024 // largest gmres_n_tmp_vectors
+#ifndef WBEM_TILE_W
 #define WBEM_TILE_W 56      // column slots (dofs) per cell cluster
+#endif
 #define WBEM_TILE_ROWS 64 // rows per CTA of the tiled regular-pair kernel
 
 struct QuadTables
@@ -188,6 +191,7 @@ struct wbem_ctx
   int h_kl = 0, h_ku = 0, h_ldab = 0;
   bool precond_ready = false;
   void *dev_precond = nullptr;  // precond.cu state
+  void *spai = nullptr;         // spai.cu state (precond_kind = 1)
 
   // comm
   NcclApi *nccl = nullptr;
@@ -244,6 +248,10 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn,
 int wbem_device_precond_factor(wbem_ctx *ctx);
 int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out);
 void wbem_device_precond_free(wbem_ctx *ctx);
+// spai.cu
+int wbem_spai_setup(wbem_ctx *ctx);
+int wbem_spai_apply(wbem_ctx *ctx, const double *d_in, double *d_out);
+void wbem_spai_free(wbem_ctx *ctx);
 // api.cu
 void wbem_p2p_close(wbem_ctx *ctx);
 // comm.cpp

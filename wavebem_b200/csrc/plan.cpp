@@ -141,20 +141,6 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
   pl->cell_pos.assign(C, 0);
   for (uint32_t p = 0; p < C; ++p) pl->cell_pos[pl->cell_order[p]] = p;
 
-  // slot index of each cell's local dofs
-  pl->cell_slots.assign(4 * (size_t)C, 0);
-  {
-    std::vector<uint32_t> slot_of(N, NONE);
-    for (uint32_t k = 0; k < ncl; ++k)
-      {
-        for (uint32_t s = pl->cl_slot_ptr[k]; s < pl->cl_slot_ptr[k + 1]; ++s)
-          slot_of[cl_nodes_all[s]] = s - pl->cl_slot_ptr[k];
-        for (uint32_t p = pl->cl_cell_ptr[k]; p < pl->cl_cell_ptr[k + 1]; ++p)
-          for (int j = 0; j < 4; ++j)
-            pl->cell_slots[4 * (size_t)p + j] = (uint8_t)slot_of[cell_dofs[4 * pl->cell_order[p] + j]];
-      }
-  }
-
   // colouring of the cluster conflict graph (clusters sharing a dof)
   std::vector<uint32_t> color(ncl, NONE);
   {
@@ -201,7 +187,10 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
     std::vector<uint32_t> fill(pl->color_ptr.begin(), pl->color_ptr.end() - 1);
     for (uint32_t k = 0; k < ncl; ++k) pl->color_clusters[fill[color[k]]++] = k;
   }
-  // storage columns in first-writer order; later writers get the ADD flag
+  // storage columns in first-writer order; later writers get the ADD flag.  Inside a cluster
+  // the slots are reordered so that the STORE slots come first (in column order) and the ADD
+  // slots last: the flush of one CTA then writes one contiguous row segment per row with
+  // (almost) warp-uniform STORE / ADD lanes.
   pl->colpos.assign(N, NONE);
   pl->colperm.assign(N, 0);
   pl->slot_col.assign(cl_nodes_all.size(), 0);
@@ -209,7 +198,10 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
   for (uint32_t idx = 0; idx < ncl; ++idx)
     {
       const uint32_t k = pl->color_clusters[idx];
-      for (uint32_t s = pl->cl_slot_ptr[k]; s < pl->cl_slot_ptr[k + 1]; ++s)
+      const uint32_t s0 = pl->cl_slot_ptr[k], s1 = pl->cl_slot_ptr[k + 1];
+      std::stable_partition(cl_nodes_all.begin() + s0, cl_nodes_all.begin() + s1,
+                            [&](uint32_t d) { return pl->colpos[d] == NONE; });
+      for (uint32_t s = s0; s < s1; ++s)
         {
           const uint32_t d = cl_nodes_all[s];
           if (pl->colpos[d] == NONE)
@@ -223,6 +215,19 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
             pl->slot_col[s] = pl->colpos[d] | 0x80000000u;
         }
     }
+  // slot index of each cell's local dofs (after the reordering above)
+  pl->cell_slots.assign(4 * (size_t)C, 0);
+  {
+    std::vector<uint32_t> slot_of(N, NONE);
+    for (uint32_t k = 0; k < ncl; ++k)
+      {
+        for (uint32_t s = pl->cl_slot_ptr[k]; s < pl->cl_slot_ptr[k + 1]; ++s)
+          slot_of[cl_nodes_all[s]] = s - pl->cl_slot_ptr[k];
+        for (uint32_t p = pl->cl_cell_ptr[k]; p < pl->cl_cell_ptr[k + 1]; ++p)
+          for (int j = 0; j < 4; ++j)
+            pl->cell_slots[4 * (size_t)p + j] = (uint8_t)slot_of[cell_dofs[4 * pl->cell_order[p] + j]];
+      }
+  }
   pl->n_cols_written = next_col;
   for (uint32_t k = 0; k < ncl; ++k)
     pl->max_cells = std::max(pl->max_cells, pl->cl_cell_ptr[k + 1] - pl->cl_cell_ptr[k]);
