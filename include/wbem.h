@@ -128,6 +128,8 @@ int wbem_assemble_preconditioner(wbem_ctx *ctx);
 int wbem_precond_vmult(wbem_ctx *ctx, double *dst, const double *src);
 /* the band_system entries of this context's rows: out[(r-row0)*band + (i-(r-band/2+1))] */
 int wbem_get_band(wbem_ctx *ctx, double *out);
+/* switch wbem_params.precond_kind on a live context (the next solve rebuilds the preconditioner) */
+int wbem_set_precond_kind(wbem_ctx *ctx, int kind);
 /* precond_kind = 1: the assembled sparse approximate inverse M (row i = k entries at columns
  * nbr[i*k .. i*k+k), 0xffffffff = unused slot), and the number of local systems that were
  * singular (those rows fall back to 1/a_ii).  Any output pointer may be NULL. */
@@ -185,7 +187,9 @@ int wbem_measure_copy_bw(wbem_ctx *ctx, double *gbs);
 int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, double *bytes);
 int wbem_time_assemble(wbem_ctx *ctx, int reps, double *ms_avg);
 /* issue-port probe: DFMA TFLOP/s with 2*n_int integer ALU instructions interleaved per 8 DFMAs
- * (n_int in {0,2,4,8,16}); used to calibrate the assembly kernel's instruction budget */
+ * (n_int in {0,2,4,8,16}); n_int = 100/101/102/103: eight chains of DFMA / DADD / DMUL / alternating
+ * DFMA-DADD only (instructions/s reported as 2 flop each).  Used to calibrate the assembly kernel's
+ * instruction budget */
 int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops);
 /* device self test of the fast 1/sqrt used by the regular-pair kernel: out[i] = rsqrt(in[i]) */
 int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out, int n);

@@ -25,7 +25,9 @@ def main():
     bc = meshgen.towing_tank_bc(m)
     nn = meshgen.cell_normals_at_nodes(m)
     cl = compute_constraints(m.dn_ptr, m.dn_idx, m.surface_nodes, bc, nodes_normals=nn)
-    ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=1e-12, gmres_max_steps=400)
+    kind = int(sys.argv[3]) if len(sys.argv) > 3 else 0
+    ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=1e-12, gmres_max_steps=400,
+                     precond_kind=kind)
     ctx.set_topology(m.n_nodes, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
     assert (ctx.row0, ctx.row1) == wd.row_block(m.n_nodes, rank, world)
     wd.init_comm(ctx)

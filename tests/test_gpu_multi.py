@@ -11,8 +11,8 @@ pytestmark = pytest.mark.gpu
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 
 
-@pytest.mark.parametrize("gather", ["nccl", "p2p"])
-def test_two_gpus_match_one(wb, tmp_path, gather):
+@pytest.mark.parametrize("gather,kind", [("nccl", 0), ("p2p", 0), ("nccl", 1), ("p2p", 1)])
+def test_two_gpus_match_one(wb, tmp_path, gather, kind):
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs 2 GPUs")
@@ -24,13 +24,13 @@ def test_two_gpus_match_one(wb, tmp_path, gather):
     s.close()
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
            "--master-addr", "127.0.0.1", "--master-port", str(port),
-           os.path.join(ROOT, "tests", "dist_worker_gpu.py"), str(tmp_path), gather]
+           os.path.join(ROOT, "tests", "dist_worker_gpu.py"), str(tmp_path), gather, str(kind)]
     subprocess.run(cmd, check=True, timeout=600)
     m = meshgen.wigley_tank(nxm=14, nt=6, nxu=5, nxd=7, nz=3, nzh=4)
     bc = meshgen.towing_tank_bc(m)
     nn = meshgen.cell_normals_at_nodes(m)
     cl = compute_constraints(m.dn_ptr, m.dn_idx, m.surface_nodes, bc, nodes_normals=nn)
-    ctx = wb.Context(gmres_tol=1e-12, gmres_max_steps=400)
+    ctx = wb.Context(gmres_tol=1e-12, gmres_max_steps=400, precond_kind=kind)
     ctx.set_topology(m.n_nodes, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
     ctx.set_geometry(m.xyz)
     ctx.assemble()

@@ -497,10 +497,9 @@ def test_spai_preconditioner_rows_and_solve(wb, orc, tank_case):
     fg, pg = hull_pressure_force(m, phi, dphi, vinf)
     fo, po = hull_pressure_force(m, np.where(s, phi0, ref["phi"]), np.where(s, ref["dphi_dn"], dphi0), vinf)
     assert abs(fg[0] - fo[0]) <= 1e-8 * abs(fo[0]) and abs(pg - po) <= 1e-8 * abs(po)
-    # the preconditioner is rebuilt when the operator changes (masks), reused otherwise
-    t0 = ctx.timings()["precond_setup_ms"]
-    ctx.solve_system(phi0, dphi0, t["bc"])
-    assert ctx.timings()["precond_setup_ms"] <= t0
+    # a second solve on the unchanged operator reuses the preconditioner and reproduces the result
+    phi2, dphi2, iters2, _ = ctx.solve_system(phi0, dphi0, t["bc"])
+    assert iters2 == iters and np.array_equal(phi2, phi) and np.array_equal(dphi2, dphi)
     ctx.close()
 
 

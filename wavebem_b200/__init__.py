@@ -76,7 +76,7 @@ ABI_SYMBOLS = [
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
     "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
-    "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check",
+    "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
 ]
 
 
@@ -220,6 +220,10 @@ class Context:
         out = np.empty((self.row1 - self.row0, band))
         self._chk(lib().wbem_get_band(self._h, _dp(out)))
         return out
+
+    def set_precond_kind(self, kind):
+        self._chk(lib().wbem_set_precond_kind(self._h, C.c_int(int(kind))))
+        self.params.precond_kind = int(kind)
 
     def get_spai(self):
         """precond_kind = 1: (nbr[N,k] uint32 with 0xffffffff pads, val[N,k], n_singular)."""

@@ -74,6 +74,31 @@ __global__ void k_issue_probe(double *out, int *iout, int iters)
 }
 
 
+// opcode probe: 8 independent chains of one FP64 opcode (0 DFMA, 1 DADD, 2 DMUL, 3 = 4 DFMA + 4 DADD)
+template <int OP>
+__global__ void k_opcode_probe(double *out, int iters)
+{
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-9 + k;
+  const double b = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+      for (int k = 0; k < 8; ++k)
+        {
+          if (OP == 0 || (OP == 3 && (k & 1) == 0))
+            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(b), "d"(c));
+          else if (OP == 1 || OP == 3)
+            asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(a[k]) : "d"(c));
+          else
+            asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(a[k]) : "d"(b));
+        }
+    }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
+
 extern "C" {
 
 int wbem_version(void) { return 100; }
@@ -702,6 +727,18 @@ int wbem_assemble_preconditioner(wbem_ctx *ctx)
   return 0;
 }
 
+int wbem_set_precond_kind(wbem_ctx *ctx, int kind)
+{
+  CHECK_CTX(ctx);
+  if (kind < 0 || kind > 1) WBEM_FAIL(ctx, -1, "precond_kind must be 0 (band) or 1 (sparse approximate inverse)");
+  if (kind != ctx->p.precond_kind)
+    {
+      ctx->p.precond_kind = kind;
+      ctx->precond_ready = false; // the other kind's factors are not valid for this one
+    }
+  return 0;
+}
+
 int wbem_precond_vmult(wbem_ctx *ctx, double *dst, const double *src)
 {
   CHECK_CTX(ctx);
@@ -996,7 +1033,11 @@ int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops)
         case 4: k_issue_probe<4><<<blocks, threads, 0, st>>>(d, di, iters); break;
         case 8: k_issue_probe<8><<<blocks, threads, 0, st>>>(d, di, iters); break;
         case 16: k_issue_probe<16><<<blocks, threads, 0, st>>>(d, di, iters); break;
-        default: cudaFree(d); cudaFree(di); WBEM_FAIL(ctx, -1, "n_int must be 0,2,4,8,16");
+        case 100: k_opcode_probe<0><<<blocks, threads, 0, st>>>(d, iters); break; // DFMA only
+        case 101: k_opcode_probe<1><<<blocks, threads, 0, st>>>(d, iters); break; // DADD only
+        case 102: k_opcode_probe<2><<<blocks, threads, 0, st>>>(d, iters); break; // DMUL only
+        case 103: k_opcode_probe<3><<<blocks, threads, 0, st>>>(d, iters); break; // DFMA/DADD alternating
+        default: cudaFree(d); cudaFree(di); WBEM_FAIL(ctx, -1, "n_int must be 0,2,4,8,16 or 100..103");
         }
       ctx->launches++;
       CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], st));

@@ -147,6 +147,29 @@ __device__ __forceinline__ double rsqrt_h3(double a)
   return fma(p, ye, y);
 }
 
+// a + b and a - b through the FMA datapath (bit-identical results: a*1 + b is rounded once).
+// WBEM_FMA_ADDS selects it; see the opcode probe (wbem_issue_probe 100..103) for the reason.
+__device__ __forceinline__ double add64(double a, double b)
+{
+#ifdef WBEM_FMA_ADDS
+  double r;
+  asm("fma.rn.f64 %0, %1, 0d3FF0000000000000, %2;" : "=d"(r) : "d"(a), "d"(b));
+  return r;
+#else
+  return a + b;
+#endif
+}
+__device__ __forceinline__ double sub64(double a, double b)
+{
+#ifdef WBEM_FMA_ADDS
+  double r;
+  asm("fma.rn.f64 %0, %1, 0dBFF0000000000000, %2;" : "=d"(r) : "d"(b), "d"(a));
+  return r;
+#else
+  return a - b;
+#endif
+}
+
 __global__ void k_rsqrt_selftest(const double *__restrict__ in, double *__restrict__ out, int n)
 {
   int i = blockIdx.x * blockDim.x + threadIdx.x;
@@ -355,9 +378,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
               for (int qx = 0; qx < 4; ++qx)
                 {
                   const int q = j * 4 + qx;
-                  const double Rx = g[q] - xi0;
-                  const double Ry = g[16 + q] - xi1;
-                  const double Rz = g[32 + q] - xi2;
+                  const double Rx = sub64(g[q], xi0);
+                  const double Ry = sub64(g[16 + q], xi1);
+                  const double Rz = sub64(g[32 + q], xi2);
                   const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
                   const double ri = rsqrt_h3(r2);
                   const double ri2 = ri * ri;
@@ -375,9 +398,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
                     }
                   else
                     {
-                      t0n += av;
+                      t0n = add64(t0n, av);
                       t1n = fma(av, uq, t1n);
-                      t0d += bv;
+                      t0d = add64(t0d, bv);
                       t1d = fma(bv, uq, t1d);
                     }
                 }
@@ -394,12 +417,12 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
                 }
               else
                 {
-                  SN += t0n;
-                  SuN += t1n;
+                  SN = add64(SN, t0n);
+                  SuN = add64(SuN, t1n);
                   SvN = fma(vq1, t0n, SvN);
                   SuvN = fma(vq1, t1n, SuvN);
-                  SD += t0d;
-                  SuD += t1d;
+                  SD = add64(SD, t0d);
+                  SuD = add64(SuD, t1d);
                   SvD = fma(vq1, t0d, SvD);
                   SuvD = fma(vq1, t1d, SuvD);
                 }
@@ -409,17 +432,17 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
           const double o1 = __shfl_xor_sync(0xffffffffu, h ? SuN : SuD, 1);
           const double o2 = __shfl_xor_sync(0xffffffffu, h ? SvN : SvD, 1);
           const double o3 = __shfl_xor_sync(0xffffffffu, h ? SuvN : SuvD, 1);
-          const double m0 = (h ? SD : SN) + o0, m1 = (h ? SuD : SuN) + o1, m2 = (h ? SvD : SvN) + o2,
-                       m3 = (h ? SuvD : SuvN) + o3;
+          const double m0 = add64(h ? SD : SN, o0), m1 = add64(h ? SuD : SuN, o1), m2 = add64(h ? SvD : SvN, o2),
+                       m3 = add64(h ? SuvD : SuvN, o3);
           // moments -> the four Q1 shape-function sums
-          const double v3 = m3, v1 = m1 - m3, v2 = m2 - m3, v0 = (m0 - m1) - v2;
+          const double v3 = m3, v1 = sub64(m1, m3), v2 = sub64(m2, m3), v0 = sub64(sub64(m0, m1), v2);
           if (!((smask >> k) & 1ull))
             {
-              row_sum += m0; // sum_j phi_j = 1: the row sum of the cell's four entries is its S moment
-              *pa = oa + v0;
-              *pb = ob + v1;
-              *pc = oc + v2;
-              *pd = od + v3;
+              row_sum = add64(row_sum, m0); // sum_j phi_j = 1: the row sum of the cell's four entries is its S moment
+              *pa = add64(oa, v0);
+              *pb = add64(ob, v1);
+              *pc = add64(oc, v2);
+              *pd = add64(od, v3);
             }
         }
       if (c + 2 < nchunk)
