@@ -96,7 +96,13 @@ if t:
     json.dump({"bytes_per_launch": sum(t) / len(t), "launches_captured": len(t),
                "source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full"},
               open(os.path.join(PROF, "gemv_dram_bytes_per_launch.json"), "w"))
-summarize(os.path.join(OUT, "prof_assemble.ncu-rep"), "assemble")
+t = summarize(os.path.join(OUT, "prof_assemble.ncu-rep"), "assemble")
+if t:
+    # the capture holds the launches (one per colour) of ONE assembly: the step's traffic is their sum
+    json.dump({"bytes_per_step": sum(t), "launches_captured": len(t),
+               "source": "sum over the k_assemble_tiled launches of one assembly of dram__bytes_read.sum + "
+                         "dram__bytes_write.sum, ncu --set full"},
+              open(os.path.join(PROF, "assemble_dram_bytes_per_step.json"), "w"))
 for f in ("bench.json", "gpu_info.csv"):
     src = os.path.join(OUT, f)
     if os.path.exists(src):
