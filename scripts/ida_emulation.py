@@ -32,6 +32,7 @@ def main():
     ap.add_argument("--residuals", type=int, default=2)
     ap.add_argument("--jv", type=int, default=5)
     ap.add_argument("--tol", type=float, default=1e-10)
+    ap.add_argument("--precond", default="spai", choices=["spai", "band"])
     args = ap.parse_args()
     rank, world, local = wd.env_rank_world()
     if world > 1:
@@ -44,7 +45,8 @@ def main():
     kw = {k: base.meta[k] for k in ("nxm", "nt", "nxu", "nxd", "nz", "nzh")}
     n = base.n_nodes
     nn = meshgen.cell_normals_at_nodes(base)
-    ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=1000)
+    ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=1000,
+                     precond_kind=1 if args.precond == "spai" else 0)
     ctx.set_topology(n, base.cells, base.dir_flag, base.dn_ptr, base.dn_idx)
     wd.init_comm(ctx)
     wd.init_peer_gather(ctx)
@@ -78,7 +80,7 @@ def main():
     if rank == 0:
         per_step = (sum(t_solve) + sum(t_jv)) / args.steps
         print(json.dumps({"config": "IDA call pattern (emulated; IDA itself not run)", "nodes": n, "n_gpus": world,
-                          "steps": args.steps, "residuals_per_step": args.residuals, "jv_per_step": args.jv,
+                          "preconditioner": args.precond, "steps": args.steps, "residuals_per_step": args.residuals, "jv_per_step": args.jv,
                           "solve_ms_mean": 1e3 * float(np.mean(t_solve)), "solve_system_ms_mean": 1e3 * float(np.mean(t_jv)),
                           "bem_ms_per_time_step": 1e3 * per_step, "gmres_iters_mean": float(np.mean(its))}))
     ctx.close()

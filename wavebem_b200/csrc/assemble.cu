@@ -268,7 +268,7 @@ struct TiledArgs
 
 constexpr size_t tiled_smem_bytes()
 {
-  return sizeof(double) * (2 * ACC_MATOFF + 2 * TILE_CHUNK * 7 * 16) + 32 /*mbar + counters*/ + TILE_MAX_CELLS * 4 +
+  return sizeof(double) * (2 * ACC_MATOFF + 2 * TILE_CHUNK * 7 * 16) + 40 /*mbar + counters*/ + TILE_MAX_CELLS * 4 +
          ((TILE_W + 3) / 4) * 16;
 }
 
@@ -292,9 +292,9 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double *acc = reinterpret_cast<double *>(smem_raw);              // [2][ACC_MATOFF]
   double *geo = acc + 2 * ACC_MATOFF;                              // [2][CHUNK][7][16]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * TILE_CHUNK * 112); // [2] "full" barriers
-  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(bar + 2);         // [2] warps done with a buffer
-  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 4);       // [cells] packed 4 x u8
+  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * TILE_CHUNK * 112); // [2] "full" + [2] "empty" barriers
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(bar + 4);         // [2] warps done with a buffer
+  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 5);       // [cells] packed 4 x u8
   uint32_t *s_col = s_slots + TILE_MAX_CELLS;                      // [W]
 
   const int tid = threadIdx.x;
@@ -319,6 +319,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
     {
       mbar_init(&bar[0], 1); // "full": TMA bytes landed
       mbar_init(&bar[1], 1);
+      mbar_init(&bar[2], TILE_WARPS); // "empty": every warp is done reading the buffer
+      mbar_init(&bar[3], TILE_WARPS);
       s_cnt[0] = 0;
       s_cnt[1] = 0;
       issue_chunk(0);
@@ -450,13 +452,15 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
           __syncwarp();
           if ((tid & 31) == 0)
             {
-              __threadfence_block();
+              // release on the "empty" barrier (orders this warp's reads); the shared counter
+              // only elects the warp that arrived last -- its wait on the completed phase
+              // returns at once and acquires every warp's release
+              mbar_arrive(&bar[2 + (c & 1)]);
               if (atomicAdd(&s_cnt[c & 1], 1u) == TILE_WARPS - 1)
                 {
                   s_cnt[c & 1] = 0;
-                  __threadfence_block();
-                  // the warps' generic-proxy reads of this buffer are ordered before the
-                  // async-proxy refill
+                  mbar_wait(&bar[2 + (c & 1)], (c >> 1) & 1);
+                  // generic-proxy reads of the buffer are ordered before the async-proxy refill
                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                   issue_chunk(c + 2);
                 }
