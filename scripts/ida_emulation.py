@@ -58,6 +58,12 @@ def main():
     z = np.zeros(n)
     t_solve, t_jv, its = [], [], []
     dt = 0.02
+
+    def sync():
+        # ranks build their meshes at different speeds: line them up before a timed call
+        if world > 1:
+            dist.barrier()
+
     for step in range(args.steps):
         t = step * dt
         for r in range(args.residuals):
@@ -66,6 +72,7 @@ def main():
             bc = bc0
             cl = compute_constraints(m.dn_ptr, m.dn_idx, m.surface_nodes, bc, nodes_normals=nn)
             ctx.set_constraints(cl)
+            sync()
             t0 = time.perf_counter()
             phi, dphi, it, res = ctx.solve(m.xyz, z, z, bc)
             t_solve.append(time.perf_counter() - t0)
@@ -74,15 +81,20 @@ def main():
             v = bc0 * np.cos(0.1 * (j + 1) * np.arange(n))      # a Krylov direction's boundary data
             cl = compute_constraints(base.dn_ptr, base.dn_idx, base.surface_nodes, v, nodes_normals=nn)
             ctx.set_constraints(cl)
+            sync()
             t0 = time.perf_counter()
             ctx.solve_system(z, z, v)
             t_jv.append(time.perf_counter() - t0)
     if rank == 0:
-        per_step = (sum(t_solve) + sum(t_jv)) / args.steps
+        # the first time step pays the once-per-mesh host work (tiling plan, sparsity pattern)
+        first = (sum(t_solve[:args.residuals]) + sum(t_jv[:args.jv]))
+        if args.steps > 1:
+            t_solve, t_jv, its = t_solve[args.residuals:], t_jv[args.jv:], its[args.residuals:]
+        per_step = (sum(t_solve) + sum(t_jv)) / max(1, args.steps - 1 if args.steps > 1 else 1)
         print(json.dumps({"config": "IDA call pattern (emulated; IDA itself not run)", "nodes": n, "n_gpus": world,
                           "preconditioner": args.precond, "steps": args.steps, "residuals_per_step": args.residuals, "jv_per_step": args.jv,
                           "solve_ms_mean": 1e3 * float(np.mean(t_solve)), "solve_system_ms_mean": 1e3 * float(np.mean(t_jv)),
-                          "bem_ms_per_time_step": 1e3 * per_step, "gmres_iters_mean": float(np.mean(its))}))
+                          "bem_ms_per_time_step": 1e3 * per_step, "first_time_step_ms": 1e3 * first, "gmres_iters_mean": float(np.mean(its))}))
     ctx.close()
 
 
