@@ -40,3 +40,5 @@ def test_cpp_bem_problem(wb, orc, tmp_path):
     assert np.linalg.norm(phi[~s] - ref["phi"][~s]) < 1e-9 * np.linalg.norm(ref["phi"])
     assert np.linalg.norm(dphi[s] - ref["dphi_dn"][s]) < 1e-9 * np.linalg.norm(ref["dphi_dn"])
     assert abs(checks[0] - ref["iters"]) <= 3 and checks[1] < 1e-16 and checks[2] < 1e-9 and checks[3] == 5
+    # precond_kind = 1 through the C++ mirror: same solution, at most half the iterations
+    assert checks[4] < 1e-9 and 0 < checks[5] <= checks[0] / 2
