@@ -319,8 +319,8 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
     {
       mbar_init(&bar[0], 1); // "full": TMA bytes landed
       mbar_init(&bar[1], 1);
-      mbar_init(&bar[2], TILE_WARPS); // "empty": every warp is done reading the buffer
-      mbar_init(&bar[3], TILE_WARPS);
+      mbar_init(&bar[2], TILE_THREADS); // "empty": every thread is done reading the buffer
+      mbar_init(&bar[3], TILE_THREADS);
       s_cnt[0] = 0;
       s_cnt[1] = 0;
       issue_chunk(0);
@@ -449,13 +449,13 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
         }
       if (c + 2 < nchunk)
         { // this warp is done with the buffer; the last of the CTA's warps refills it
+          // every thread releases its reads on the "empty" barrier; the shared counter only
+          // elects the warp that arrived last -- its wait on the completed phase returns at
+          // once and acquires all the releases
+          mbar_arrive(&bar[2 + (c & 1)]);
           __syncwarp();
           if ((tid & 31) == 0)
             {
-              // release on the "empty" barrier (orders this warp's reads); the shared counter
-              // only elects the warp that arrived last -- its wait on the completed phase
-              // returns at once and acquires every warp's release
-              mbar_arrive(&bar[2 + (c & 1)]);
               if (atomicAdd(&s_cnt[c & 1], 1u) == TILE_WARPS - 1)
                 {
                   s_cnt[c & 1] = 0;
