@@ -48,7 +48,10 @@ typedef struct wbem_params
   int precond_kind;        /* 0 = the reference's band preconditioner (default); 1 = local-inverse
                               sparse approximate inverse (spai.cu): same solution within the solver
                               tolerance, ~4x fewer GMRES iterations, no dependence on the numbering */
-  int reserved[4];
+  int auto_constraints;    /* 1 = solve_system / solve / residual call compute_constraints(tmp_rhs)
+                              themselves, as the reference does (source/bem_problem.cc:845); 0 (default)
+                              = the caller installs the lines with wbem_set_constraints */
+  int reserved[3];
 } wbem_params;
 
 typedef struct wbem_timings
@@ -69,7 +72,8 @@ typedef struct wbem_timings
   int gmres_iters;
   long long kernel_launches; /* kernels of this library launched since create/reset */
   double gemv_bytes_last;  /* matrix bytes the last operator application had to stream */
-  double reserved[6];
+  double constraints_ms;   /* compute_constraints inside solve_system (auto_constraints = 1) */
+  double reserved[5];
 } wbem_timings;
 
 void wbem_default_params(wbem_params *p);
@@ -115,6 +119,25 @@ int wbem_set_masks(wbem_ctx *ctx, const double *surface_nodes, const double *oth
 int wbem_set_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t *lines,
                          const uint32_t *ptr, const uint32_t *col, const double *val,
                          const double *inhom);
+
+/* ComputationalDomain<3>::compute_normals (source/computational_domain.cc:1525-1620): L2
+ * projection of the cell normals onto the Q1 space, normalised; normals[N][3] (may be NULL). */
+int wbem_compute_normals(wbem_ctx *ctx, double *normals);
+/* BEMProblem<3>::compute_surface_gradients (source/bem_problem.cc:1153-1293): L2 projection of
+ * the surface gradient of phi = tmp_rhs o surface_nodes; gradients[N][3] (may be NULL). */
+int wbem_compute_surface_gradients(wbem_ctx *ctx, const double *tmp_rhs, double *gradients);
+/* BEMProblem<3>::compute_constraints (source/bem_problem.cc:990-1105) inside the library: runs the
+ * two projections above when a double-node set needs them, walks the double-node sets and
+ * installs the lines (like wbem_set_constraints).  Hanging-node lines
+ * (DoFTools::make_hanging_node_constraints, :1000) stay the caller's: hand them over once with
+ * wbem_set_hanging_constraints (weights only, no inhomogeneities).  wbem_get_constraints returns
+ * the lines of the last call (sizes first, then the arrays; any pointer may be NULL). */
+int wbem_set_hanging_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t *lines,
+                                 const uint32_t *ptr, const uint32_t *col, const double *val);
+int wbem_compute_constraints(wbem_ctx *ctx, const double *tmp_rhs);
+int wbem_get_constraints(wbem_ctx *ctx, uint32_t *n_lines, uint32_t *nnz, uint32_t *lines,
+                         uint32_t *ptr, uint32_t *col, double *val, double *inhom);
+int wbem_mass_cg_iterations(wbem_ctx *ctx); /* CG iterations of the last projection solve */
 
 /* BEMProblem<3>::vmult (source/bem_problem.cc:620-670). */
 int wbem_vmult(wbem_ctx *ctx, double *dst, const double *src);

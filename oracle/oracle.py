@@ -267,6 +267,31 @@ def residual(nm, dm, surface_nodes, other_nodes, con: Constraints, phi, dphi_dn,
     return res
 
 
+def l2_projection(which, xyz, cells, dir_flag, phi=None, quad_order=4):
+    """which = 0: ComputationalDomain::compute_normals (computational_domain.cc:1525-1620);
+    which = 1: BEMProblem::compute_surface_gradients of the nodal field phi (bem_problem.cc:1153-1293)."""
+    xyz = np.ascontiguousarray(xyz, dtype=np.float64)
+    cells = np.ascontiguousarray(cells, dtype=np.uint32)
+    dir_flag = np.ascontiguousarray(dir_flag, dtype=np.uint8)
+    n = xyz.shape[0]
+    phi = np.zeros(n) if phi is None else np.ascontiguousarray(phi, dtype=np.float64)
+    out = np.zeros((n, 3))
+    f = lib().orc_l2_projection
+    f.argtypes = [C.c_int, C.c_int, C.c_int, _dp, _u32p, _u8p, C.c_int, _dp, _dp]
+    rc = f(int(which), n, cells.shape[0], xyz, cells, dir_flag, int(quad_order), phi, out)
+    if rc:
+        raise RuntimeError(f"oracle: L2 projection failed ({rc})")
+    return out
+
+
+def compute_normals(xyz, cells, dir_flag, quad_order=4):
+    return l2_projection(0, xyz, cells, dir_flag, None, quad_order)
+
+
+def compute_surface_gradients(xyz, cells, dir_flag, tmp_rhs, surface_nodes, quad_order=4):
+    return l2_projection(1, xyz, cells, dir_flag, np.asarray(tmp_rhs) * np.asarray(surface_nodes), quad_order)
+
+
 def max_threads():
     f = lib().orc_max_threads
     f.restype = C.c_int

@@ -873,6 +873,177 @@ void orc_residual(int N, const double *Nm, const double *Dm, const double *surfa
   free(alpha); free(tmp); free(rrhs); free(sol);
 }
 
+/* ------------------------------------------------------------------------------------
+ * L2 projections run by compute_constraints on every solve_system (reference
+ * source/bem_problem.cc:996-997):
+ *   ComputationalDomain<3>::compute_normals        source/computational_domain.cc:1525-1620
+ *   BEMProblem<3>::compute_surface_gradients       source/bem_problem.cc:1153-1293
+ * Both assemble, cell by cell, the mass matrix of FESystem(FE_Q(1),3) -- component-wise the
+ * scalar Q1 mass matrix, (:1576-1588 / :1246-1258) -- and a right-hand side
+ *   int phi_i n_d dS        (:1589-1590)          resp.   int phi_i (grad_s phi)_d dS  (:1259-1260)
+ * and solve with SparseDirectUMFPACK.  Restated with a dense Cholesky factorisation per
+ * connected mesh component (patches do not couple: their edge dofs are double nodes), which
+ * is the same exact solve up to rounding.  which = 0: normals (normalised, :1613),
+ * which = 1: surface gradients of the nodal field phi[N] (= tmp_rhs o surface_nodes, :1157-1158).
+ * The surface gradient in a quadrature point is deal.II's covariant transformation of the
+ * reference gradients: grad_s f = DX_t^T G^-1 [d_u f, d_v f].
+ * ---------------------------------------------------------------------------------- */
+static int uf_find(int *parent, int i)
+{
+  while (parent[i] != i)
+    {
+      parent[i] = parent[parent[i]];
+      i = parent[i];
+    }
+  return i;
+}
+
+int orc_l2_projection(int which, int N, int C, const double *xyz, const uint32_t *cell_dofs,
+                      const uint8_t *cell_dir_flag, int quad_order, const double *phi, double *out)
+{
+  const int nq = quad_order * quad_order;
+  double *uv = (double *)malloc(sizeof(double) * 2 * nq), *w = (double *)malloc(sizeof(double) * nq);
+  if (orc_qgauss2(quad_order, uv, w)) return -1;
+  /* connected components */
+  int *parent = (int *)malloc(sizeof(int) * N);
+  for (int i = 0; i < N; ++i) parent[i] = i;
+  for (int c = 0; c < C; ++c)
+    for (int j = 1; j < 4; ++j)
+      {
+        int a = uf_find(parent, (int)cell_dofs[4 * c]), b = uf_find(parent, (int)cell_dofs[4 * c + j]);
+        if (a != b) parent[b] = a;
+      }
+  int *comp = (int *)malloc(sizeof(int) * N), *local = (int *)malloc(sizeof(int) * N);
+  int ncomp = 0;
+  int *root_id = (int *)malloc(sizeof(int) * N);
+  for (int i = 0; i < N; ++i) root_id[i] = -1;
+  int *csize = (int *)calloc((size_t)N, sizeof(int));
+  for (int i = 0; i < N; ++i)
+    {
+      int r = uf_find(parent, i);
+      if (root_id[r] < 0) root_id[r] = ncomp++;
+      comp[i] = root_id[r];
+      local[i] = csize[comp[i]]++;
+    }
+  double **M = (double **)calloc((size_t)ncomp, sizeof(double *));
+  double **B = (double **)calloc((size_t)ncomp, sizeof(double *));
+  for (int k = 0; k < ncomp; ++k)
+    {
+      M[k] = (double *)calloc((size_t)csize[k] * csize[k], sizeof(double));
+      B[k] = (double *)calloc((size_t)csize[k] * 3, sizeof(double));
+    }
+  /* cell loop (:1566-1600 / :1229-1273) */
+  for (int c = 0; c < C; ++c)
+    {
+      const uint32_t *dofs = cell_dofs + 4 * c;
+      double X[12];
+      for (int k = 0; k < 4; ++k)
+        for (int d = 0; d < 3; ++d) X[3 * k + d] = xyz[3 * (size_t)dofs[k] + d];
+      double lm[4][4] = {{0}}, lr[4][3] = {{0}};
+      for (int q = 0; q < nq; ++q)
+        {
+          double ph[4], du[4], dv[4];
+          shape_q1(uv[2 * q], uv[2 * q + 1], ph, du, dv);
+          double t0[3] = {0, 0, 0}, t1[3] = {0, 0, 0};
+          for (int k = 0; k < 4; ++k)
+            for (int d = 0; d < 3; ++d)
+              {
+                t0[d] += du[k] * X[3 * k + d];
+                t1[d] += dv[k] * X[3 * k + d];
+              }
+          const double g00 = t0[0] * t0[0] + t0[1] * t0[1] + t0[2] * t0[2];
+          const double g01 = t0[0] * t1[0] + t0[1] * t1[1] + t0[2] * t1[2];
+          const double g11 = t1[0] * t1[0] + t1[1] * t1[1] + t1[2] * t1[2];
+          const double detG = g00 * g11 - g01 * g01;
+          const double jxw = sqrt(detG) * w[q];
+          double vec[3];
+          if (which == 0)
+            {
+              const double cr[3] = {t0[1] * t1[2] - t0[2] * t1[1], t0[2] * t1[0] - t0[0] * t1[2],
+                                    t0[0] * t1[1] - t0[1] * t1[0]};
+              const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
+              const double sgn = cell_dir_flag[c] ? 1.0 : -1.0;
+              for (int d = 0; d < 3; ++d) vec[d] = sgn * (cr[d] / cn);
+            }
+          else
+            { /* fe_v.get_function_gradients(phi, phi_surf_grads) (:1236): sum_k phi_k grad_s(shape_k) */
+              for (int d = 0; d < 3; ++d) vec[d] = 0.0;
+              for (int k = 0; k < 4; ++k)
+                {
+                  const double a = (g11 * du[k] - g01 * dv[k]) / detG, b = (g00 * dv[k] - g01 * du[k]) / detG;
+                  for (int d = 0; d < 3; ++d) vec[d] += phi[dofs[k]] * (t0[d] * a + t1[d] * b);
+                }
+            }
+          for (int i = 0; i < 4; ++i)
+            {
+              for (int j = 0; j < 4; ++j) lm[i][j] += ph[i] * ph[j] * jxw;
+              for (int d = 0; d < 3; ++d) lr[i][d] += ph[i] * vec[d] * jxw;
+            }
+        }
+      const int k = comp[dofs[0]], n = csize[k];
+      for (int i = 0; i < 4; ++i)
+        {
+          for (int j = 0; j < 4; ++j) M[k][(size_t)local[dofs[i]] * n + local[dofs[j]]] += lm[i][j];
+          for (int d = 0; d < 3; ++d) B[k][(size_t)local[dofs[i]] * 3 + d] += lr[i][d];
+        }
+    }
+  /* Cholesky M = L L^T per component, three right-hand sides */
+  int rc = 0;
+  for (int k = 0; k < ncomp && !rc; ++k)
+    {
+      const int n = csize[k];
+      double *A = M[k], *b = B[k];
+      if (n == 1 && A[0] == 0.0)
+        { /* a dof no cell touches */
+          b[0] = b[1] = b[2] = 0.0;
+          continue;
+        }
+      for (int j = 0; j < n && !rc; ++j)
+        {
+          double s = A[(size_t)j * n + j];
+          for (int t = 0; t < j; ++t) s -= A[(size_t)j * n + t] * A[(size_t)j * n + t];
+          if (!(s > 0.0)) { rc = -2; break; }
+          const double ljj = sqrt(s);
+          A[(size_t)j * n + j] = ljj;
+          for (int i = j + 1; i < n; ++i)
+            {
+              double v = A[(size_t)i * n + j];
+              for (int t = 0; t < j; ++t) v -= A[(size_t)i * n + t] * A[(size_t)j * n + t];
+              A[(size_t)i * n + j] = v / ljj;
+            }
+        }
+      for (int d = 0; d < 3 && !rc; ++d)
+        {
+          for (int i = 0; i < n; ++i)
+            {
+              double v = b[(size_t)i * 3 + d];
+              for (int t = 0; t < i; ++t) v -= A[(size_t)i * n + t] * b[(size_t)t * 3 + d];
+              b[(size_t)i * 3 + d] = v / A[(size_t)i * n + i];
+            }
+          for (int i = n - 1; i >= 0; --i)
+            {
+              double v = b[(size_t)i * 3 + d];
+              for (int t = i + 1; t < n; ++t) v -= A[(size_t)t * n + i] * b[(size_t)t * 3 + d];
+              b[(size_t)i * 3 + d] = v / A[(size_t)i * n + i];
+            }
+        }
+    }
+  for (int i = 0; i < N && !rc; ++i)
+    {
+      double v[3];
+      for (int d = 0; d < 3; ++d) v[d] = B[comp[i]][(size_t)local[i] * 3 + d];
+      if (which == 0)
+        { /* nodes_normals[i] /= |nodes_normals[i]| (:1613) */
+          const double nn = sqrt(v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+          for (int d = 0; d < 3; ++d) v[d] /= nn;
+        }
+      for (int d = 0; d < 3; ++d) out[3 * (size_t)i + d] = v[d];
+    }
+  for (int k = 0; k < ncomp; ++k) { free(M[k]); free(B[k]); }
+  free(M); free(B); free(uv); free(w); free(parent); free(comp); free(local); free(root_id); free(csize);
+  return rc;
+}
+
 int orc_max_threads(void)
 {
 #ifdef _OPENMP

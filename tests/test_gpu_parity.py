@@ -529,3 +529,82 @@ def test_spai_on_tiny_and_randomly_numbered_meshes(wb, orc, mesh):
             assert np.all((nbr != 0xFFFFFFFF).sum(axis=1) == min(32, n))
         ctx.close()
     assert np.linalg.norm(sols[0][0] - sols[1][0]) <= 1e-9 * max(1.0, np.linalg.norm(sols[0][0]))
+
+
+@pytest.mark.parametrize("name", ["tank", "sphere6", "cube4_random_flipped", "tank_wave"])
+def test_normals_and_surface_gradients_match_oracle(wb, orc, name):
+    """wbem_compute_normals / wbem_compute_surface_gradients (constraints.cu: node-gathered mass
+    matrix + CG in one cooperative kernel) against the oracle's Cholesky solve of the reference's
+    two L2 projections (computational_domain.cc:1525-1620, bem_problem.cc:1153-1293)."""
+    m = MESHES[name]()
+    n = m.n_nodes
+    s = m.surface_nodes if m.surface_nodes is not None else (m.node_patch <= 1).astype(float)
+    ctx = _ctx(wb, m)
+    ctx.set_masks(s, 1.0 - s)
+    gn = ctx.compute_normals()
+    on = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
+    assert np.abs(gn - on).max() < 1e-11
+    assert 5 < ctx.mass_cg_iterations() < 200
+    f = np.cos(1.3 * m.xyz[:, 0]) + m.xyz[:, 1] * m.xyz[:, 2]
+    gg = ctx.compute_surface_gradients(f)
+    og = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, f, s)
+    assert np.abs(gg - og).max() <= 1e-11 * max(1.0, np.abs(og).max())
+    # linear in tmp_rhs, zero for a zero field
+    assert np.abs(ctx.compute_surface_gradients(np.zeros(n))).max() == 0.0
+    assert np.abs(ctx.compute_surface_gradients(2 * f) - 2 * gg).max() <= 1e-11 * max(1.0, np.abs(og).max())
+    ctx.close()
+
+
+def _lines_dict(cl):
+    return {int(l): (sorted(zip(cl.col[cl.ptr[k]:cl.ptr[k + 1]].tolist(), cl.val[cl.ptr[k]:cl.ptr[k + 1]].tolist())),
+                     float(cl.inhom[k])) for k, l in enumerate(cl.lines)}
+
+
+def test_compute_constraints_inside_the_library(wb, orc):
+    """wbem_compute_constraints restates bem_problem.cc:990-1105: same lines as the host
+    restatement fed with the oracle's normals / surface gradients -- flat Dirichlet-Dirichlet
+    edges (tank free surface), sharp ones (two Dirichlet faces of a cube: inhomogeneities from the
+    surface gradients), Dirichlet-Neumann and all-Neumann sets, plus caller-owned hanging lines."""
+    from wavebem_b200.constraints import compute_constraints
+    cases = []
+    t = meshgen.wigley_tank(nxm=12, nt=6, nxu=4, nxd=6, nz=3, nzh=3)
+    cases.append((t, t.surface_nodes, meshgen.towing_tank_bc(t), None))
+    c = meshgen.cube(4, renumber="random", seed=7)
+    sc = (c.node_patch <= 2).astype(float)      # three Dirichlet faces meeting in sharp edges
+    cases.append((c, sc, np.sin(2.0 * c.xyz[:, 0]) + c.xyz[:, 1] ** 2 - c.xyz[:, 2], None))
+    interior = np.nonzero(~c.node_on_patch_boundary)[0]
+    hanging = [(int(interior[3]), [(int(interior[0]), 0.5), (int(interior[1]), 0.5)])]
+    cases.append((c, sc, np.cos(c.xyz[:, 1]), hanging))
+    for m, s, bc, hanging in cases:
+        ctx = _ctx(wb, m, gmres_tol=1e-12, gmres_max_steps=400)
+        ctx.set_masks(s, 1.0 - s)
+        if hanging:
+            ctx.set_hanging_constraints(hanging)
+        got = ctx.compute_constraints(bc)
+        nrm = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
+        grd = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, bc, s)
+        ref = compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=nrm, node_surface_gradients=grd,
+                                  hanging=hanging)
+        a, b = _lines_dict(got), _lines_dict(ref)
+        assert a.keys() == b.keys() and len(a) > 0
+        for k in a:
+            assert a[k][0] == b[k][0], k
+            assert abs(a[k][1] - b[k][1]) <= 1e-10 * max(1.0, abs(b[k][1])), (k, a[k], b[k])
+        if m is c and not hanging:
+            assert any(not e and ih != 0.0 for e, ih in a.values())      # sharp-edge inhomogeneities present
+        # auto_constraints = 1: solve_system computes the lines itself (reference :845) -- same answer
+        ctx.assemble()
+        z = np.zeros(m.n_nodes)
+        phi1, dphi1, it1, _ = ctx.solve_system(z, z, bc)
+        auto = _ctx(wb, m, gmres_tol=1e-12, gmres_max_steps=400, auto_constraints=1)
+        auto.set_masks(s, 1.0 - s)
+        if hanging:
+            auto.set_hanging_constraints(hanging)
+        auto.assemble()
+        phi2, dphi2, it2, _ = auto.solve_system(z, z, bc)
+        assert it1 == it2 and np.array_equal(phi1, phi2) and np.array_equal(dphi1, dphi2)
+        assert auto.timings()["constraints_ms"] > 0.0
+        r = auto.residual(np.where(s == 1, bc, phi2), np.where(s == 1, dphi2, bc))
+        assert np.abs(r).max() < 1e-9
+        ctx.close()
+        auto.close()

@@ -271,3 +271,31 @@ def test_mixed_problem_recovers_trace(orc):
         assert out["converged"]
         errs.append(np.abs(out["phi"][~top] - phi_ex[~top]).max() / np.abs(phi_ex).max())
     assert errs[1] < errs[0] and errs[1] < 2e-2
+
+
+def test_l2_projected_normals_and_surface_gradients(orc):
+    """compute_normals (computational_domain.cc:1525-1620) and compute_surface_gradients
+    (bem_problem.cc:1153-1293), first principles: flat faces give exact answers, on a sphere
+    the projected normal converges to the radial direction."""
+    from wavebem_b200 import meshgen
+    m = meshgen.cube(4, renumber="random", seed=3, flip_every=3)
+    nrm = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
+    axis = {"z0": (0, 0, -1), "z1": (0, 0, 1), "y0": (0, -1, 0), "y1": (0, 1, 0), "x0": (-1, 0, 0), "x1": (1, 0, 0)}
+    exact_n = np.array([axis[m.patch_names[p]] for p in m.node_patch], dtype=float)
+    assert np.abs(nrm - exact_n).max() < 1e-13            # patch-wise dofs: exact outward face normals
+    grad = np.array([1.0, 2.0, -0.5])
+    g = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, m.xyz @ grad, np.ones(m.n_nodes))
+    assert np.abs(g - (grad - (exact_n @ grad)[:, None] * exact_n)).max() < 1e-13
+    # only the Dirichlet part of tmp_rhs enters (phi = tmp_rhs o surface_nodes, :1157-1158)
+    s = (m.node_patch == 1).astype(float)
+    g1 = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, m.xyz @ grad, s)
+    assert np.abs(g1[m.node_patch == 1] - g[m.node_patch == 1]).max() < 1e-13
+    assert np.abs(g1[m.node_patch != 1]).max() == 0.0
+    errs = []
+    for n in (6, 12):
+        sp = meshgen.sphere(n, radius=0.7, center=(0.1, -0.2, 0.3))
+        nr = orc.compute_normals(sp.xyz, sp.cells, sp.dir_flag)
+        rad = (sp.xyz - np.array([0.1, -0.2, 0.3])) / 0.7
+        assert np.abs(np.linalg.norm(nr, axis=1) - 1).max() < 1e-14
+        errs.append(np.sqrt(np.mean(np.sum((nr - rad) ** 2, axis=1))))
+    assert errs[1] < 0.6 * errs[0] and errs[1] < 0.03

@@ -47,7 +47,7 @@ class Params(C.Structure):
                 ("gmres_max_steps", C.c_int), ("gmres_n_tmp_vectors", C.c_int),
                 ("preconditioner_band", C.c_int), ("device", C.c_int), ("rank", C.c_int),
                 ("world_size", C.c_int), ("assemble_variant", C.c_int), ("precond_on_host", C.c_int),
-                ("precond_kind", C.c_int), ("reserved", C.c_int * 4)]
+                ("precond_kind", C.c_int), ("auto_constraints", C.c_int), ("reserved", C.c_int * 3)]
 
 
 class Timings(C.Structure):
@@ -58,7 +58,8 @@ class Timings(C.Structure):
                 ("gemv_ms_sum", C.c_double), ("precond_apply_ms_sum", C.c_double),
                 ("allgather_ms_sum", C.c_double), ("solve_system_total_ms", C.c_double),
                 ("gemv_calls", C.c_int), ("gmres_iters", C.c_int), ("kernel_launches", C.c_longlong),
-                ("gemv_bytes_last", C.c_double), ("reserved", C.c_double * 6)]
+                ("gemv_bytes_last", C.c_double), ("constraints_ms", C.c_double),
+                ("reserved", C.c_double * 5)]
 
     def as_dict(self):
         return {k: getattr(self, k) for k, _ in self._fields_ if k != "reserved"}
@@ -77,6 +78,8 @@ ABI_SYMBOLS = [
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
     "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
     "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
+    "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",
+    "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations",
 ]
 
 
@@ -220,6 +223,50 @@ class Context:
         out = np.empty((self.row1 - self.row0, band))
         self._chk(lib().wbem_get_band(self._h, _dp(out)))
         return out
+
+    def compute_normals(self):
+        out = np.empty((self.n, 3))
+        self._chk(lib().wbem_compute_normals(self._h, _dp(out)))
+        return out
+
+    def compute_surface_gradients(self, tmp_rhs):
+        out = np.empty((self.n, 3))
+        self._chk(lib().wbem_compute_surface_gradients(self._h, _dp(_f64(tmp_rhs)), _dp(out)))
+        return out
+
+    def set_hanging_constraints(self, hanging):
+        """hanging: list of (dof, [(master, weight), ...]) -- DoFTools::make_hanging_node_constraints"""
+        lines = np.array([d for d, _ in hanging], dtype=np.uint32)
+        ptr = np.zeros(len(hanging) + 1, dtype=np.uint32)
+        col, val = [], []
+        for k, (_, ent) in enumerate(hanging):
+            for m, w in ent:
+                col.append(m)
+                val.append(w)
+            ptr[k + 1] = len(col)
+        col = np.array(col, dtype=np.uint32)
+        val = np.array(val, dtype=np.float64)
+        self._chk(lib().wbem_set_hanging_constraints(self._h, C.c_uint32(len(lines)), _dp(lines), _dp(ptr), _dp(col),
+                                                     _dp(val)))
+
+    def compute_constraints(self, tmp_rhs):
+        """BEMProblem<3>::compute_constraints inside the library; returns the installed lines."""
+        self._chk(lib().wbem_compute_constraints(self._h, _dp(_f64(tmp_rhs))))
+        return self.get_constraints()
+
+    def get_constraints(self):
+        nl, nnz = C.c_uint32(0), C.c_uint32(0)
+        self._chk(lib().wbem_get_constraints(self._h, C.byref(nl), C.byref(nnz), None, None, None, None, None))
+        lines = np.empty(nl.value, dtype=np.uint32)
+        ptr = np.empty(nl.value + 1, dtype=np.uint32)
+        col = np.empty(nnz.value, dtype=np.uint32)
+        val = np.empty(nnz.value)
+        inhom = np.empty(nl.value)
+        self._chk(lib().wbem_get_constraints(self._h, None, None, _dp(lines), _dp(ptr), _dp(col), _dp(val), _dp(inhom)))
+        return _constraints.ConstraintLines(self.n, lines, ptr, col, val, inhom)
+
+    def mass_cg_iterations(self):
+        return lib().wbem_mass_cg_iterations(self._h)
 
     def set_precond_kind(self, kind):
         self._chk(lib().wbem_set_precond_kind(self._h, C.c_int(int(kind))))

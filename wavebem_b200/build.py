@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT, "libwbem.so")
-SOURCES = ["api.cu", "assemble.cu", "operator.cu", "gmres.cu", "precond.cu", "spai.cu", "plan.cpp",
+SOURCES = ["api.cu", "assemble.cu", "operator.cu", "gmres.cu", "precond.cu", "spai.cu", "constraints.cu", "plan.cpp",
            "quadrature.cpp", "comm.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
@@ -27,7 +27,8 @@ def _stale(target, deps):
 
 def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) -> str:
     os.makedirs(OUT, exist_ok=True)
-    headers = [os.path.join(CSRC, "internal.h"), os.path.join(HERE, "..", "include", "wbem.h")]
+    headers = [os.path.join(CSRC, "internal.h"), os.path.join(CSRC, "q1map.cuh"),
+               os.path.join(HERE, "..", "include", "wbem.h")]
     objs, jobs = [], []
     for s in SOURCES:
         src = os.path.join(CSRC, s)

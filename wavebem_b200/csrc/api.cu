@@ -118,6 +118,7 @@ void wbem_default_params(wbem_params *p)
   p->assemble_variant = 0;
   p->precond_on_host = 0;
   p->precond_kind = 0;
+  p->auto_constraints = 0;
 }
 
 const char *wbem_last_error(const wbem_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -178,7 +179,7 @@ int wbem_create(const wbem_params *p, wbem_ctx **out)
       return -2;
     }
   for (auto &ev : ctx->ev) cudaEventCreate(&ev);
-  if (wbem_upload_tables(ctx))
+  if (wbem_upload_tables(ctx) || wbem_constraints_upload_tables(ctx))
     {
       g_create_error = ctx->err;
       delete ctx;
@@ -251,6 +252,11 @@ static void free_topology(wbem_ctx *ctx)
   ctx->h_pinned = nullptr;
   wbem_device_precond_free(ctx);
   wbem_spai_free(ctx);
+  wbem_constraints_free(ctx);
+  ctx->h_con_lines.clear();
+  ctx->h_con_ptr.clear();
+  ctx->h_con_col.clear();
+  ctx->h_con_val.clear();
   ctx->have_geometry = ctx->assembled = ctx->have_alpha = ctx->have_masks = false;
   ctx->precond_ready = false;
   ctx->n_lines = 0;
@@ -449,6 +455,7 @@ int wbem_set_geometry_dev(wbem_ctx *ctx, const double *d_support_points)
   ctx->have_geometry = true;
   ctx->assembled = false;
   ctx->have_alpha = false;
+  ctx->geom_version++;
   return 0;
 }
 
@@ -464,6 +471,7 @@ int wbem_set_geometry(wbem_ctx *ctx, const double *support_points)
   ctx->have_geometry = true;
   ctx->assembled = false;
   ctx->have_alpha = false;
+  ctx->geom_version++;
   return 0;
 }
 
@@ -639,15 +647,29 @@ int wbem_set_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t *lines,
   const uint32_t nnz = n_lines ? ptr[n_lines] : 0;
   for (uint32_t k = 0; k < nnz; ++k)
     if (col[k] >= N) WBEM_FAIL(ctx, -1, "constraint entry out of range");
-  // the band preconditioner depends on which rows are constrained (not on the values)
-  if (line_of != ctx->h_con_line_of) ctx->op_version++;
-  ctx->h_con_line_of = line_of;
-  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-  int rc;
   std::vector<uint32_t> vl(lines, lines + n_lines), vp(ptr, ptr + (n_lines ? n_lines + 1 : 1)),
     vc(col, col + nnz);
   std::vector<double> vv(val, val + nnz), vi(inhom, inhom + n_lines);
   if (!n_lines) vp.assign(1, 0);
+  // same lines and coefficients as last time (the per-solve pattern: only the inhomogeneities
+  // follow tmp_rhs): one small copy, nothing else changes
+  if (ctx->n_lines == n_lines && n_lines && ctx->d_con_inhom && vl == ctx->h_con_lines && vp == ctx->h_con_ptr &&
+      vc == ctx->h_con_col && vv == ctx->h_con_val)
+    {
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_con_inhom, vi.data(), sizeof(double) * n_lines, cudaMemcpyHostToDevice,
+                                   ctx->stream));
+      CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+      return 0;
+    }
+  // the preconditioners depend on which rows are constrained and on the line coefficients
+  if (line_of != ctx->h_con_line_of || vc != ctx->h_con_col || vv != ctx->h_con_val) ctx->op_version++;
+  ctx->h_con_line_of = line_of;
+  ctx->h_con_lines = vl;
+  ctx->h_con_ptr = vp;
+  ctx->h_con_col = vc;
+  ctx->h_con_val = vv;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  int rc;
   std::vector<uint32_t> free_rows;
   for (uint32_t r = 0; r < ctx->nloc; ++r)
     if (line_of[ctx->row0 + r] < 0) free_rows.push_back(r);
@@ -857,6 +879,8 @@ int wbem_residual(wbem_ctx *ctx, double *res, const double *phi, const double *d
   k_residual_inputs<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->d_tmp[3], ctx->d_tmp[4], ctx->d_surf,
                                                     ctx->d_other, ctx->d_tmp[5], ctx->d_tmp[6]);
   ctx->launches++;
+  // compute_constraints(constraints, serv_tmp_rhs) (:929)
+  if (ctx->p.auto_constraints && (rc = wbem_compute_constraints_device(ctx, ctx->d_tmp[5]))) return rc;
   if ((rc = wbem_apply_operator(ctx, 1, ctx->d_tmp[5], ctx->d_tmp[7], false))) return rc;
   if ((rc = wbem_apply_operator(ctx, 0, ctx->d_tmp[6], ctx->d_tmp[2], true))) return rc;
   k_residual_combine<<<(N + 255) / 256, 256, 0, st>>>(N, ctx->d_tmp[2], ctx->d_tmp[7],

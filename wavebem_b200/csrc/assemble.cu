@@ -15,6 +15,7 @@
 #include <cstdio>
 
 #include "internal.h"
+#include "q1map.cuh"
 
 #define FOUR_PI 12.566370614359172953850573533118
 
@@ -46,47 +47,6 @@ int wbem_upload_tables(wbem_ctx *ctx)
   memcpy(t.s_w, q.s_w, sizeof(t.s_w));
   CUDA_OK(ctx, cudaMemcpyToSymbol(c_qt, &t, sizeof(t)));
   return 0;
-}
-
-// ---------------------------------------------------------------------------------------
-// Q1 codimension-one mapping at reference point (u,v): position, d_u x d_v, shape values.
-// ---------------------------------------------------------------------------------------
-struct QuadVerts
-{
-  double x[4][3];
-};
-
-__device__ __forceinline__ void load_verts(const double *__restrict__ xyz,
-                                           const uint32_t *__restrict__ dofs, QuadVerts &X)
-{
-#pragma unroll
-  for (int k = 0; k < 4; ++k)
-    {
-      const double *p = xyz + 3 * (size_t)dofs[k];
-      X.x[k][0] = p[0];
-      X.x[k][1] = p[1];
-      X.x[k][2] = p[2];
-    }
-}
-
-__device__ __forceinline__ void map_q1(const QuadVerts &X, double u, double v, double y[3],
-                                       double cr[3], double phi[4])
-{
-  phi[0] = (1 - u) * (1 - v);
-  phi[1] = u * (1 - v);
-  phi[2] = (1 - u) * v;
-  phi[3] = u * v;
-  double tu[3], tv[3];
-#pragma unroll
-  for (int d = 0; d < 3; ++d)
-    {
-      y[d] = phi[0] * X.x[0][d] + phi[1] * X.x[1][d] + phi[2] * X.x[2][d] + phi[3] * X.x[3][d];
-      tu[d] = (1 - v) * (X.x[1][d] - X.x[0][d]) + v * (X.x[3][d] - X.x[2][d]);
-      tv[d] = (1 - u) * (X.x[2][d] - X.x[0][d]) + u * (X.x[3][d] - X.x[1][d]);
-    }
-  cr[0] = tu[1] * tv[2] - tu[2] * tv[1];
-  cr[1] = tu[2] * tv[0] - tu[0] * tv[2];
-  cr[2] = tu[0] * tv[1] - tu[1] * tv[0];
 }
 
 // One thread per (cell position, q).  Output layout per cell: [7][nq] =

@@ -431,6 +431,13 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   rc = wbem_apply_operator(ctx, 1, d_bc, ctx->d_rhs, false);
   g_timer.end();
   if (rc) return rc;
+  if (ctx->p.auto_constraints)
+    { // compute_constraints(constraints, tmp_rhs) (:845)
+      g_timer.begin(T_CONSTRAINTS);
+      rc = wbem_compute_constraints_device(ctx, d_bc);
+      g_timer.end();
+      if (rc) return rc;
+    }
   if (ctx->n_lines)
     {
       k_distribute_rhs<<<(ctx->n_lines + 255) / 256, 256, 0, st>>>(ctx->n_lines, ctx->d_con_lines,
@@ -563,6 +570,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   ctx->tm.gemv_ms_sum = sums[T_GEMV];
   ctx->tm.precond_apply_ms_sum = sums[T_PRECOND_APPLY];
   ctx->tm.allgather_ms_sum = sums[T_ALLGATHER];
+  ctx->tm.constraints_ms = sums[T_CONSTRAINTS];
   ctx->tm.solve_system_total_ms = ms;
   ctx->tm.gmres_iters = accumulated;
   ctx->tm.gemv_calls = counts[T_GEMV];

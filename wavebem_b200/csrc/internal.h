@@ -110,7 +110,7 @@ struct EvTimer
     ev.clear();
   }
 };
-enum { T_RHS = 0, T_PRECOND_SETUP, T_GMRES, T_ALPHA, T_GEMV, T_PRECOND_APPLY, T_ALLGATHER, T_NTAGS };
+enum { T_RHS = 0, T_PRECOND_SETUP, T_GMRES, T_ALPHA, T_GEMV, T_PRECOND_APPLY, T_ALLGATHER, T_CONSTRAINTS, T_NTAGS };
 
 struct wbem_ctx
 {
@@ -192,6 +192,10 @@ struct wbem_ctx
   bool precond_ready = false;
   void *dev_precond = nullptr;  // precond.cu state
   void *spai = nullptr;         // spai.cu state (precond_kind = 1)
+  void *con = nullptr;          // constraints.cu state (compute_constraints on the device)
+  uint64_t geom_version = 0;    // bumped by every wbem_set_geometry
+  std::vector<uint32_t> h_con_lines, h_con_ptr, h_con_col; // last installed constraint structure
+  std::vector<double> h_con_val;
 
   // comm
   NcclApi *nccl = nullptr;
@@ -252,6 +256,10 @@ void wbem_device_precond_free(wbem_ctx *ctx);
 int wbem_spai_setup(wbem_ctx *ctx);
 int wbem_spai_apply(wbem_ctx *ctx, const double *d_in, double *d_out);
 void wbem_spai_free(wbem_ctx *ctx);
+// constraints.cu
+int wbem_constraints_upload_tables(wbem_ctx *ctx);
+int wbem_compute_constraints_device(wbem_ctx *ctx, const double *d_tmp_rhs);
+void wbem_constraints_free(wbem_ctx *ctx);
 // api.cu
 void wbem_p2p_close(wbem_ctx *ctx);
 // comm.cpp
