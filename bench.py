@@ -185,12 +185,13 @@ def run_ours(args):
     n = m.n_nodes
     kind = 1 if args.precond == "spai" else 0
     ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=args.max_steps,
-                     precond_kind=kind)
+                     precond_kind=kind, auto_constraints=1)
     ctx.set_topology(n, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
     wd.init_comm(ctx)
     p2p = (not args.no_p2p) and wd.init_peer_gather(ctx)
     ctx.set_masks(m.surface_nodes, m.other_nodes)
-    ctx.set_constraints(cl)
+    # no constraint lines are handed over: solve_system runs compute_constraints itself
+    # (compute_normals + compute_surface_gradients + the double-node walk, bem_problem.cc:845)
 
     dev = torch.device("cuda", local)
     d_xyz = torch.from_numpy(m.xyz).to(dev)
@@ -225,7 +226,7 @@ def run_ours(args):
     ctx.reset_counters()
     ctx.timer_start()
     acc = dict(asm=0.0, reg=0.0, sing=0.0, geo=0.0, alpha=0.0, solve=0.0, gmres=0.0, gemv=0.0, gemv_calls=0,
-               precond_setup=0.0, precond_apply=0.0, allgather=0.0, rhs=0.0)
+               precond_setup=0.0, precond_apply=0.0, allgather=0.0, rhs=0.0, constraints=0.0)
     iters = res = rc = 0
     for _ in range(args.steps):
         rc, iters, res = step_dev()
@@ -235,7 +236,7 @@ def run_ours(args):
         acc["solve"] += t["solve_system_total_ms"]; acc["gmres"] += t["gmres_ms"]; acc["gemv"] += t["gemv_ms_sum"]
         acc["gemv_calls"] += t["gemv_calls"]; acc["precond_setup"] += t["precond_setup_ms"]
         acc["precond_apply"] += t["precond_apply_ms_sum"]; acc["allgather"] += t["allgather_ms_sum"]
-        acc["rhs"] += t["rhs_ms"]
+        acc["rhs"] += t["rhs_ms"]; acc["constraints"] += t["constraints_ms"]
     ms_total = ctx.timer_stop()
     barrier()
     sampler.stop_flag = True
@@ -322,7 +323,7 @@ def run_ours(args):
             "assemble_ms": acc["asm"] / K, "assemble_regular_ms": acc["reg"] / K,
             "assemble_singular_ms": acc["sing"] / K, "geometry_ms": acc["geo"] / K, "alpha_ms": acc["alpha"] / K,
             "gmres_solve_ms": acc["solve"] / K, "rhs_ms": acc["rhs"] / K,
-            "precond_setup_ms": acc["precond_setup"] / K, "precond_apply_ms_per_call": acc["precond_apply"] / max(1, acc["gemv_calls"]),
+            "compute_constraints_ms": acc["constraints"] / K, "precond_setup_ms": acc["precond_setup"] / K, "precond_apply_ms_per_call": acc["precond_apply"] / max(1, acc["gemv_calls"]),
             "gemv_ms_per_call": gemv_ms_avg, "gemv_calls_per_step": acc["gemv_calls"] / K,
             "allgather_ms_per_step": acc["allgather"] / K,
             "roofline_gemv": {"bound": "hbm", "kernel": "k_bem_gemv", "achieved": gemv_gbs, "peak": hbm_peak,

@@ -46,7 +46,7 @@ def main():
     n = base.n_nodes
     nn = meshgen.cell_normals_at_nodes(base)
     ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=1000,
-                     precond_kind=1 if args.precond == "spai" else 0)
+                     precond_kind=1 if args.precond == "spai" else 0, auto_constraints=1)
     ctx.set_topology(n, base.cells, base.dir_flag, base.dn_ptr, base.dn_idx)
     wd.init_comm(ctx)
     wd.init_peer_gather(ctx)
@@ -69,9 +69,7 @@ def main():
         for r in range(args.residuals):
             m = meshgen.wigley_tank(**kw, renumber="hierarchical", wave_amp=0.01 * L, wave_k=k_wave,
                                     wave_phase=omega * (t + 0.3 * dt * r))
-            bc = bc0
-            cl = compute_constraints(m.dn_ptr, m.dn_idx, m.surface_nodes, bc, nodes_normals=nn)
-            ctx.set_constraints(cl)
+            bc = bc0      # compute_constraints runs inside solve_system (auto_constraints)
             sync()
             t0 = time.perf_counter()
             phi, dphi, it, res = ctx.solve(m.xyz, z, z, bc)
@@ -79,8 +77,6 @@ def main():
             its.append(it)
         for j in range(args.jv):
             v = bc0 * np.cos(0.1 * (j + 1) * np.arange(n))      # a Krylov direction's boundary data
-            cl = compute_constraints(base.dn_ptr, base.dn_idx, base.surface_nodes, v, nodes_normals=nn)
-            ctx.set_constraints(cl)
             sync()
             t0 = time.perf_counter()
             ctx.solve_system(z, z, v)

@@ -55,7 +55,7 @@ int main(int argc, char **argv)
   p.gmres_tol = 1e-12;
   p.gmres_max_steps = 400;
   std::vector<double> phi(N, 0.0), dphi(N, 0.0), res, y;
-  double checks[6] = {0, 0, 0, 0, 0, 0};
+  double checks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
   try
     {
       wbem::BEMProblem bem(dom, &p);
@@ -118,11 +118,27 @@ int main(int argc, char **argv)
         }
       checks[4] = std::sqrt(d3 / s3);
       checks[5] = bem3.last_step;
+      // compute_constraints inside the library (auto_constraints = 1): no lines handed over
+      wbem_params ap = p;
+      ap.auto_constraints = 1;
+      wbem::BEMProblem bem4(dom, &ap);
+      bem4.reinit();
+      std::vector<double> phi4(N, 0.0), dphi4(N, 0.0);
+      bem4.solve(phi4, dphi4, bc);
+      double d4 = 0, s4 = 0;
+      for (uint32_t i = 0; i < N; ++i)
+        {
+          d4 += (phi4[i] - phi[i]) * (phi4[i] - phi[i]) + (dphi4[i] - dphi[i]) * (dphi4[i] - dphi[i]);
+          s4 += phi[i] * phi[i] + dphi[i] * dphi[i];
+        }
+      checks[6] = std::sqrt(d4 / s4);
+      bem4.compute_constraints(bc);
+      checks[7] = (double)bem4.constraints.lines.size();
       FILE *o = fopen(argv[2], "wb");
       fwrite(phi.data(), sizeof(double), N, o);
       fwrite(dphi.data(), sizeof(double), N, o);
       fwrite(bem.alpha.data(), sizeof(double), N, o);
-      fwrite(checks, sizeof(double), 6, o);
+      fwrite(checks, sizeof(double), 8, o);
       fclose(o);
     }
   catch (const std::exception &e)

@@ -42,3 +42,5 @@ def test_cpp_bem_problem(wb, orc, tmp_path):
     assert abs(checks[0] - ref["iters"]) <= 3 and checks[1] < 1e-16 and checks[2] < 1e-9 and checks[3] == 5
     # precond_kind = 1 through the C++ mirror: same solution, at most half the iterations
     assert checks[4] < 1e-9 and 0 < checks[5] <= checks[0] / 2
+    # auto_constraints = 1: the library's compute_constraints gives the same lines, hence the same solve
+    assert checks[6] < 1e-9 and checks[7] == cl.n_lines

@@ -274,6 +274,19 @@ def test_bem_problem_mirror_api(wb, orc):
     bem2.reinit()
     with pytest.raises(wb.NoConvergence):
         bem2.solve(np.zeros(n), np.zeros(n), bc)
+    # a domain without its own nodes_normals: compute_constraints runs inside the library
+    # (auto_constraints, bem_problem.cc:845) and produces the same lines here (flat free surface)
+    lines_host = _lines_dict(bem.constraints)
+    del m.nodes_normals
+    bem3 = wb.BEMProblem(m, gmres_tol=1e-12, gmres_max_steps=300)
+    bem3.reinit()
+    phi3, dphi3 = np.zeros(n), np.zeros(n)
+    bem3.solve(phi3, dphi3, bc)
+    assert np.array_equal(phi3, phi) and np.array_equal(dphi3, dphi)
+    got = _lines_dict(bem3.constraints)
+    assert got.keys() == lines_host.keys()
+    nrm = bem3.compute_normals()
+    assert np.abs(nrm - orc.compute_normals(m.xyz, m.cells, m.dir_flag)).max() < 1e-11
 
 
 def test_hanging_node_lines(wb, orc):
@@ -544,7 +557,7 @@ def test_normals_and_surface_gradients_match_oracle(wb, orc, name):
     gn = ctx.compute_normals()
     on = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
     assert np.abs(gn - on).max() < 1e-11
-    assert 5 < ctx.mass_cg_iterations() < 200
+    assert 0 < ctx.mass_cg_iterations() < 200   # (a flat patch with constant normals needs one step)
     f = np.cos(1.3 * m.xyz[:, 0]) + m.xyz[:, 1] * m.xyz[:, 2]
     gg = ctx.compute_surface_gradients(f)
     og = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, f, s)

@@ -410,12 +410,18 @@ class BEMProblem:
     """Mirror of the reference's BEMProblem<3> (include/bem_problem.h:87-180) over the C ABI.
 
     `comp_dom` plays ComputationalDomain<3>: it must expose xyz (support points), cells,
-    dir_flag, dn_ptr/dn_idx (double_nodes_set), surface_nodes, other_nodes and, for
-    compute_constraints on Dirichlet-Dirichlet double nodes, nodes_normals.
+    dir_flag, dn_ptr/dn_idx (double_nodes_set), surface_nodes, other_nodes; optionally `hanging`
+    (make_hanging_node_constraints lines).  compute_constraints runs inside the library
+    (compute_normals + compute_surface_gradients on the GPU, like the reference's solve_system,
+    bem_problem.cc:845); a domain that carries its own `nodes_normals` gets the host restatement
+    with those normals instead.
     """
 
     def __init__(self, comp_dom, **params):
         self.comp_dom = comp_dom
+        self._host_constraints = getattr(comp_dom, "nodes_normals", None) is not None
+        if not self._host_constraints:
+            params.setdefault("auto_constraints", 1)
         self.ctx = Context(**params)
         self.constraints = None
         self.alpha = None
@@ -428,11 +434,15 @@ class BEMProblem:
     def reinit(self):
         d = self.comp_dom
         self.ctx.set_topology(d.xyz.shape[0], d.cells, d.dir_flag, d.dn_ptr, d.dn_idx)
+        if getattr(d, "hanging", None) and not self._host_constraints:
+            self.ctx.set_hanging_constraints(d.hanging)
         self.constraints = None
+        self._have_geometry = False
 
     # BEMProblem::assemble_system (source/bem_problem.cc:106-590)
     def assemble_system(self):
         self.ctx.set_geometry(self.comp_dom.xyz)
+        self._have_geometry = True
         self.ctx.assemble()
         self.alpha = self.ctx.get_alpha()
 
@@ -453,16 +463,37 @@ class BEMProblem:
         self._masks()
         dst[:] = self.ctx.compute_rhs(src)
 
-    # BEMProblem::compute_constraints (source/bem_problem.cc:990-1105) -- host code
+    # BEMProblem::compute_constraints (source/bem_problem.cc:990-1105)
     def compute_constraints(self, tmp_rhs):
         d = self.comp_dom
-        self.constraints = _constraints.compute_constraints(
-            d.dn_ptr, d.dn_idx, d.surface_nodes, tmp_rhs,
-            nodes_normals=getattr(d, "nodes_normals", None),
-            node_surface_gradients=getattr(d, "node_surface_gradients", None),
-            hanging=getattr(d, "hanging", None))
-        self.ctx.set_constraints(self.constraints)
+        if self._host_constraints:
+            self.constraints = _constraints.compute_constraints(
+                d.dn_ptr, d.dn_idx, d.surface_nodes, tmp_rhs,
+                nodes_normals=getattr(d, "nodes_normals", None),
+                node_surface_gradients=getattr(d, "node_surface_gradients", None),
+                hanging=getattr(d, "hanging", None))
+            self.ctx.set_constraints(self.constraints)
+        else:
+            self._masks()
+            if not self._have_geometry:
+                self.ctx.set_geometry(d.xyz)
+                self._have_geometry = True
+            self.constraints = self.ctx.compute_constraints(tmp_rhs)
         return self.constraints
+
+    # ComputationalDomain::compute_normals / BEMProblem::compute_surface_gradients
+    def compute_normals(self):
+        if not self._have_geometry:
+            self.ctx.set_geometry(self.comp_dom.xyz)
+            self._have_geometry = True
+        return self.ctx.compute_normals()
+
+    def compute_surface_gradients(self, tmp_rhs):
+        self._masks()
+        if not self._have_geometry:
+            self.ctx.set_geometry(self.comp_dom.xyz)
+            self._have_geometry = True
+        return self.ctx.compute_surface_gradients(tmp_rhs)
 
     # BEMProblem::assemble_preconditioner (source/bem_problem.cc:1107-1149)
     def assemble_preconditioner(self):
@@ -472,21 +503,26 @@ class BEMProblem:
     # BEMProblem::solve_system (source/bem_problem.cc:821-895): phi / dphi_dn updated in place
     def solve_system(self, phi, dphi_dn, tmp_rhs):
         self._masks()
-        self.compute_constraints(tmp_rhs)
+        if self._host_constraints:
+            self.compute_constraints(tmp_rhs)
         p, d, it, res = self.ctx.solve_system(phi, dphi_dn, tmp_rhs, raise_on_no_convergence=False)
         self._finish(phi, dphi_dn, p, d, it, res)
 
     # BEMProblem::solve (source/bem_problem.cc:969-987)
     def solve(self, phi, dphi_dn, tmp_rhs):
         self._masks()
-        self.compute_constraints(tmp_rhs)
+        if self._host_constraints:
+            self.compute_constraints(tmp_rhs)
         p, d, it, res = self.ctx.solve(self.comp_dom.xyz, phi, dphi_dn, tmp_rhs, raise_on_no_convergence=False)
+        self._have_geometry = True
         self._finish(phi, dphi_dn, p, d, it, res)
 
     def _finish(self, phi, dphi_dn, p, d, it, res):
         phi[:] = p
         dphi_dn[:] = d
         self.last_step, self.last_residual = it, res
+        if not self._host_constraints:
+            self.constraints = self.ctx.get_constraints()   # what solve_system's compute_constraints built
         self.alpha = self.ctx.get_alpha()
         self.system_rhs = self.ctx.get_system_rhs()
         self.sol = self.ctx.get_sol()
@@ -499,7 +535,8 @@ class BEMProblem:
         self._masks()
         d = self.comp_dom
         tmp = np.asarray(dphi_dn) * d.other_nodes + np.asarray(phi) * d.surface_nodes
-        self.compute_constraints(tmp)
+        if self._host_constraints:
+            self.compute_constraints(tmp)
         res[:] = self.ctx.residual(phi, dphi_dn)
 
     # public members of the reference class (include/bem_problem.h:153-154)

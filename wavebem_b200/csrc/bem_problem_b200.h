@@ -103,7 +103,42 @@ public:
     dst.resize(src.size());
     check(wbem_compute_rhs(ctx, dst.data(), src.data()));
   }
-  // the ConstraintMatrix produced by the reference's own compute_constraints (host code)
+  // source/bem_problem.cc:990-1105 inside the library (compute_normals + compute_surface_gradients
+  // on the GPU, the walk over the double-node sets on the host); with wbem_params.auto_constraints
+  // = 1 solve_system / solve / residual call it themselves, as the reference does (:845, :929)
+  void compute_constraints(const std::vector<double> &tmp_rhs)
+  {
+    masks();
+    check(wbem_compute_constraints(ctx, tmp_rhs.data()));
+    uint32_t nl = 0, nnz = 0;
+    check(wbem_get_constraints(ctx, &nl, &nnz, nullptr, nullptr, nullptr, nullptr, nullptr));
+    constraints.lines.resize(nl);
+    constraints.ptr.resize(nl + 1);
+    constraints.col.resize(nnz);
+    constraints.val.resize(nnz);
+    constraints.inhom.resize(nl);
+    check(wbem_get_constraints(ctx, nullptr, nullptr, constraints.lines.data(), constraints.ptr.data(),
+                               constraints.col.data(), constraints.val.data(), constraints.inhom.data()));
+  }
+  // make_hanging_node_constraints lines stay the caller's (:1000): hand them over once per mesh
+  void set_hanging_constraints(const ConstraintLines &c)
+  {
+    check(wbem_set_hanging_constraints(ctx, (uint32_t)c.lines.size(), c.lines.data(), c.ptr.data(), c.col.data(),
+                                       c.val.data()));
+  }
+  // source/computational_domain.cc:1525-1620 and source/bem_problem.cc:1153-1293
+  void compute_normals(std::vector<double> &nodes_normals)
+  {
+    nodes_normals.resize(3 * (size_t)comp_dom.n_dofs());
+    check(wbem_compute_normals(ctx, nodes_normals.data()));
+  }
+  void compute_surface_gradients(const std::vector<double> &tmp_rhs, std::vector<double> &node_surface_gradients)
+  {
+    masks();
+    node_surface_gradients.resize(3 * (size_t)comp_dom.n_dofs());
+    check(wbem_compute_surface_gradients(ctx, tmp_rhs.data(), node_surface_gradients.data()));
+  }
+  // a ConstraintMatrix produced elsewhere (e.g. by the reference's own host compute_constraints)
   void set_constraints(const ConstraintLines &c)
   {
     check(wbem_set_constraints(ctx, (uint32_t)c.lines.size(), c.lines.data(), c.ptr.data(), c.col.data(),
@@ -150,6 +185,7 @@ public:
 
   FlatDomain &comp_dom;
   std::vector<double> system_rhs, sol, alpha; // include/bem_problem.h:155-158
+  ConstraintLines constraints;                // include/bem_problem.h:163 (lines of the last compute_constraints)
   unsigned int last_step = 0;
   double last_residual = 0;
   wbem_ctx *ctx = nullptr;
