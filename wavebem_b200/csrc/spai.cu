@@ -399,7 +399,7 @@ static int spai_build_pattern(wbem_ctx *ctx)
   return 0;
 }
 
-static bool g_spai_attr = false;
+static size_t g_spai_smem_opt_in = 0; // largest dynamic shared-memory size opted in so far
 
 int wbem_spai_setup(wbem_ctx *ctx)
 {
@@ -423,10 +423,10 @@ int wbem_spai_setup(wbem_ctx *ctx)
   if (ctx->nloc)
     {
       const size_t smem = sizeof(double) * SPAI_WARPS * SPAI_K * SPAI_LD + sizeof(uint32_t) * SPAI_WARPS * s->EW;
-      if (!g_spai_attr && smem > 48 * 1024)
+      if (smem > 48 * 1024 && smem > g_spai_smem_opt_in)
         {
           CUDA_OK(ctx, cudaFuncSetAttribute(k_spai_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          g_spai_attr = true;
+          g_spai_smem_opt_in = smem;
         }
       k_spai_solve<<<(ctx->nloc + SPAI_WARPS - 1) / SPAI_WARPS, 32 * SPAI_WARPS, smem, st>>>(
         ctx->nloc, ctx->row0, s->EW, s->d_nbr, s->d_ecol, s->d_nf, s->d_val, s->d_info);
