@@ -39,40 +39,73 @@ def measured_peaks():
 
 
 class ClockSampler(threading.Thread):
-    """nvidia-smi clocks / throttle reasons during the timed region."""
+    """SM clock / power / throttle reasons during the timed regions.  NVML in-process (a query
+    costs ~0.1 ms and does not disturb the run; spawning nvidia-smi every few ms measurably slows
+    the HBM-bound mat-vec), nvidia-smi as the fallback."""
     Q = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,"
          "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,"
          "clocks_event_reasons.sw_power_cap")
+    REASONS = (("hw_slowdown", 0x8), ("hw_thermal_slowdown", 0x40), ("sw_thermal_slowdown", 0x20),
+               ("sw_power_cap", 0x4))
 
     def __init__(self, gpu_index):
         super().__init__(daemon=True)
         self.gpu = gpu_index
-        self.samples = []
+        self.samples = []      # (sm_mhz, sm_max_mhz, power_w, set of reasons)
         self.stop_flag = False
+        self.nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # NVML enumerates all GPUs of the box; CUDA_VISIBLE_DEVICES may renumber them
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES", "")
+            idx = gpu_index
+            if vis and all(x.strip().isdigit() for x in vis.split(",")):
+                idx = int(vis.split(",")[gpu_index])
+            self.handle = pynvml.nvmlDeviceGetHandleByIndex(idx)
+            self.nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def sample_nvml(self):
+        n, h = self.nvml, self.handle
+        sm = n.nvmlDeviceGetClockInfo(h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(h) / 1e3
+        try:
+            mask = n.nvmlDeviceGetCurrentClocksEventReasons(h)
+        except Exception:
+            mask = n.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        self.samples.append((float(sm), float(mx), float(pw), {k for k, bit in self.REASONS if mask & bit}))
+
+    def sample_smi(self):
+        out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
+                              "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
+        f = [x.strip() for x in out.strip().split(",")]
+        if len(f) >= 8:
+            names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+            self.samples.append((float(f[1]), float(f[2]), float(f[3]),
+                                 {k for k, v in zip(names, f[4:8]) if v.lower().startswith("active")}))
 
     def run(self):
         while not self.stop_flag:
             try:
-                out = subprocess.run(["nvidia-smi", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits",
-                                      "-i", str(self.gpu)], capture_output=True, text=True, timeout=5).stdout
-                f = [x.strip() for x in out.strip().split(",")]
-                if len(f) >= 8:
-                    self.samples.append(f)
+                if self.nvml:
+                    self.sample_nvml()
+                else:
+                    self.sample_smi()
             except Exception:
                 pass
-            time.sleep(0.05)
+            time.sleep(0.02 if self.nvml else 0.2)
 
     def summary(self):
         if not self.samples:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["unavailable"]}
-        sm = sorted(float(s[1]) for s in self.samples)
-        reasons = []
-        for name, k in (("hw_slowdown", 4), ("hw_thermal_slowdown", 5), ("sw_thermal_slowdown", 6),
-                        ("sw_power_cap", 7)):
-            if any(s[k].lower().startswith("active") for s in self.samples):
-                reasons.append(name)
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": float(self.samples[0][2]), "reasons": reasons,
-                "power_w_max": max(float(s[3]) for s in self.samples), "samples": len(self.samples)}
+        sm = sorted(s[0] for s in self.samples)
+        reasons = [k for k, _ in self.REASONS if any(k in s[3] for s in self.samples)]
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": self.samples[0][1], "reasons": reasons,
+                "power_w_max": max(s[2] for s in self.samples), "samples": len(self.samples), "source": self.source}
 
 
 def build_case(n_target, froude=0.28):

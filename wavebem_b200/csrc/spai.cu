@@ -38,6 +38,7 @@ struct SpaiState
   uint32_t *d_ecol = nullptr; // [npad][EW] near-field columns, sorted ascending, padded with NONE
   double *d_nf = nullptr;     // [npad][EW] near-field values of the merged constrained operator
   double *d_val = nullptr;    // [npad][K] rows of M
+  uint16_t *d_pos = nullptr;  // [nloc][K][K] position of S_b in the near-field row of S_a
   int *d_info = nullptr;      // number of singular local systems (those rows fall back to 1/a_ii)
   std::vector<uint32_t> h_nbr;
   bool pattern_ready = false;
@@ -203,19 +204,18 @@ __global__ void __launch_bounds__(256)
 
 #define SPAI_LD (SPAI_K + 1)
 #define SPAI_WARPS 4
+#define SPAI_NOPOS 0xffffu
 
-// One warp per local row i: gather T[b][a] = A[S_a, S_b] from the near-field rows, solve
-// T m = e_i by Gaussian elimination with partial pivoting, store m.
+// Once per sparsity pattern, one warp per local row i: pos[i][a][b] = position of column S_b in
+// the near-field row of S_a (binary search in the sorted ELL row), so that the per-solve gather
+// of A[S_a, S_b] is two plain loads.
 __global__ void __launch_bounds__(32 * SPAI_WARPS)
-  k_spai_solve(uint32_t nloc, uint32_t row0, uint32_t EW, const uint32_t *__restrict__ nbr,
-               const uint32_t *__restrict__ ecol, const double *__restrict__ nf, double *__restrict__ val,
-               int *__restrict__ info)
+  k_spai_positions(uint32_t nloc, uint32_t row0, uint32_t EW, const uint32_t *__restrict__ nbr,
+                   const uint32_t *__restrict__ ecol, uint16_t *__restrict__ pos)
 {
   extern __shared__ __align__(16) unsigned char spai_smem[];
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
-  double *T = reinterpret_cast<double *>(spai_smem) + (size_t)warp * SPAI_K * SPAI_LD;
-  uint32_t *ec = reinterpret_cast<uint32_t *>(reinterpret_cast<double *>(spai_smem) + (size_t)SPAI_WARPS * SPAI_K * SPAI_LD) +
-                 (size_t)warp * EW;
+  uint32_t *ec = reinterpret_cast<uint32_t *>(spai_smem) + (size_t)warp * EW;
   const uint32_t il = blockIdx.x * SPAI_WARPS + warp;
   if (il >= nloc) return;
   const uint32_t g = row0 + il;
@@ -223,12 +223,11 @@ __global__ void __launch_bounds__(32 * SPAI_WARPS)
   for (int a = 0; a < SPAI_K; ++a)
     {
       const uint32_t r = __shfl_sync(0xffffffffu, mine, a);
-      double v = (a == lane) ? 1.0 : 0.0; // padding: identity
+      uint16_t found = SPAI_NOPOS;
       if (r != SPAI_NONE)
         {
           for (uint32_t p = lane; p < EW; p += 32) ec[p] = ecol[(size_t)r * EW + p];
           __syncwarp();
-          v = 0.0;
           if (mine != SPAI_NONE)
             {
               uint32_t lo = 0, hi = EW; // first position with ec[pos] >= mine (NONE pads sort last)
@@ -240,10 +239,39 @@ __global__ void __launch_bounds__(32 * SPAI_WARPS)
                   else
                     hi = mid;
                 }
-              if (lo < EW && ec[lo] == mine) v = nf[(size_t)r * EW + lo];
+              if (lo < EW && ec[lo] == mine) found = (uint16_t)lo;
             }
           __syncwarp();
         }
+      pos[((size_t)il * SPAI_K + a) * SPAI_K + lane] = found;
+    }
+}
+
+// One warp per local row i: gather T[b][a] = A[S_a, S_b] from the near-field rows, solve
+// T m = e_i by Gaussian elimination with partial pivoting, store m.
+__global__ void __launch_bounds__(32 * SPAI_WARPS)
+  k_spai_solve(uint32_t nloc, uint32_t row0, uint32_t EW, const uint32_t *__restrict__ nbr,
+               const uint32_t *__restrict__ ecol, const uint16_t *__restrict__ pos,
+               const double *__restrict__ nf, double *__restrict__ val, int *__restrict__ info)
+{
+  extern __shared__ __align__(16) unsigned char spai_smem[];
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  double *T = reinterpret_cast<double *>(spai_smem) + (size_t)warp * SPAI_K * SPAI_LD;
+  const uint32_t il = blockIdx.x * SPAI_WARPS + warp;
+  if (il >= nloc) return;
+  const uint32_t g = row0 + il;
+  const uint32_t mine = nbr[(size_t)g * SPAI_K + lane]; // S_lane
+  const uint16_t *prow = pos + (size_t)il * SPAI_K * SPAI_K + lane;
+#pragma unroll 8
+  for (int a = 0; a < SPAI_K; ++a)
+    {
+      const uint32_t r = __shfl_sync(0xffffffffu, mine, a);
+      const uint16_t p = prow[a * SPAI_K];
+      double v = 0.0;
+      if (r == SPAI_NONE)
+        v = (a == lane) ? 1.0 : 0.0; // padding slot: identity row / column
+      else if (p != SPAI_NOPOS)
+        v = nf[(size_t)r * EW + p];
       T[lane * SPAI_LD + a] = v;
     }
   double e = (mine == g) ? 1.0 : 0.0;
@@ -360,6 +388,7 @@ void wbem_spai_free(wbem_ctx *ctx)
   cudaFree(s->d_ecol);
   cudaFree(s->d_nf);
   cudaFree(s->d_val);
+  cudaFree(s->d_pos);
   cudaFree(s->d_info);
   delete s;
   ctx->spai = nullptr;
@@ -394,12 +423,19 @@ static int spai_build_pattern(wbem_ctx *ctx)
   CUDA_OK(ctx, cudaMemcpyAsync(s->d_ecol, ell.data(), sizeof(uint32_t) * ell.size(), cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(s->d_nf, 0, sizeof(double) * ell.size(), ctx->stream));
   CUDA_OK(ctx, cudaMemsetAsync(s->d_val, 0, sizeof(double) * nbr_pad.size(), ctx->stream));
+  CUDA_OK(ctx, cudaMalloc((void **)&s->d_pos, sizeof(uint16_t) * std::max<size_t>(1, (size_t)ctx->nloc * K * K)));
+  if (ctx->nloc)
+    {
+      k_spai_positions<<<(ctx->nloc + SPAI_WARPS - 1) / SPAI_WARPS, 32 * SPAI_WARPS, sizeof(uint32_t) * SPAI_WARPS * s->EW,
+                         ctx->stream>>>(ctx->nloc, ctx->row0, s->EW, s->d_nbr, s->d_ecol, s->d_pos);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+    }
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   s->pattern_ready = true;
   return 0;
 }
 
-static size_t g_spai_smem_opt_in = 0; // largest dynamic shared-memory size opted in so far
 
 int wbem_spai_setup(wbem_ctx *ctx)
 {
@@ -422,14 +458,9 @@ int wbem_spai_setup(wbem_ctx *ctx)
   if (rc) return rc;
   if (ctx->nloc)
     {
-      const size_t smem = sizeof(double) * SPAI_WARPS * SPAI_K * SPAI_LD + sizeof(uint32_t) * SPAI_WARPS * s->EW;
-      if (smem > 48 * 1024 && smem > g_spai_smem_opt_in)
-        {
-          CUDA_OK(ctx, cudaFuncSetAttribute(k_spai_solve, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-          g_spai_smem_opt_in = smem;
-        }
+      const size_t smem = sizeof(double) * SPAI_WARPS * SPAI_K * SPAI_LD; // 33 KB: below the default limit
       k_spai_solve<<<(ctx->nloc + SPAI_WARPS - 1) / SPAI_WARPS, 32 * SPAI_WARPS, smem, st>>>(
-        ctx->nloc, ctx->row0, s->EW, s->d_nbr, s->d_ecol, s->d_nf, s->d_val, s->d_info);
+        ctx->nloc, ctx->row0, s->EW, s->d_nbr, s->d_ecol, s->d_pos, s->d_nf, s->d_val, s->d_info);
       ctx->launches++;
       CUDA_OK(ctx, cudaGetLastError());
     }
