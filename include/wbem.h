@@ -211,7 +211,8 @@ int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, do
 int wbem_time_assemble(wbem_ctx *ctx, int reps, double *ms_avg);
 /* issue-port probe: DFMA TFLOP/s with 2*n_int integer ALU instructions interleaved per 8 DFMAs
  * (n_int in {0,2,4,8,16}); n_int = 100/101/102/103: eight chains of DFMA / DADD / DMUL / alternating
- * DFMA-DADD only (instructions/s reported as 2 flop each).  Used to calibrate the assembly kernel's
+ * DFMA-DADD only (instructions/s reported as 2 flop each); 104: FP64 tensor-core MMA (m8n8k4) rate;
+ * 105/106/107: the DFMA rate of 8 chains with 1 / 2 / 0 such MMAs issued beside them per iteration.  Used to calibrate the assembly kernel's
  * instruction budget */
 int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops);
 /* device self test of the fast 1/sqrt used by the regular-pair kernel: out[i] = rsqrt(in[i]) */

@@ -373,7 +373,7 @@ def test_pure_neumann_with_constraints(wb, orc):
     ctx.close()
 
 
-@pytest.mark.parametrize("n_tmp,band", [(12, 100), (100, 0), (30, 40)])
+@pytest.mark.parametrize("n_tmp,band", [(12, 100), (100, 0), (30, 40), (400, 0)])
 def test_gmres_restart_and_preconditioner_options(wb, orc, tank_case, n_tmp, band):
     """Short restart cycles (AdditionalData(n_tmp)) and other band widths, incl. no preconditioner."""
     t = tank_case

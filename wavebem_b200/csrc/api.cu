@@ -99,6 +99,36 @@ __global__ void k_opcode_probe(double *out, int iters)
 }
 
 
+// DMMA probe: NF independent DFMA chains + NM independent m8n8k4 FP64 tensor-core MMAs per
+// iteration -- does the FP64 tensor pipe run beside the FP64 FMA pipe on this chip?
+template <int NF, int NM>
+__global__ void k_dmma_probe(double *out, int iters)
+{
+  double a[8], c0[4], c1[4];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-9 + k;
+#pragma unroll
+  for (int k = 0; k < 4; ++k) c0[k] = c1[k] = 0.0;
+  const double b = 1.0000001, c = 1e-7, ma = 1e-3 * (threadIdx.x & 3), mb = 1e-3 * (threadIdx.x >> 2);
+  for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+      for (int k = 0; k < NF; ++k) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(b), "d"(c));
+#pragma unroll
+      for (int k = 0; k < NM; ++k)
+        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                     : "+d"(c0[k]), "+d"(c1[k])
+                     : "d"(ma), "d"(mb));
+    }
+  double s = 0;
+#pragma unroll
+  for (int k = 0; k < 8; ++k) s += a[k];
+#pragma unroll
+  for (int k = 0; k < 4; ++k) s += c0[k] + c1[k];
+  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
+}
+
+
 extern "C" {
 
 int wbem_version(void) { return 100; }
@@ -1061,7 +1091,11 @@ int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops)
         case 101: k_opcode_probe<1><<<blocks, threads, 0, st>>>(d, iters); break; // DADD only
         case 102: k_opcode_probe<2><<<blocks, threads, 0, st>>>(d, iters); break; // DMUL only
         case 103: k_opcode_probe<3><<<blocks, threads, 0, st>>>(d, iters); break; // DFMA/DADD alternating
-        default: cudaFree(d); cudaFree(di); WBEM_FAIL(ctx, -1, "n_int must be 0,2,4,8,16 or 100..103");
+        case 104: k_dmma_probe<0, 4><<<blocks, threads, 0, st>>>(d, iters); break; // 4 DMMA, no DFMA
+        case 105: k_dmma_probe<8, 1><<<blocks, threads, 0, st>>>(d, iters); break; // 8 DFMA + 1 DMMA
+        case 106: k_dmma_probe<8, 2><<<blocks, threads, 0, st>>>(d, iters); break; // 8 DFMA + 2 DMMA
+        case 107: k_dmma_probe<8, 0><<<blocks, threads, 0, st>>>(d, iters); break; // 8 DFMA (same loop)
+        default: cudaFree(d); cudaFree(di); WBEM_FAIL(ctx, -1, "n_int must be 0,2,4,8,16 or 100..107");
         }
       ctx->launches++;
       CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], st));
@@ -1073,6 +1107,8 @@ int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops)
   cudaFree(d);
   cudaFree(di);
   *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
+  // 104: report the tensor-pipe rate itself (4 MMAs of 8x8x4 FMAs per warp and iteration)
+  if (n_int == 104) *tflops = 2.0 * 4.0 * 256.0 * (double)iters * blocks * (threads / 32) / (best * 1e-3) / 1e12;
   return 0;
 }
 
