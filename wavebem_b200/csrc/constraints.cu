@@ -70,6 +70,12 @@ struct ConState
   std::vector<uint32_t> out_lines, out_ptr{0}, out_col;
   std::vector<double> out_val, out_inhom;
   int last_cg_iters = 0;
+  // host walk: only the dofs whose double-node set has more than one member matter (a few % of N)
+  std::vector<uint32_t> multi;
+  std::vector<uint8_t> kind;       // per dof: 0 none, 1 one entry (master, 1.0), 2 inhomogeneity only
+  std::vector<uint32_t> master;
+  std::vector<double> inhom;
+  std::vector<double> h_rhs;       // pinned-size staging of tmp_rhs
 };
 
 static ConState *con_state(wbem_ctx *ctx)
@@ -471,6 +477,22 @@ static int con_prepare(wbem_ctx *ctx)
   CUDA_OK(ctx, cudaMalloc((void **)&s->d_barrier, sizeof(unsigned int)));
   CUDA_OK(ctx, cudaMalloc((void **)&s->d_iters, sizeof(int)));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  // dofs with a non-trivial double-node set, and (should a caller's sets not be symmetric) their members
+  s->multi.clear();
+  {
+    std::vector<uint8_t> in(N, 0);
+    for (uint32_t i = 0; i < N; ++i)
+      if (ctx->h_dn_ptr[i + 1] - ctx->h_dn_ptr[i] >= 2)
+        {
+          in[i] = 1;
+          for (uint32_t k = ctx->h_dn_ptr[i]; k < ctx->h_dn_ptr[i + 1]; ++k) in[ctx->h_dn_idx[k]] = 1;
+        }
+    for (uint32_t i = 0; i < N; ++i)
+      if (in[i]) s->multi.push_back(i);
+  }
+  s->kind.assign(N, 0);
+  s->master.assign(N, 0);
+  s->inhom.assign(N, 0.0);
   s->ready = true;
   return 0;
 }
@@ -562,23 +584,23 @@ int wbem_compute_constraints_device(wbem_ctx *ctx, const double *d_tmp_rhs)
   // which inputs does the walk need?  normals: a set with two Dirichlet dofs; gradients: such a
   // pair with different normals; tmp_rhs values: a Dirichlet first with a Neumann double
   bool need_normals = false, need_rhs = false;
-  for (uint32_t i = 0; i < N && !(need_normals && need_rhs); ++i)
+  for (uint32_t i : s->multi)
     {
       const uint32_t b = dn_ptr[i], e = dn_ptr[i + 1];
-      if (e - b < 2) continue;
       int nd = 0;
       for (uint32_t k = b; k < e; ++k) nd += surf[dn_idx[k]] == 1;
       if (nd >= 2) need_normals = true;
       if (nd >= 1 && nd < (int)(e - b)) need_rhs = true;
+      if (need_normals && need_rhs) break;
+    }
+  if (need_rhs)
+    { // start the copy now: it overlaps the normals' kernels
+      s->h_rhs.resize(N);
+      CUDA_OK(ctx, cudaMemcpyAsync(s->h_rhs.data(), d_tmp_rhs, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
     }
   if (need_normals && (rc = con_normals(ctx))) return rc;
-  std::vector<double> h_rhs;
-  if (need_rhs)
-    {
-      h_rhs.resize(N);
-      CUDA_OK(ctx, cudaMemcpyAsync(h_rhs.data(), d_tmp_rhs, sizeof(double) * N, cudaMemcpyDeviceToHost, ctx->stream));
-      CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
-    }
+  if (need_rhs) CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  const double *h_rhs = s->h_rhs.data();
   const double *nrm = s->h_normals.data();
   auto ndist = [&](uint32_t a, uint32_t b) {
     double d2 = 0;
@@ -587,24 +609,24 @@ int wbem_compute_constraints_device(wbem_ctx *ctx, const double *d_tmp_rhs)
   };
   bool need_grads = false;
   if (need_normals)
-    for (uint32_t i = 0; i < N && !need_grads; ++i)
+    for (uint32_t i : s->multi)
       {
-        const uint32_t b = dn_ptr[i], e = dn_ptr[i + 1];
-        if (e - b < 2 || surf[i] != 1) continue;
-        for (uint32_t k = b; k < e; ++k)
+        if (surf[i] != 1) continue;
+        for (uint32_t k = dn_ptr[i]; k < dn_ptr[i + 1]; ++k)
           if (dn_idx[k] != i && surf[dn_idx[k]] == 1 && !(ndist(dn_idx[k], i) < 1e-4)) need_grads = true;
+        if (need_grads) break;
       }
   if (need_grads && (rc = con_gradients(ctx, d_tmp_rhs))) return rc;
   const double *grd = s->h_grads.data();
 
-  // the walk of :1002-1101.  kind: 0 none, 1 one entry (master, 1.0), 2 inhomogeneity only
-  std::vector<uint8_t> kind(N, 0);
-  std::vector<uint32_t> master(N, 0);
-  std::vector<double> inhom(N, 0.0);
-  for (uint32_t i = 0; i < N; ++i)
+  // the walk of :1002-1101 over the non-trivial sets (ascending dof order, like the reference loop)
+  std::vector<uint8_t> &kind = s->kind;
+  std::vector<uint32_t> &master = s->master;
+  std::vector<double> &inhom = s->inhom;
+  for (uint32_t i : s->multi) kind[i] = 0;
+  for (uint32_t i : s->multi)
     {
       const uint32_t b = dn_ptr[i], e = dn_ptr[i + 1];
-      if (e - b < 2) continue;
       uint32_t first = dn_idx[b];
       for (uint32_t k = b; k < e; ++k)
         if (surf[dn_idx[k]] == 1)
@@ -657,31 +679,43 @@ int wbem_compute_constraints_device(wbem_ctx *ctx, const double *d_tmp_rhs)
             }
         }
     }
-  // merge with the caller's hanging-node lines, sorted by constrained dof (ConstraintMatrix::close)
-  std::vector<int32_t> base_of(N, -1);
-  for (size_t k = 0; k < s->base_lines.size(); ++k) base_of[s->base_lines[k]] = (int32_t)k;
+  // merge with the caller's hanging-node lines, sorted by constrained dof (ConstraintMatrix::close):
+  // two sorted lists -- the dofs of the non-trivial sets and the (sorted) hanging-node lines
+  std::vector<uint32_t> base_order(s->base_lines.size());
+  for (size_t k = 0; k < base_order.size(); ++k) base_order[k] = (uint32_t)k;
+  std::sort(base_order.begin(), base_order.end(),
+            [&](uint32_t x, uint32_t y) { return s->base_lines[x] < s->base_lines[y]; });
   s->out_lines.clear();
   s->out_ptr.assign(1, 0);
   s->out_col.clear();
   s->out_val.clear();
   s->out_inhom.clear();
-  for (uint32_t i = 0; i < N; ++i)
+  size_t im = 0, ib = 0;
+  while (im < s->multi.size() || ib < base_order.size())
     {
-      if (base_of[i] < 0 && kind[i] == 0) continue;
-      s->out_lines.push_back(i);
-      if (base_of[i] >= 0)
-        for (uint32_t k = s->base_ptr[base_of[i]]; k < s->base_ptr[base_of[i] + 1]; ++k)
-          {
-            s->out_col.push_back(s->base_col[k]);
-            s->out_val.push_back(s->base_val[k]);
-          }
-      if (kind[i] == 1)
+      const uint32_t dm = im < s->multi.size() ? s->multi[im] : CON_NONE;
+      const uint32_t db = ib < base_order.size() ? s->base_lines[base_order[ib]] : CON_NONE;
+      const uint32_t i = std::min(dm, db);
+      const bool has_base = db == i, has_set = dm == i && kind[i] != 0;
+      if (has_base || has_set)
         {
-          s->out_col.push_back(master[i]);
-          s->out_val.push_back(1.0);
+          s->out_lines.push_back(i);
+          if (has_base)
+            for (uint32_t k = s->base_ptr[base_order[ib]]; k < s->base_ptr[base_order[ib] + 1]; ++k)
+              {
+                s->out_col.push_back(s->base_col[k]);
+                s->out_val.push_back(s->base_val[k]);
+              }
+          if (has_set && kind[i] == 1)
+            {
+              s->out_col.push_back(master[i]);
+              s->out_val.push_back(1.0);
+            }
+          s->out_ptr.push_back((uint32_t)s->out_col.size());
+          s->out_inhom.push_back(has_set ? inhom[i] : 0.0);
         }
-      s->out_ptr.push_back((uint32_t)s->out_col.size());
-      s->out_inhom.push_back(kind[i] ? inhom[i] : 0.0);
+      if (dm == i) ++im;
+      if (db == i) ++ib;
     }
   return wbem_set_constraints(ctx, (uint32_t)s->out_lines.size(), s->out_lines.data(), s->out_ptr.data(),
                               s->out_col.data(), s->out_val.data(), s->out_inhom.data());
