@@ -22,7 +22,6 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import wavebem_b200 as wb  # noqa: E402
 from wavebem_b200 import dist as wd  # noqa: E402
 from wavebem_b200 import meshgen  # noqa: E402
-from wavebem_b200.constraints import compute_constraints  # noqa: E402
 
 
 def main():
@@ -44,7 +43,6 @@ def main():
     base = meshgen.wigley_tank_for_nodes(args.nodes)
     kw = {k: base.meta[k] for k in ("nxm", "nt", "nxu", "nxd", "nz", "nzh")}
     n = base.n_nodes
-    nn = meshgen.cell_normals_at_nodes(base)
     ctx = wb.Context(device=local, rank=rank, world_size=world, gmres_tol=args.tol, gmres_max_steps=1000,
                      precond_kind=1 if args.precond == "spai" else 0, auto_constraints=1)
     ctx.set_topology(n, base.cells, base.dir_flag, base.dn_ptr, base.dn_idx)

@@ -331,15 +331,11 @@ __global__ void __launch_bounds__(32 * SPAI_WARPS)
   else
     { // fall back to the diagonal (Jacobi) for this row
       if (lane == 0) atomicAdd(info, 1);
-      double d = 0.0;
-      {
-        const uint32_t base = 0;
-        (void)base;
-        for (uint32_t pp = lane; pp < EW; pp += 32)
-          if (ecol[(size_t)g * EW + pp] == g) d = nf[(size_t)g * EW + pp];
+      double d = 0.0; // a_gg: exactly one lane finds column g in the near-field row of g
+      for (uint32_t pp = lane; pp < EW; pp += 32)
+        if (ecol[(size_t)g * EW + pp] == g) d = nf[(size_t)g * EW + pp];
 #pragma unroll
-        for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
-      }
+      for (int off = 16; off > 0; off >>= 1) d += __shfl_xor_sync(0xffffffffu, d, off);
       m = (mine == g) ? (d != 0.0 ? 1.0 / d : 1.0) : 0.0;
     }
   if (mine == SPAI_NONE) m = 0.0;
