@@ -95,6 +95,12 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t n_dofs, uint32_t n_cells,
  * (the FEValues of :133-137, 192-196, 495-501) are recomputed on the device from them. */
 int wbem_set_geometry(wbem_ctx *ctx, const double *support_points);
 int wbem_set_geometry_dev(wbem_ctx *ctx, const double *d_support_points);
+/* Optional, after wbem_set_geometry: the literal FEValues output of the regular rule
+ * (source/bem_problem.cc:192-196) -- q_points[C][nq][3], normals[C][nq][3], JxW[C][nq] in the
+ * caller's cell order -- used for the regular pairs instead of the values recomputed from the
+ * support points (bitwise the reference's inputs, e.g. for a mapping that is not Q1).  Singular
+ * pairs keep using the Q1 mapping of the support points.  The next wbem_set_geometry drops them. */
+int wbem_set_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW);
 
 /* BEMProblem<3>::assemble_system (source/bem_problem.cc:106-590): both matrices for this
  * context's rows, plus alpha (compute_alpha, :594-618) fused behind it. */
@@ -168,6 +174,10 @@ int wbem_spai_pattern_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *c
  * Returns 1 when GMRES hits max_steps (SolverControl::NoConvergence). */
 int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double *tmp_rhs,
                       int *iters, double *last_res);
+/* solver.solve(cc, sol, system_rhs, preconditioner) alone (source/bem_problem.cc:853): GMRES on the
+ * constrained operator for a right-hand side the caller prepared (compute_rhs + distribute_rhs),
+ * x0 = 0, with the preconditioner wbem_params selects.  Same return convention as solve_system. */
+int wbem_gmres(wbem_ctx *ctx, const double *rhs, double *sol, int *iters, double *last_res);
 /* BEMProblem<3>::solve (source/bem_problem.cc:969-987) = assemble_system + solve_system,
  * with the geometry upload in front (the caller moved the mesh,
  * source/free_surface.cc:5306-5307). */

@@ -621,3 +621,50 @@ def test_compute_constraints_inside_the_library(wb, orc):
         assert np.abs(r).max() < 1e-9
         ctx.close()
         auto.close()
+
+
+def test_gmres_entry_point_and_literal_fevalues_input(wb, orc, tank_case):
+    """wbem_gmres = solver.solve(cc, sol, system_rhs, preconditioner) alone (bem_problem.cc:853);
+    wbem_set_fevalues = the reference's own FEValues output (:192-196) as the regular-pair input."""
+    t = tank_case
+    m = t["m"]
+    n = m.n_nodes
+    ctx = _ctx(wb, m, gmres_tol=1e-10, gmres_max_steps=400)
+    ctx.assemble()
+    ctx.set_masks(m.surface_nodes, m.other_nodes)
+    ctx.set_constraints(t["cl"])
+    rhs = ctx.distribute_rhs(ctx.compute_rhs(t["bc"]))
+    sol, it, res = ctx.gmres(rhs)
+    z = np.zeros(n)
+    _, _, it2, _ = ctx.solve_system(z, z, t["bc"])
+    assert it == it2 and res <= 1e-10 and np.array_equal(sol, ctx.get_sol())
+    assert np.abs(ctx.constrained_vmult(sol) - rhs).max() < 1e-8
+    # linearity of the solve in the right-hand side
+    sol2, _, _ = ctx.gmres(-2.0 * rhs)
+    assert np.linalg.norm(sol2 + 2.0 * sol) <= 1e-7 * np.linalg.norm(sol)
+    rows_n, rows_d = ctx.get_rows(0), ctx.get_rows(1)
+    uv, w = orc.qgauss2(4)
+    nc = m.n_cells
+    qp, nr, jw = np.zeros((nc, 16, 3)), np.zeros((nc, 16, 3)), np.zeros((nc, 16))
+    for c in range(nc):
+        qp[c], nr[c], jw[c], _ = orc.fe_values(m.xyz[m.cells[c].astype(np.int64)], m.dir_flag[c], uv, w)
+    ctx.set_fevalues(qp, nr, jw)
+    ctx.assemble()
+    assert rel_err_rowscaled(ctx.get_rows(1), rows_d) < 1e-13
+    assert rel_err_rowscaled(ctx.get_rows(0), rows_n, diag=t["alpha"]) < 1e-13
+    assert rel_err_rowscaled(ctx.get_rows(1), t["od"]) < ENTRY_TOL
+    assert rel_err_rowscaled(ctx.get_rows(0), t["on"], diag=t["alpha"]) < ENTRY_TOL
+    # scaled JxW scales the regular part of D: the values really are taken from the caller
+    ctx.set_fevalues(qp, nr, 2.0 * jw)
+    ctx.assemble()
+    d2 = ctx.get_rows(1)
+    single = np.nonzero(np.diff(m.dn_ptr.astype(np.int64)) == 1)[0][::37]   # rows without double nodes
+    for i in single:
+        far = np.linalg.norm(m.xyz - m.xyz[i], axis=1) > 2.0               # columns fed by regular pairs only
+        sel = far & (np.abs(rows_d[i]) > 1e-12)
+        assert sel.any() and np.abs(d2[i][sel] / rows_d[i][sel] - 2.0).max() < 1e-9
+    # the next set_geometry goes back to the values recomputed from the support points
+    ctx.set_geometry(m.xyz)
+    ctx.assemble()
+    assert np.array_equal(ctx.get_rows(1), rows_d) and np.array_equal(ctx.get_rows(0), rows_n)
+    ctx.close()

@@ -136,3 +136,20 @@ def test_spai_pattern_invariants_and_locality(wb):
             d32 = cKDTree(m.xyz).query(m.xyz, k=32)[0][:, -1]
             ratio = tree_d.max(axis=1) / d32
             assert np.median(ratio) < 1.2 and np.percentile(ratio, 99) < 3.0
+
+
+def test_bench_reference_iteration_table():
+    """bench.py --impl reference runs the GMRES iteration count the reference's band preconditioner
+    needs at the benchmark size (table measured with precond_kind = 0)."""
+    import importlib.util
+    import os
+    spec = importlib.util.spec_from_file_location("bench", os.path.join(os.path.dirname(os.path.dirname(__file__)), "bench.py"))
+    bench = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(bench)
+    assert bench.reference_band_iters(20073) == 83 and bench.reference_band_iters(57001) == 154
+    assert bench.reference_band_iters(100) == bench.BAND_ITERS[0][1]
+    assert bench.reference_band_iters(10 ** 6) == bench.BAND_ITERS[-1][1]
+    xs = [bench.reference_band_iters(n) for n in range(4000, 81000, 1000)]
+    assert all(b >= a for a, b in zip(xs, xs[1:]))
+    peak, src = bench.measured_peaks()
+    assert peak > 1000 and isinstance(src, str)

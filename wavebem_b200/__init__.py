@@ -79,7 +79,8 @@ ABI_SYMBOLS = [
     "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
     "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
     "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",
-    "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations",
+    "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations", "wbem_gmres",
+    "wbem_set_fevalues",
 ]
 
 
@@ -173,6 +174,19 @@ class Context:
                                              _dp(cl.col), _dp(cl.val), _dp(cl.inhom)))
 
     # --- compute ---
+    def set_fevalues(self, q_points, normals, jxw):
+        self._chk(lib().wbem_set_fevalues(self._h, _dp(_f64(q_points)), _dp(_f64(normals)), _dp(_f64(jxw))))
+
+    def gmres(self, rhs, raise_on_no_convergence=True):
+        """solver.solve(cc, sol, system_rhs, preconditioner) for a prepared right-hand side."""
+        sol = np.empty(self.n)
+        it, res = C.c_int(0), C.c_double(0)
+        rc = self._chk(lib().wbem_gmres(self._h, _dp(_f64(rhs)), _dp(sol), C.byref(it), C.byref(res)),
+                       allow_positive=True)
+        if rc > 0 and raise_on_no_convergence:
+            raise NoConvergence(it.value, res.value)
+        return sol, it.value, res.value
+
     def assemble(self):
         self._chk(lib().wbem_assemble(self._h))
 

@@ -483,6 +483,7 @@ int wbem_set_geometry_dev(wbem_ctx *ctx, const double *d_support_points)
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_xyz, d_support_points, sizeof(double) * 3 * (size_t)ctx->N,
                                cudaMemcpyDeviceToDevice, ctx->stream));
   ctx->have_geometry = true;
+  ctx->fevalues_given = false; // quadrature data follow the new support points again
   ctx->assembled = false;
   ctx->have_alpha = false;
   ctx->geom_version++;
@@ -499,6 +500,7 @@ int wbem_set_geometry(wbem_ctx *ctx, const double *support_points)
                                cudaMemcpyHostToDevice, ctx->stream));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); // caller may reuse its buffer
   ctx->have_geometry = true;
+  ctx->fevalues_given = false; // quadrature data follow the new support points again
   ctx->assembled = false;
   ctx->have_alpha = false;
   ctx->geom_version++;
@@ -511,7 +513,7 @@ static int assemble_async(wbem_ctx *ctx)
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   cudaStream_t st = ctx->stream;
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[6], st));
-  int rc = wbem_launch_geometry(ctx);
+  int rc = ctx->fevalues_given ? 0 : wbem_launch_geometry(ctx); // caller-supplied FEValues stay in place
   if (rc) return rc;
   rc = wbem_launch_assemble(ctx); // records ev[0..2]
   if (rc) return rc;
@@ -841,6 +843,36 @@ int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double 
   CUDA_OK(ctx, cudaMemcpyAsync(dphi_dn, d_dphi, nb, cudaMemcpyDeviceToHost, st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   return rc;
+}
+
+int wbem_gmres(wbem_ctx *ctx, const double *rhs, double *sol, int *iters, double *last_res)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_gmres before wbem_set_topology");
+  if (!rhs || !sol) WBEM_FAIL(ctx, -1, "null argument");
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  cudaStream_t st = ctx->stream;
+  const size_t nb = sizeof(double) * ctx->N;
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[5], rhs, nb, cudaMemcpyHostToDevice, st));
+  const int rc = wbem_solve_system_device(ctx, nullptr, nullptr, ctx->d_tmp[5], iters, last_res);
+  if (rc < 0) return rc;
+  CUDA_OK(ctx, cudaMemcpyAsync(sol, ctx->d_sol, nb, cudaMemcpyDeviceToHost, st));
+  CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return rc;
+}
+
+int wbem_set_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->have_geometry) WBEM_FAIL(ctx, -3, "wbem_set_fevalues needs the support points first (wbem_set_geometry)");
+  if (!q_points || !normals || !JxW) WBEM_FAIL(ctx, -1, "null argument");
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  const int rc = wbem_upload_fevalues(ctx, q_points, normals, JxW);
+  if (rc) return rc;
+  ctx->fevalues_given = true;
+  ctx->assembled = false;
+  ctx->have_alpha = false;
+  return 0;
 }
 
 int wbem_solve(wbem_ctx *ctx, const double *support_points, double *phi, double *dphi_dn,

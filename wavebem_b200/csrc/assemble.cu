@@ -78,6 +78,49 @@ __global__ void k_cell_geometry(uint32_t C, int nq, const double *__restrict__ x
   g[6 * nq + q] = cn * w * (1.0 / FOUR_PI);
 }
 
+// The literal FEValues of the regular rule handed over by the caller (reference :192-196:
+// get_quadrature_points / get_normal_vectors / JxW), caller's cell order, folded into the same
+// per-(cell,q) constants as k_cell_geometry.
+__global__ void k_fevalues_to_geometry(uint32_t C, int nq, const uint32_t *__restrict__ cell_order,
+                                       const double *__restrict__ qp, const double *__restrict__ nrm,
+                                       const double *__restrict__ jxw, double *__restrict__ geo)
+{
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t p = t / nq; // processing position
+  const int q = t - p * nq;
+  if (p >= C) return;
+  const size_t src = (size_t)cell_order[p] * nq + q;
+  double *g = geo + (size_t)p * 7 * nq;
+  const double w = jxw[src];
+  g[0 * nq + q] = qp[3 * src + 0];
+  g[1 * nq + q] = qp[3 * src + 1];
+  g[2 * nq + q] = qp[3 * src + 2];
+  g[3 * nq + q] = nrm[3 * src + 0] * w * (-1.0 / FOUR_PI);
+  g[4 * nq + q] = nrm[3 * src + 1] * w * (-1.0 / FOUR_PI);
+  g[5 * nq + q] = nrm[3 * src + 2] * w * (-1.0 / FOUR_PI);
+  g[6 * nq + q] = w * (1.0 / FOUR_PI);
+}
+
+int wbem_upload_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW)
+{
+  const int nq = ctx->qt.nq;
+  const size_t n = (size_t)ctx->C * nq;
+  if (n == 0) return 0;
+  double *d = nullptr;
+  CUDA_OK(ctx, cudaMalloc((void **)&d, sizeof(double) * 7 * n));
+  cudaStream_t st = ctx->stream;
+  CUDA_OK(ctx, cudaMemcpyAsync(d, q_points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(ctx, cudaMemcpyAsync(d + 3 * n, normals, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
+  CUDA_OK(ctx, cudaMemcpyAsync(d + 6 * n, JxW, sizeof(double) * n, cudaMemcpyHostToDevice, st));
+  k_fevalues_to_geometry<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->C, nq, ctx->d_cell_order, d, d + 3 * n,
+                                                                     d + 6 * n, ctx->d_cellgeo);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  CUDA_OK(ctx, cudaStreamSynchronize(st));
+  cudaFree(d);
+  return 0;
+}
+
 int wbem_launch_geometry(wbem_ctx *ctx)
 {
   const int nq = ctx->qt.nq;

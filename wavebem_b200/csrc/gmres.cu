@@ -426,19 +426,26 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
       g_timer.end();
       if (rc) return rc;
     }
+  // wbem_gmres: the caller supplies system_rhs as it stands (d_bc = that vector, no unpack)
+  const bool rhs_given = (d_phi == nullptr);
+  if (rhs_given)
+    CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_rhs, d_bc, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
   // system_rhs (:839) and constrained rows (:845)
-  g_timer.begin(T_RHS);
-  rc = wbem_apply_operator(ctx, 1, d_bc, ctx->d_rhs, false);
-  g_timer.end();
-  if (rc) return rc;
-  if (ctx->p.auto_constraints)
+  if (!rhs_given)
+    {
+      g_timer.begin(T_RHS);
+      rc = wbem_apply_operator(ctx, 1, d_bc, ctx->d_rhs, false);
+      g_timer.end();
+      if (rc) return rc;
+    }
+  if (ctx->p.auto_constraints && !rhs_given)
     { // compute_constraints(constraints, tmp_rhs) (:845)
       g_timer.begin(T_CONSTRAINTS);
       rc = wbem_compute_constraints_device(ctx, d_bc);
       g_timer.end();
       if (rc) return rc;
     }
-  if (ctx->n_lines)
+  if (ctx->n_lines && !rhs_given)
     {
       k_distribute_rhs<<<(ctx->n_lines + 255) / 256, 256, 0, st>>>(ctx->n_lines, ctx->d_con_lines,
                                                                    ctx->d_con_inhom, ctx->d_rhs);
@@ -552,8 +559,11 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   while (state == 0);
   g_timer.end();
   // unpack (:869-879)
-  k_unpack<<<nb, 256, 0, st>>>(N, ctx->d_surf, x, d_phi, d_dphi_dn);
-  ctx->launches++;
+  if (!rhs_given)
+    {
+      k_unpack<<<nb, 256, 0, st>>>(N, ctx->d_surf, x, d_phi, d_dphi_dn);
+      ctx->launches++;
+    }
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   CUDA_OK(ctx, cudaGetLastError());

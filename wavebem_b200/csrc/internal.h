@@ -150,6 +150,7 @@ struct wbem_ctx
   double *d_xyz = nullptr;     // [N][3]
   double *d_cellgeo = nullptr; // [C][7][nq] in processing order
   bool have_geometry = false, assembled = false, have_alpha = false;
+  bool fevalues_given = false; // cellgeo was filled by wbem_set_fevalues, not from the support points
   bool has_degenerate_cells = false; // a cell lists the same dof twice -> simple kernel
 
   // matrices: nloc x ld, row-major, columns in storage order (colperm)
@@ -236,6 +237,7 @@ struct wbem_ctx
 // assemble.cu
 int wbem_upload_tables(wbem_ctx *ctx);
 int wbem_launch_geometry(wbem_ctx *ctx);
+int wbem_upload_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW);
 int wbem_launch_assemble(wbem_ctx *ctx);
 int wbem_launch_alpha(wbem_ctx *ctx, bool from_matrix = false);
 // operator.cu
