@@ -299,3 +299,43 @@ def test_l2_projected_normals_and_surface_gradients(orc):
         assert np.abs(np.linalg.norm(nr, axis=1) - 1).max() < 1e-14
         errs.append(np.sqrt(np.mean(np.sum((nr - rad) ** 2, axis=1))))
     assert errs[1] < 0.6 * errs[0] and errs[1] < 0.03
+
+
+def test_compute_constraints_sharp_dirichlet_edges_recover_the_normal_derivative(orc):
+    """compute_constraints on an edge between two Dirichlet faces (bem_problem.cc:1054-1075): the
+    imposed normal derivatives follow from the two surface gradients.  For a linear potential on a
+    cube (orthogonal faces) the formula must return grad(phi).n exactly on both sides; flat
+    Dirichlet-Dirichlet, Dirichlet-Neumann and Neumann-Neumann double nodes give the other three
+    kinds of lines."""
+    from wavebem_b200 import meshgen
+    from wavebem_b200.constraints import compute_constraints
+    m = meshgen.cube(3)
+    grad = np.array([1.0, 2.0, -0.5])
+    phi = m.xyz @ grad
+    s = (m.node_patch <= 2).astype(float)          # faces z0, z1, y0 Dirichlet; y1, x0, x1 Neumann
+    nrm = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
+    grd = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, phi, s)
+    cl = compute_constraints(m.dn_ptr, m.dn_idx, s, phi, nodes_normals=nrm, node_surface_gradients=grd)
+    kinds = {"sharp": 0, "dirichlet_neumann": 0, "neumann_neumann": 0}
+    for k, line in enumerate(cl.lines):
+        ent = list(zip(cl.col[cl.ptr[k]:cl.ptr[k + 1]], cl.val[cl.ptr[k]:cl.ptr[k + 1]]))
+        doubles = set(int(j) for j in m.double_nodes_set(line))
+        if s[line] == 1 and not ent:
+            # a Dirichlet dof on a sharp Dirichlet-Dirichlet edge: its unknown dphi/dn is imposed
+            others = [j for j in doubles if j != line and s[j] == 1]
+            assert others and abs(cl.inhom[k] - grad @ nrm[line]) < 1e-12
+            kinds["sharp"] += 1
+        elif s[line] == 0 and not ent:
+            # a Neumann double of a Dirichlet node: its potential is the imposed one
+            first = min(j for j in doubles if s[j] == 1)
+            assert cl.inhom[k] == phi[first]
+            kinds["dirichlet_neumann"] += 1
+        else:
+            assert len(ent) == 1 and ent[0][1] == 1.0 and int(ent[0][0]) in doubles and cl.inhom[k] == 0.0
+            assert s[line] == 0 and s[int(ent[0][0])] == 0
+            kinds["neumann_neumann"] += 1
+    assert all(v > 0 for v in kinds.values()), kinds
+    # every double node except the first of its set is constrained (first Dirichlet ones on sharp edges too)
+    n_sets = len({tuple(m.double_nodes_set(i)) for i in range(m.n_nodes) if len(m.double_nodes_set(i)) > 1})
+    n_in_sets = sum(1 for i in range(m.n_nodes) if len(m.double_nodes_set(i)) > 1)
+    assert n_in_sets - n_sets <= cl.n_lines <= n_in_sets
