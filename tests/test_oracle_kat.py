@@ -339,3 +339,49 @@ def test_compute_constraints_sharp_dirichlet_edges_recover_the_normal_derivative
     n_sets = len({tuple(m.double_nodes_set(i)) for i in range(m.n_nodes) if len(m.double_nodes_set(i)) > 1})
     n_in_sets = sum(1 for i in range(m.n_nodes) if len(m.double_nodes_set(i)) > 1)
     assert n_in_sets - n_sets <= cl.n_lines <= n_in_sets
+
+
+def test_singular_rule_on_a_warped_cell_against_adaptive_quadrature(orc):
+    """The 50-point QGaussOneOverR rule at each of the four vertices of a NON-planar bilinear cell
+    (the reference's singular branch, bem_problem.cc:261-525), against an adaptive polar
+    integration centred at the vertex (integrand * rho is smooth).  Pins the vertex <-> rule
+    orientation and the Q1 mapping on a cell without any symmetry."""
+    from scipy import integrate
+    X = np.array([[0.0, 0.0, 0.0], [1.3, 0.1, 0.2], [-0.1, 0.9, -0.15], [1.1, 1.2, 0.35]])
+    cells = np.array([[0, 1, 2, 3]], dtype=np.uint32)
+    ptr, idx = np.arange(5, dtype=np.uint32), np.arange(4, dtype=np.uint32)
+    on, od = orc.assemble_rows(X, cells, np.ones(1, np.uint8), ptr, idx)   # every (node, cell) pair is singular
+
+    def shape(u, v):
+        return np.array([(1 - u) * (1 - v), u * (1 - v), (1 - u) * v, u * v])
+
+    def geom(u, v):
+        tu = (1 - v) * (X[1] - X[0]) + v * (X[3] - X[2])
+        tv = (1 - u) * (X[2] - X[0]) + u * (X[3] - X[1])
+        cr = np.cross(tu, tv)
+        return shape(u, v) @ X, cr
+
+    ref_d, ref_n = np.zeros((4, 4)), np.zeros((4, 4))
+    for k, (u0, v0) in enumerate([(0, 0), (1, 0), (0, 1), (1, 1)]):
+        su, sv = (1 if u0 == 0 else -1), (1 if v0 == 0 else -1)
+
+        def integrand(rho, th, j, which):
+            u, v = u0 + su * rho * np.cos(th), v0 + sv * rho * np.sin(th)
+            y, cr = geom(u, v)
+            R = y - X[k]
+            r = np.linalg.norm(R)
+            f = shape(u, v)[j]
+            if which == 0:
+                return f * np.linalg.norm(cr) / (4 * np.pi * r) * rho
+            return f * (R @ cr) / (-4 * np.pi * r ** 3) * rho
+
+        for j in range(4):
+            for which, out in ((0, ref_d), (1, ref_n)):
+                val = 0.0
+                for a, b, rmax in ((0, np.pi / 4, lambda th: 1 / np.cos(th)), (np.pi / 4, np.pi / 2, lambda th: 1 / np.sin(th))):
+                    v, _ = integrate.dblquad(lambda rho, th: integrand(rho, th, j, which), a, b, 1e-14, rmax,
+                                             epsabs=1e-12, epsrel=1e-10)
+                    val += v
+                out[k, j] = val
+    assert np.abs(od - ref_d).max() < 2e-6 * np.abs(ref_d).max()
+    assert np.abs(on - ref_n).max() < 2e-5 * max(np.abs(ref_n).max(), 1e-3)
