@@ -385,3 +385,31 @@ def test_singular_rule_on_a_warped_cell_against_adaptive_quadrature(orc):
                 out[k, j] = val
     assert np.abs(od - ref_d).max() < 2e-6 * np.abs(ref_d).max()
     assert np.abs(on - ref_n).max() < 2e-5 * max(np.abs(ref_n).max(), 1e-3)
+
+
+def test_regular_rule_on_a_warped_cell_against_adaptive_quadrature(orc):
+    """Regular (node, cell) pairs, bem_problem.cc:241-260: the 4x4 Gauss integrals of both kernels
+    over a non-planar bilinear cell, seen from nodes a few cell sizes away, against scipy's adaptive
+    quadrature of the same integrands (normal orientation, JxW and shape functions included)."""
+    from scipy import integrate
+    X = np.array([[0.0, 0.0, 0.0], [1.3, 0.1, 0.2], [-0.1, 0.9, -0.15], [1.1, 1.2, 0.35],
+                  [3.0, 2.0, 1.5], [3.5, 2.0, 1.5], [3.0, 2.5, 1.5], [3.5, 2.5, 1.6]])
+    cells = np.array([[0, 1, 2, 3], [4, 5, 6, 7]], dtype=np.uint32)
+    ptr, idx = np.arange(9, dtype=np.uint32), np.arange(8, dtype=np.uint32)
+    for flag in (1, 0):
+        on, od = orc.assemble_rows(X, cells, np.array([flag, 1], np.uint8), ptr, idx)
+
+        def f(v, u, j, which, i):
+            sh = np.array([(1 - u) * (1 - v), u * (1 - v), (1 - u) * v, u * v])
+            tu = (1 - v) * (X[1] - X[0]) + v * (X[3] - X[2])
+            tv = (1 - u) * (X[2] - X[0]) + u * (X[3] - X[1])
+            cr = np.cross(tu, tv) * (1.0 if flag else -1.0)       # cell->direction_flag()
+            R = sh @ X[:4] - X[i]
+            r = np.linalg.norm(R)
+            return sh[j] * (np.linalg.norm(cr) / (4 * np.pi * r) if which == 0 else (R @ cr) / (-4 * np.pi * r ** 3))
+
+        for i in (4, 7):
+            for j in range(4):
+                d, _ = integrate.dblquad(f, 0, 1, 0, 1, args=(j, 0, i), epsabs=1e-14, epsrel=1e-12)
+                nn, _ = integrate.dblquad(f, 0, 1, 0, 1, args=(j, 1, i), epsabs=1e-14, epsrel=1e-12)
+                assert abs(od[i, j] / d - 1) < 5e-7 and abs(on[i, j] / nn - 1) < 5e-6
