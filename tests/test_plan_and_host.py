@@ -153,3 +153,63 @@ def test_bench_reference_iteration_table():
     assert all(b >= a for a, b in zip(xs, xs[1:]))
     peak, src = bench.measured_peaks()
     assert peak > 1000 and isinstance(src, str)
+
+
+def test_spai_pattern_gives_a_better_preconditioner_than_the_band(wb, orc):
+    """The ALGORITHM of spai.cu restated in numpy on the oracle's matrices (no GPU): with the
+    library's sparsity pattern, rows m_i = e_i^T A[S,S]^-1 precondition GMRES better than the
+    reference's band-100 LU on the same system (iterations of a plain numpy GMRES vs the oracle's)."""
+    import scipy.linalg as sla
+    from conftest import make_problem
+    from wavebem_b200 import meshgen
+    m = meshgen.wigley_tank(nxm=12, nt=6, nxu=4, nxd=6, nz=3, nzh=3)
+    bc, nn, cl = make_problem(m)
+    n = m.n_nodes
+    on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
+    alpha = orc.compute_alpha(on)
+    s, o = m.surface_nodes, m.other_nodes
+    A = on * o[None, :] - od * s[None, :]
+    A[np.arange(n), np.arange(n)] += alpha * o
+    b = orc.compute_rhs(on, od, alpha, s, o, bc)
+    for k, line in enumerate(cl.lines):
+        A[line, :] = 0.0
+        A[line, line] = 1.0
+        for c, v in zip(cl.col[cl.ptr[k]:cl.ptr[k + 1]], cl.val[cl.ptr[k]:cl.ptr[k + 1]]):
+            A[line, c] -= v
+        b[line] = cl.inhom[k]
+    rc, nbr, st = _spai_pattern(wb, m)
+    assert rc == 0
+    M = np.zeros((n, n))
+    for i in range(n):
+        S = nbr[i][nbr[i] != 0xFFFFFFFF].astype(np.int64)
+        M[i, S] = np.linalg.solve(A[np.ix_(S, S)].T, (S == i).astype(float))
+
+    def gmres_iters(prec, tol=1e-10, restart=98, maxit=400):
+        x, it = np.zeros(n), 0
+        while it < maxit:
+            r = prec(b - A @ x)
+            beta = np.linalg.norm(r)
+            V = np.zeros((restart + 1, n))
+            H = np.zeros((restart + 1, restart))
+            V[0] = r / beta
+            for k in range(restart):
+                w = prec(A @ V[k])
+                for _ in range(2):
+                    h = V[:k + 1] @ w
+                    w -= h @ V[:k + 1]
+                    H[:k + 1, k] += h
+                H[k + 1, k] = np.linalg.norm(w)
+                V[k + 1] = w / H[k + 1, k]
+                it += 1
+                e1 = np.zeros(k + 2)
+                e1[0] = beta
+                y, res, _, _ = np.linalg.lstsq(H[:k + 2, :k + 1], e1, rcond=None)
+                if np.linalg.norm(H[:k + 2, :k + 1] @ y - e1) <= tol or it >= maxit:
+                    return it
+            x += y @ V[:restart]
+        return it
+
+    it_spai = gmres_iters(lambda v: M @ v)
+    con = orc.Constraints(cl.n, cl.lines, cl.ptr, cl.col, cl.val, cl.inhom)
+    ref = orc.solve_system(on, od, s, o, bc, con, np.zeros(n), np.zeros(n), tol=1e-10, max_steps=400)
+    assert ref["converged"] and it_spai <= 0.6 * ref["iters"], (it_spai, ref["iters"])
