@@ -45,7 +45,25 @@ def case(name, mesh, surface_nodes, bc, tol=1e-12):
     print(name, "N", n, "lines", cl.n_lines, "GMRES its", sol["iters"])
 
 
+def projections(name):
+    """<name>_projections.npz: the L2 projections run by compute_constraints and the lines it produces
+    (computational_domain.cc:1525-1620, bem_problem.cc:1153-1293, :990-1105) on a committed case."""
+    g = np.load(os.path.join(HERE, name + ".npz"))
+    s = g["surface_nodes"]
+    nrm = orc.compute_normals(g["xyz"], g["cells"], g["dir_flag"])
+    grd = orc.compute_surface_gradients(g["xyz"], g["cells"], g["dir_flag"], g["bc"], s)
+    cl = compute_constraints(g["dn_ptr"], g["dn_idx"], s, g["bc"], nodes_normals=nrm, node_surface_gradients=grd)
+    np.savez_compressed(os.path.join(HERE, name + "_projections.npz"), case=name, nodes_normals=nrm,
+                        node_surface_gradients=grd, con_lines=cl.lines, con_ptr=cl.ptr, con_col=cl.col,
+                        con_val=cl.val, con_inhom=cl.inhom)
+    print(name, "projections: lines", cl.n_lines)
+
+
 if __name__ == "__main__":
+    if "--projections-only" in sys.argv:
+        projections("cube3_mixed")
+        projections("tank_small")
+        sys.exit(0)
     m = meshgen.cube(3, renumber="random", seed=1, flip_every=4)
     top = (m.node_patch == m.patch_names.index("z1")).astype(float)
     x0 = np.array([1.7, 1.3, 2.1])
@@ -55,3 +73,5 @@ if __name__ == "__main__":
     case("cube3_mixed", m, top, np.where(top == 1, 1 / r, -(d * nn).sum(1) / r ** 3))
     t = meshgen.wigley_tank(nxm=8, nt=4, nxu=3, nxd=4, nz=2, nzh=3, renumber="hierarchical")
     case("tank_small", t, t.surface_nodes, meshgen.towing_tank_bc(t))
+    projections("cube3_mixed")
+    projections("tank_small")
