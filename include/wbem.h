@@ -90,6 +90,15 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t n_dofs, uint32_t n_cells,
                       const uint32_t *cell_dofs, const uint8_t *cell_dir_flag,
                       const uint32_t *dn_ptr, const uint32_t *dn_idx);
 
+/* Host-only helper for that flattening: ComputationalDomain<3>::generate_double_nodes_set
+ * (source/computational_domain.cc:258-307, tol = 1e-8 at :271) with a uniform-grid search instead of
+ * the reference's O(N_boundary N) loop.  boundary_dofs[N] (NULL = every dof is tested) is
+ * DoFTools::extract_boundary_dofs; dn_ptr[N+1] is always filled; dn_idx receives the sorted sets when
+ * it holds `capacity` entries.  Returns 0, or 1 when dn_idx is NULL / too small (*needed = entries). */
+int wbem_generate_double_nodes_set(uint32_t n_dofs, const double *support_points,
+                                   const uint8_t *boundary_dofs, double tol, uint32_t *dn_ptr,
+                                   uint32_t *dn_idx, uint64_t capacity, uint64_t *needed);
+
 /* Per assembly: support_points[N][3] = DoFTools::map_dofs_to_support_points
  * (source/bem_problem.cc:168-169).  The Q1 mapping's quadrature points, normals and JxW
  * (the FEValues of :133-137, 192-196, 495-501) are recomputed on the device from them. */

@@ -213,3 +213,35 @@ def test_spai_pattern_gives_a_better_preconditioner_than_the_band(wb, orc):
     con = orc.Constraints(cl.n, cl.lines, cl.ptr, cl.col, cl.val, cl.inhom)
     ref = orc.solve_system(on, od, s, o, bc, con, np.zeros(n), np.zeros(n), tol=1e-10, max_steps=400)
     assert ref["converged"] and it_spai <= 0.6 * ref["iters"], (it_spai, ref["iters"])
+
+
+def test_generate_double_nodes_set_matches_the_reference_loop(wb):
+    """wbem_generate_double_nodes_set (grid search) against a literal numpy restatement of the
+    reference's all-pairs loop (computational_domain.cc:279-303) and against the mesh generator's
+    KD-tree version, including triple nodes, interior coincidences that must NOT be searched from
+    (non-boundary dofs) but are found as doubles of boundary ones, and points within / beyond tol."""
+    from wavebem_b200 import meshgen
+    for m in (meshgen.cube(3, renumber="random", seed=2), meshgen.wigley_tank(nxm=10, nt=5, nxu=4, nxd=5, nz=3, nzh=3)):
+        ptr, idx = wb.generate_double_nodes_set(m.xyz, m.node_on_patch_boundary)
+        assert np.array_equal(ptr, m.dn_ptr) and np.array_equal(idx, m.dn_idx)
+    rng = np.random.default_rng(4)
+    x = rng.uniform(-3, 3, (400, 3))
+    x[50] = x[10] + np.array([3e-9, -4e-9, 0.0])          # 5e-9 apart: inside tol
+    x[51] = x[10] + np.array([0.0, 0.0, 9e-9])             # 9e-9: inside
+    x[52] = x[10] + np.array([8e-9, 8e-9, 0.0])            # 1.13e-8: outside
+    x[60] = x[20]                                          # exact duplicate of a non-boundary dof
+    bnd = np.zeros(400, dtype=bool)
+    bnd[[10, 50, 60]] = True
+    ptr, idx = wb.generate_double_nodes_set(x, bnd, tol=1e-8)
+    for i in range(400):
+        got = idx[ptr[i]:ptr[i + 1]].tolist()
+        if bnd[i]:
+            want = sorted(set([i]) | set(np.nonzero(np.linalg.norm(x - x[i], axis=1) < 1e-8)[0].tolist()))
+        else:
+            want = [i]
+        assert got == want, (i, got, want)
+    assert idx[ptr[10]:ptr[11]].tolist() == [10, 50, 51] and idx[ptr[60]:ptr[61]].tolist() == [20, 60]
+    assert idx[ptr[20]:ptr[21]].tolist() == [20]           # 20 is not a boundary dof: no search from it
+    # boundary_dofs = None: every dof is tested
+    ptr2, idx2 = wb.generate_double_nodes_set(x, None)
+    assert idx2[ptr2[20]:ptr2[21]].tolist() == [20, 60]

@@ -80,7 +80,7 @@ ABI_SYMBOLS = [
     "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
     "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",
     "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations", "wbem_gmres",
-    "wbem_set_fevalues",
+    "wbem_set_fevalues", "wbem_generate_double_nodes_set",
 ]
 
 
@@ -95,6 +95,27 @@ def lib():
         _lib.wbem_last_error.restype = C.c_char_p
         _lib.wbem_last_error.argtypes = [C.c_void_p]
     return _lib
+
+
+def generate_double_nodes_set(xyz, boundary_dofs=None, tol=1e-8):
+    """ComputationalDomain::generate_double_nodes_set (computational_domain.cc:258-307) through the
+    library's host helper: returns the CSR (dn_ptr, dn_idx) that Context.set_topology takes."""
+    xyz = _f64(xyz)
+    n = xyz.shape[0]
+    b = None if boundary_dofs is None else np.ascontiguousarray(boundary_dofs, dtype=np.uint8)
+    ptr = np.zeros(n + 1, dtype=np.uint32)
+    needed = C.c_uint64(0)
+    f = lib().wbem_generate_double_nodes_set
+    f.argtypes = [C.c_uint32, C.c_void_p, C.c_void_p, C.c_double, C.c_void_p, C.c_void_p, C.c_uint64,
+                  C.POINTER(C.c_uint64)]
+    rc = f(n, _dp(xyz), None if b is None else _dp(b), float(tol), _dp(ptr), None, 0, C.byref(needed))
+    if rc < 0:
+        raise WbemError("wbem_generate_double_nodes_set: bad argument")
+    idx = np.zeros(needed.value, dtype=np.uint32)
+    rc = f(n, _dp(xyz), None if b is None else _dp(b), float(tol), _dp(ptr), _dp(idx), idx.size, C.byref(needed))
+    if rc != 0:
+        raise WbemError("wbem_generate_double_nodes_set failed")
+    return ptr, idx
 
 
 def default_params(**kw) -> Params:
