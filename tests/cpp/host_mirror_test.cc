@@ -55,7 +55,7 @@ int main(int argc, char **argv)
   p.gmres_tol = 1e-12;
   p.gmres_max_steps = 400;
   std::vector<double> phi(N, 0.0), dphi(N, 0.0), res, y;
-  double checks[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  double checks[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
   try
     {
       wbem::BEMProblem bem(dom, &p);
@@ -134,11 +134,15 @@ int main(int argc, char **argv)
       checks[6] = std::sqrt(d4 / s4);
       bem4.compute_constraints(bc);
       checks[7] = (double)bem4.constraints.lines.size();
+      // the double-node sets regenerated from the support points equal the ones handed in
+      wbem::FlatDomain dom2 = dom;
+      dom2.generate_double_nodes_set();
+      checks[8] = (dom2.dn_ptr == dom.dn_ptr && dom2.dn_idx == dom.dn_idx) ? 1.0 : 0.0;
       FILE *o = fopen(argv[2], "wb");
       fwrite(phi.data(), sizeof(double), N, o);
       fwrite(dphi.data(), sizeof(double), N, o);
       fwrite(bem.alpha.data(), sizeof(double), N, o);
-      fwrite(checks, sizeof(double), 8, o);
+      fwrite(checks, sizeof(double), 9, o);
       fclose(o);
     }
   catch (const std::exception &e)

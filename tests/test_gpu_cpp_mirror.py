@@ -44,3 +44,4 @@ def test_cpp_bem_problem(wb, orc, tmp_path):
     assert checks[4] < 1e-9 and 0 < checks[5] <= checks[0] / 2
     # auto_constraints = 1: the library's compute_constraints gives the same lines, hence the same solve
     assert checks[6] < 1e-9 and checks[7] == cl.n_lines
+    assert checks[8] == 1.0     # FlatDomain::generate_double_nodes_set reproduces the sets

@@ -39,6 +39,20 @@ struct FlatDomain
   std::vector<double> surface_nodes, other_nodes; // [N]
   unsigned int n_dofs() const { return (unsigned int)(support_points.size() / 3); }
   unsigned int n_cells() const { return (unsigned int)(cell_dofs.size() / 4); }
+  // ComputationalDomain<3>::generate_double_nodes_set (source/computational_domain.cc:258-307) from the
+  // support points; boundary_dofs = DoFTools::extract_boundary_dofs (empty: every dof is tested)
+  void generate_double_nodes_set(const std::vector<uint8_t> &boundary_dofs = std::vector<uint8_t>(), double tol = 1e-8)
+  {
+    const uint32_t n = n_dofs();
+    const uint8_t *b = boundary_dofs.empty() ? nullptr : boundary_dofs.data();
+    dn_ptr.assign(n + 1, 0);
+    uint64_t needed = 0;
+    if (wbem_generate_double_nodes_set(n, support_points.data(), b, tol, dn_ptr.data(), nullptr, 0, &needed) < 0)
+      throw std::runtime_error("wbem_generate_double_nodes_set: bad argument");
+    dn_idx.assign(needed, 0);
+    if (wbem_generate_double_nodes_set(n, support_points.data(), b, tol, dn_ptr.data(), dn_idx.data(), needed, &needed))
+      throw std::runtime_error("wbem_generate_double_nodes_set failed");
+  }
 };
 
 struct ConstraintLines
