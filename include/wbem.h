@@ -12,10 +12,15 @@
  * There is NO CPU fallback: every compute entry point fails (<0) when no sm_100 device is
  * usable.
  *
- * Multi-GPU: one process (context) per GPU.  Context `rank` of `world_size` owns the
- * contiguous block of matrix rows [rank*ceil(N/P), min(N,(rank+1)*ceil(N/P))); vectors,
- * geometry, masks and constraints are replicated.  Matrix-vector products all-gather the
- * row blocks over NCCL (wbem_comm_init).
+ * Multi-GPU, two ways.  Row block r of P owns the contiguous matrix rows
+ * [r*ceil(N/P), min(N,(r+1)*ceil(N/P))); vectors, geometry, masks and constraints are replicated.
+ *  (1) single process (what the single-threaded reference needs, source/main.cc:26):
+ *      wbem_params.n_gpus = P -- ONE context owns all P row blocks, every call below acts on all
+ *      of them, results come back to the caller's host arrays once.  Peer access between the
+ *      devices carries the fused mat-vec + gather; no NCCL, no IPC, no launcher.
+ *  (2) one process per GPU (torchrun / MPI): wbem_params.rank / world_size; the mat-vecs
+ *      all-gather over NCCL (wbem_comm_init) or, after the CUDA-IPC exchange, through the same
+ *      fused peer stores.
  */
 #ifndef WBEM_H
 #define WBEM_H
@@ -51,7 +56,17 @@ typedef struct wbem_params
   int auto_constraints;    /* 1 = solve_system / solve / residual call compute_constraints(tmp_rhs)
                               themselves, as the reference does (source/bem_problem.cc:845); 0 (default)
                               = the caller installs the lines with wbem_set_constraints */
-  int reserved[3];
+  int n_gpus;              /* 0 / 1: this context is ONE row block (rank of world_size, one process per
+                              GPU).  > 1: this ONE context owns n_gpus row blocks, block r on CUDA device
+                              devices[r]; the caller stays single-threaded (source/main.cc:26) and the
+                              library drives the devices with one internal worker thread + stream each.
+                              rank / world_size / device are ignored then. */
+  int fused_gather_on_shared_device; /* test switch: row blocks that share a device normally gather through
+                              stream-ordered copies; 1 = use the fused peer-store mat-vec there as well */
+  int reserved;
+  int devices[16];         /* n_gpus > 1: device ordinal of every row block; -1 = block r on device r.  A
+                              device may be listed more than once (several row blocks on one GPU: how the
+                              single-GPU tests exercise the sharded code) */
 } wbem_params;
 
 typedef struct wbem_timings

@@ -24,7 +24,7 @@ int main(int argc, char **argv)
 {
   if (argc < 3)
     {
-      fprintf(stderr, "usage: %s in.bin out.bin\n", argv[0]);
+      fprintf(stderr, "usage: %s in.bin out.bin [n_gpus]\n", argv[0]);
       return 2;
     }
   FILE *f = fopen(argv[1], "rb");
@@ -55,7 +55,7 @@ int main(int argc, char **argv)
   p.gmres_tol = 1e-12;
   p.gmres_max_steps = 400;
   std::vector<double> phi(N, 0.0), dphi(N, 0.0), res, y;
-  double checks[9] = {0, 0, 0, 0, 0, 0, 0, 0, 0};
+  double checks[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
   try
     {
       wbem::BEMProblem bem(dom, &p);
@@ -138,11 +138,34 @@ int main(int argc, char **argv)
       wbem::FlatDomain dom2 = dom;
       dom2.generate_double_nodes_set();
       checks[8] = (dom2.dn_ptr == dom.dn_ptr && dom2.dn_idx == dom.dn_idx) ? 1.0 : 0.0;
+      // ONE BEMProblem driving several row blocks from this single-threaded program (n_gpus > 1):
+      // across the box's GPUs when it has several, else 3 row blocks on device 0.  Same kernels,
+      // same rows, replicated Krylov vectors: bitwise the one-GPU result.
+      {
+        const int want = argc > 3 ? atoi(argv[3]) : 0; // visible GPUs to spread over (0 / 1: share device 0)
+        wbem_params gp = p;
+        gp.n_gpus = want >= 2 ? want : 3;
+        for (int r = 0; r < gp.n_gpus; ++r) gp.devices[r] = want >= 2 ? r : 0;
+        wbem::BEMProblem bemg(dom, &gp);
+        bemg.reinit();
+        bemg.set_constraints(con);
+        std::vector<double> phig(N, 0.0), dphig(N, 0.0), rows1, rowsg;
+        bemg.solve(phig, dphig, bc);
+        bool same = bemg.last_step == (unsigned int)checks[0] && !memcmp(phig.data(), phi.data(), sizeof(double) * N) &&
+                    !memcmp(dphig.data(), dphi.data(), sizeof(double) * N) &&
+                    !memcmp(bemg.alpha.data(), bem.alpha.data(), sizeof(double) * N);
+        bem.matrix_rows(0, 0, N, rows1);
+        bemg.matrix_rows(0, 0, N, rowsg);
+        same = same && !memcmp(rows1.data(), rowsg.data(), sizeof(double) * rows1.size());
+        checks[9] = same ? 1.0 : 0.0;
+        checks[10] = gp.n_gpus;
+        checks[11] = want >= 2 ? 1.0 : 0.0;
+      }
       FILE *o = fopen(argv[2], "wb");
       fwrite(phi.data(), sizeof(double), N, o);
       fwrite(dphi.data(), sizeof(double), N, o);
       fwrite(bem.alpha.data(), sizeof(double), N, o);
-      fwrite(checks, sizeof(double), 9, o);
+      fwrite(checks, sizeof(double), 12, o);
       fclose(o);
     }
   catch (const std::exception &e)

@@ -27,7 +27,9 @@ def test_cpp_bem_problem(wb, orc, tmp_path):
                       (bc, np.float64), (cl.lines, np.uint32), (cl.ptr, np.uint32), (cl.col, np.uint32),
                       (cl.val, np.float64), (cl.inhom, np.float64)):
             np.ascontiguousarray(a, dtype=dt).tofile(f)
-    out = subprocess.run([exe, str(fin), str(fout)], capture_output=True, text=True, timeout=600)
+    import torch
+    ndev = torch.cuda.device_count()
+    out = subprocess.run([exe, str(fin), str(fout), str(ndev)], capture_output=True, text=True, timeout=600)
     assert out.returncode == 0, out.stderr + out.stdout
     r = np.fromfile(fout, dtype=np.float64)
     phi, dphi, alpha, checks = r[:n], r[n:2 * n], r[2 * n:3 * n], r[3 * n:]
@@ -45,3 +47,5 @@ def test_cpp_bem_problem(wb, orc, tmp_path):
     # auto_constraints = 1: the library's compute_constraints gives the same lines, hence the same solve
     assert checks[6] < 1e-9 and checks[7] == cl.n_lines
     assert checks[8] == 1.0     # FlatDomain::generate_double_nodes_set reproduces the sets
+    # one single-threaded BEMProblem driving several row blocks (n_gpus > 1): bitwise the 1-GPU result
+    assert checks[9] == 1.0 and checks[10] == (ndev if ndev >= 2 else 3) and checks[11] == (1.0 if ndev >= 2 else 0.0)

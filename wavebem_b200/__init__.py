@@ -47,7 +47,8 @@ class Params(C.Structure):
                 ("gmres_max_steps", C.c_int), ("gmres_n_tmp_vectors", C.c_int),
                 ("preconditioner_band", C.c_int), ("device", C.c_int), ("rank", C.c_int),
                 ("world_size", C.c_int), ("assemble_variant", C.c_int), ("precond_on_host", C.c_int),
-                ("precond_kind", C.c_int), ("auto_constraints", C.c_int), ("reserved", C.c_int * 3)]
+                ("precond_kind", C.c_int), ("auto_constraints", C.c_int), ("n_gpus", C.c_int),
+                ("fused_gather_on_shared_device", C.c_int), ("reserved", C.c_int), ("devices", C.c_int * 16)]
 
 
 class Timings(C.Structure):
@@ -124,6 +125,9 @@ def default_params(**kw) -> Params:
     for k, v in kw.items():
         if not hasattr(p, k):
             raise TypeError(f"unknown wbem_params field {k}")
+        if k == "devices":   # device ordinal of every row block of a single-process context (n_gpus > 1)
+            v = list(v)
+            v = (C.c_int * 16)(*(v + [-1] * (16 - len(v))))
         setattr(p, k, v)
     return p
 
@@ -137,7 +141,8 @@ def _f64(a):
 
 
 class Context:
-    """Owns one wbem_ctx (one GPU, one block of matrix rows)."""
+    """Owns one wbem_ctx: one GPU and one block of matrix rows -- or, with n_gpus=P (and optionally
+    devices=[...]), ALL P row blocks of a single-process multi-GPU context."""
 
     def __init__(self, params: Params | None = None, **kw):
         self._h = C.c_void_p()

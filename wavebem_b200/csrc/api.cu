@@ -149,6 +149,9 @@ void wbem_default_params(wbem_params *p)
   p->precond_on_host = 0;
   p->precond_kind = 0;
   p->auto_constraints = 0;
+  p->n_gpus = 0;
+  p->fused_gather_on_shared_device = 0;
+  for (int &d : p->devices) d = -1;
 }
 
 const char *wbem_last_error(const wbem_ctx *ctx) { return ctx ? ctx->err.c_str() : g_create_error.c_str(); }
@@ -160,6 +163,17 @@ int wbem_create(const wbem_params *p, wbem_ctx **out)
       g_create_error = "null argument";
       return -1;
     }
+  *out = nullptr;
+  // n_gpus > 1: one handle, n_gpus row blocks driven from this process (group.cpp)
+  if (p->n_gpus > 1) return wbem_group_create(p, out, &g_create_error);
+  return wbem_create_single(p, out, &g_create_error);
+}
+
+} // extern "C"
+
+int wbem_create_single(const wbem_params *p, wbem_ctx **out, std::string *errp)
+{
+  std::string &g_create_error = *errp;
   *out = nullptr;
   int ndev = 0;
   cudaError_t e = cudaGetDeviceCount(&ndev);
@@ -219,7 +233,6 @@ int wbem_create(const wbem_params *p, wbem_ctx **out)
   return 0;
 }
 
-} // extern "C"
 void wbem_p2p_close(wbem_ctx *ctx)
 {
   for (int q = 0; q < WBEM_MAX_PEERS; ++q)
@@ -237,6 +250,7 @@ static void free_topology(wbem_ctx *ctx)
   wbem_p2p_close(ctx);
   FREE_DEV(ctx->d_p2p);
   FREE_DEV(ctx->d_done_counter);
+  FREE_DEV(ctx->d_gather_timeout);
   FREE_DEV(ctx->d_cell_dofs);
   FREE_DEV(ctx->d_dir);
   FREE_DEV(ctx->d_cell_order);
@@ -295,9 +309,19 @@ static void free_topology(wbem_ctx *ctx)
 int wbem_destroy(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
+  if (ctx->group) return wbem_group_destroy(ctx);
+  return wbem_destroy_single(ctx);
+}
+
+} // extern "C"
+
+int wbem_destroy_single(wbem_ctx *ctx)
+{
   cudaSetDevice(ctx->dev);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   free_topology(ctx);
+  if (ctx->d_tables) cudaFree(ctx->d_tables);
+  if (ctx->d_gauss) cudaFree(ctx->d_gauss);
   wbem_nccl_destroy(ctx);
   for (auto &ev : ctx->ev)
     if (ev) cudaEventDestroy(ev);
@@ -307,11 +331,14 @@ int wbem_destroy(wbem_ctx *ctx)
   return 0;
 }
 
+extern "C" {
+
 int wbem_row_block(const wbem_ctx *ctx, uint32_t *row0, uint32_t *row1)
 {
   CHECK_CTX(ctx);
-  if (row0) *row0 = ctx->row0;
-  if (row1) *row1 = ctx->row1;
+  const bool all = wbem_group_forward(ctx); // the handle of a single-process group owns every row
+  if (row0) *row0 = all ? 0 : ctx->row0;
+  if (row1) *row1 = all ? ctx->N : ctx->row1;
   return 0;
 }
 
@@ -322,8 +349,14 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if (!cell_dofs || !cell_dir_flag || !dn_ptr || !dn_idx || N == 0)
     WBEM_FAIL(ctx, -1, "wbem_set_topology: null argument or N == 0");
   if ((uint64_t)N >= (1ull << 31)) WBEM_FAIL(ctx, -1, "N too large");
+  GROUP_FORWARD(ctx, wbem_set_topology(s, N, C, cell_dofs, cell_dir_flag, dn_ptr, dn_idx));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (ctx->group)
+    { // no peer may still be storing into this block's gather buffer when it is freed
+      const int brc = wbem_group_barrier(ctx);
+      if (brc) return brc;
+    }
   free_topology(ctx);
   ctx->N = N;
   ctx->C = C;
@@ -446,6 +479,8 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
       const size_t nd = 2 * (size_t)ctx->chunk * P + WBEM_MAX_PEERS;
       if ((rc = dev_alloc(ctx, &ctx->d_p2p, nd))) return rc;
       if ((rc = dev_alloc(ctx, &ctx->d_done_counter, 1))) return rc;
+      if ((rc = dev_alloc(ctx, &ctx->d_gather_timeout, 1))) return rc;
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_gather_timeout, 0, sizeof(unsigned int), ctx->stream));
       CUDA_OK(ctx, cudaMemsetAsync(ctx->d_p2p, 0, sizeof(double) * nd, ctx->stream));
       CUDA_OK(ctx, cudaMemsetAsync(ctx->d_done_counter, 0, sizeof(unsigned long long), ctx->stream));
       ctx->p2p_epoch = 0;
@@ -472,6 +507,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   CUDA_OK(ctx, cudaMallocHost((void **)&ctx->h_pinned, ctx->pinned_doubles * sizeof(double)));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->op_version++;
+  if (ctx->group && (rc = wbem_group_p2p_setup(ctx))) return rc;
   return 0;
 }
 
@@ -479,6 +515,7 @@ int wbem_set_geometry_dev(wbem_ctx *ctx, const double *d_support_points)
 {
   CHECK_CTX(ctx);
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_set_geometry before wbem_set_topology");
+  GROUP_FORWARD(ctx, wbem_set_geometry_dev(s, d_support_points));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_xyz, d_support_points, sizeof(double) * 3 * (size_t)ctx->N,
                                cudaMemcpyDeviceToDevice, ctx->stream));
@@ -495,6 +532,7 @@ int wbem_set_geometry(wbem_ctx *ctx, const double *support_points)
   CHECK_CTX(ctx);
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_set_geometry before wbem_set_topology");
   if (!support_points) WBEM_FAIL(ctx, -1, "null support_points");
+  GROUP_FORWARD(ctx, wbem_set_geometry(s, support_points));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_xyz, support_points, sizeof(double) * 3 * (size_t)ctx->N,
                                cudaMemcpyHostToDevice, ctx->stream));
@@ -550,6 +588,7 @@ static int assemble_timings(wbem_ctx *ctx)
 int wbem_assemble(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_assemble(s));
   int rc = assemble_async(ctx);
   if (rc) return rc;
   return assemble_timings(ctx);
@@ -559,6 +598,7 @@ int wbem_compute_alpha(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
   if (!ctx->assembled) WBEM_FAIL(ctx, -3, "wbem_compute_alpha before wbem_assemble");
+  GROUP_FORWARD(ctx, wbem_compute_alpha(s));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   int rc = wbem_launch_alpha(ctx, true); // the literal N * (-1) of the reference
   if (rc) return rc;
@@ -589,6 +629,14 @@ int wbem_get_rows(wbem_ctx *ctx, int which, uint32_t r0, uint32_t r1, double *ou
 {
   CHECK_CTX(ctx);
   if (!ctx->assembled) WBEM_FAIL(ctx, -3, "wbem_get_rows before wbem_assemble");
+  if (wbem_group_forward(ctx))
+    { // every row block hands over its part of [r0, r1)
+      if (r0 > r1 || r1 > ctx->N) WBEM_FAIL(ctx, -1, "rows [%u,%u) out of range", r0, r1);
+      return wbem_group_run(ctx, [&](wbem_ctx *s) -> int {
+        const uint32_t a = std::max(r0, s->row0), b = std::min(r1, s->row1);
+        return a < b ? wbem_get_rows(s, which, a, b, out + (size_t)(a - r0) * s->N) : 0;
+      });
+    }
   if (r0 < ctx->row0 || r1 > ctx->row1 || r0 > r1)
     WBEM_FAIL(ctx, -1, "rows [%u,%u) outside this context's block [%u,%u)", r0, r1, ctx->row0, ctx->row1);
   if (r0 == r1) return 0;
@@ -622,6 +670,7 @@ int wbem_set_masks(wbem_ctx *ctx, const double *surface_nodes, const double *oth
 {
   CHECK_CTX(ctx);
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_set_masks before wbem_set_topology");
+  GROUP_FORWARD(ctx, wbem_set_masks(s, surface_nodes, other_nodes));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   const uint32_t N = ctx->N;
   const bool same = ctx->have_masks && !memcmp(ctx->h_surf.data(), surface_nodes, sizeof(double) * N) &&
@@ -668,6 +717,7 @@ int wbem_set_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t *lines,
 {
   CHECK_CTX(ctx);
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_set_constraints before wbem_set_topology");
+  GROUP_FORWARD(ctx, wbem_set_constraints(s, n_lines, lines, ptr, col, val, inhom));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   const uint32_t N = ctx->N;
   std::vector<int32_t> line_of(N, -1);
@@ -735,24 +785,28 @@ static int host_apply(wbem_ctx *ctx, int mode, bool constrained, double *dst, co
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[1], src, sizeof(double) * ctx->N, cudaMemcpyHostToDevice, st));
   rc = wbem_apply_operator(ctx, mode, ctx->d_tmp[1], ctx->d_tmp[2], constrained);
   if (rc) return rc;
-  CUDA_OK(ctx, cudaMemcpyAsync(dst, ctx->d_tmp[2], sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, st));
+  if (wbem_is_root(ctx)) // every row block holds the gathered result; one of them hands it over
+    CUDA_OK(ctx, cudaMemcpyAsync(dst, ctx->d_tmp[2], sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
-  return 0;
+  return wbem_check_gather_timeout(ctx);
 }
 
 int wbem_vmult(wbem_ctx *ctx, double *dst, const double *src)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_vmult(s, dst, src));
   return host_apply(ctx, 0, false, dst, src);
 }
 int wbem_constrained_vmult(wbem_ctx *ctx, double *dst, const double *src)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_constrained_vmult(s, dst, src));
   return host_apply(ctx, 0, true, dst, src);
 }
 int wbem_compute_rhs(wbem_ctx *ctx, double *dst, const double *src)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_compute_rhs(s, dst, src));
   return host_apply(ctx, 1, false, dst, src);
 }
 int wbem_distribute_rhs(wbem_ctx *ctx, double *rhs)
@@ -771,6 +825,7 @@ int wbem_distribute_rhs(wbem_ctx *ctx, double *rhs)
 int wbem_assemble_preconditioner(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_assemble_preconditioner(s));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "assemble_preconditioner before wbem_set_masks");
   int rc = ensure_alpha(ctx);
@@ -785,6 +840,7 @@ int wbem_set_precond_kind(wbem_ctx *ctx, int kind)
 {
   CHECK_CTX(ctx);
   if (kind < 0 || kind > 1) WBEM_FAIL(ctx, -1, "precond_kind must be 0 (band) or 1 (sparse approximate inverse)");
+  GROUP_FORWARD(ctx, wbem_set_precond_kind(s, kind));
   if (kind != ctx->p.precond_kind)
     {
       ctx->p.precond_kind = kind;
@@ -796,12 +852,14 @@ int wbem_set_precond_kind(wbem_ctx *ctx, int kind)
 int wbem_precond_vmult(wbem_ctx *ctx, double *dst, const double *src)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_precond_vmult(s, dst, src));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   cudaStream_t st = ctx->stream;
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[1], src, sizeof(double) * ctx->N, cudaMemcpyHostToDevice, st));
   int rc = wbem_apply_preconditioner(ctx, ctx->d_tmp[1], ctx->d_tmp[2]);
   if (rc) return rc;
-  CUDA_OK(ctx, cudaMemcpyAsync(dst, ctx->d_tmp[2], sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, st));
+  if (wbem_is_root(ctx))
+    CUDA_OK(ctx, cudaMemcpyAsync(dst, ctx->d_tmp[2], sizeof(double) * ctx->N, cudaMemcpyDeviceToHost, st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   return 0;
 }
@@ -812,6 +870,11 @@ int wbem_get_band(wbem_ctx *ctx, double *out)
   const int band = ctx->p.preconditioner_band;
   if (band <= 0 || !ctx->precond_ready) WBEM_FAIL(ctx, -3, "no band preconditioner assembled");
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  if (wbem_group_forward(ctx))
+    { // the gathered band rows of all row blocks sit on every device: all N rows from this one
+      CUDA_OK(ctx, cudaMemcpy(out, ctx->d_band, sizeof(double) * (size_t)ctx->N * band, cudaMemcpyDeviceToHost));
+      return 0;
+    }
   CUDA_OK(ctx, cudaMemcpy(out, ctx->d_band + (size_t)ctx->p.rank * ctx->chunk * band,
                           sizeof(double) * (size_t)ctx->nloc * band, cudaMemcpyDeviceToHost));
   return 0;
@@ -821,7 +884,19 @@ int wbem_solve_system_dev(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, const
                           int *iters, double *last_res)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_solve_system_dev(s, d_phi, d_dphi_dn, d_tmp_rhs, wbem_is_root(s) ? iters : nullptr,
+                                           wbem_is_root(s) ? last_res : nullptr));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  if (!wbem_is_root(ctx))
+    { // the caller's arrays live on the first row block's device: the others solve on private
+      // copies (peer reads) and leave the in-out arrays to that block
+      cudaStream_t st = ctx->stream;
+      const size_t nb = sizeof(double) * ctx->N;
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[3], d_phi, nb, cudaMemcpyDefault, st));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[4], d_dphi_dn, nb, cudaMemcpyDefault, st));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[5], d_tmp_rhs, nb, cudaMemcpyDefault, st));
+      return wbem_solve_system_device(ctx, ctx->d_tmp[3], ctx->d_tmp[4], ctx->d_tmp[5], iters, last_res);
+    }
   return wbem_solve_system_device(ctx, d_phi, d_dphi_dn, d_tmp_rhs, iters, last_res);
 }
 
@@ -830,6 +905,8 @@ int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double 
 {
   CHECK_CTX(ctx);
   if (!ctx->N) WBEM_FAIL(ctx, -3, "solve_system before wbem_set_topology");
+  GROUP_FORWARD(ctx, wbem_solve_system(s, phi, dphi_dn, tmp_rhs, wbem_is_root(s) ? iters : nullptr,
+                                       wbem_is_root(s) ? last_res : nullptr));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   cudaStream_t st = ctx->stream;
   const size_t nb = sizeof(double) * ctx->N;
@@ -839,8 +916,11 @@ int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double 
   CUDA_OK(ctx, cudaMemcpyAsync(d_bc, tmp_rhs, nb, cudaMemcpyHostToDevice, st));
   const int rc = wbem_solve_system_device(ctx, d_phi, d_dphi, d_bc, iters, last_res);
   if (rc < 0) return rc;
-  CUDA_OK(ctx, cudaMemcpyAsync(phi, d_phi, nb, cudaMemcpyDeviceToHost, st));
-  CUDA_OK(ctx, cudaMemcpyAsync(dphi_dn, d_dphi, nb, cudaMemcpyDeviceToHost, st));
+  if (wbem_is_root(ctx))
+    {
+      CUDA_OK(ctx, cudaMemcpyAsync(phi, d_phi, nb, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaMemcpyAsync(dphi_dn, d_dphi, nb, cudaMemcpyDeviceToHost, st));
+    }
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   return rc;
 }
@@ -850,13 +930,14 @@ int wbem_gmres(wbem_ctx *ctx, const double *rhs, double *sol, int *iters, double
   CHECK_CTX(ctx);
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_gmres before wbem_set_topology");
   if (!rhs || !sol) WBEM_FAIL(ctx, -1, "null argument");
+  GROUP_FORWARD(ctx, wbem_gmres(s, rhs, sol, wbem_is_root(s) ? iters : nullptr, wbem_is_root(s) ? last_res : nullptr));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   cudaStream_t st = ctx->stream;
   const size_t nb = sizeof(double) * ctx->N;
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[5], rhs, nb, cudaMemcpyHostToDevice, st));
   const int rc = wbem_solve_system_device(ctx, nullptr, nullptr, ctx->d_tmp[5], iters, last_res);
   if (rc < 0) return rc;
-  CUDA_OK(ctx, cudaMemcpyAsync(sol, ctx->d_sol, nb, cudaMemcpyDeviceToHost, st));
+  if (wbem_is_root(ctx)) CUDA_OK(ctx, cudaMemcpyAsync(sol, ctx->d_sol, nb, cudaMemcpyDeviceToHost, st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   return rc;
 }
@@ -866,6 +947,7 @@ int wbem_set_fevalues(wbem_ctx *ctx, const double *q_points, const double *norma
   CHECK_CTX(ctx);
   if (!ctx->have_geometry) WBEM_FAIL(ctx, -3, "wbem_set_fevalues needs the support points first (wbem_set_geometry)");
   if (!q_points || !normals || !JxW) WBEM_FAIL(ctx, -1, "null argument");
+  GROUP_FORWARD(ctx, wbem_set_fevalues(s, q_points, normals, JxW));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   const int rc = wbem_upload_fevalues(ctx, q_points, normals, JxW);
   if (rc) return rc;
@@ -879,6 +961,8 @@ int wbem_solve(wbem_ctx *ctx, const double *support_points, double *phi, double 
                const double *tmp_rhs, int *iters, double *last_res)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_solve(s, support_points, phi, dphi_dn, tmp_rhs, wbem_is_root(s) ? iters : nullptr,
+                                wbem_is_root(s) ? last_res : nullptr));
   int rc = wbem_set_geometry(ctx, support_points);
   if (rc) return rc;
   rc = assemble_async(ctx);
@@ -893,11 +977,13 @@ int wbem_solve_dev(wbem_ctx *ctx, const double *d_support_points, double *d_phi,
                    const double *d_tmp_rhs, int *iters, double *last_res)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_solve_dev(s, d_support_points, d_phi, d_dphi_dn, d_tmp_rhs, wbem_is_root(s) ? iters : nullptr,
+                                    wbem_is_root(s) ? last_res : nullptr));
   int rc = wbem_set_geometry_dev(ctx, d_support_points);
   if (rc) return rc;
   rc = assemble_async(ctx);
   if (rc) return rc;
-  rc = wbem_solve_system_device(ctx, d_phi, d_dphi_dn, d_tmp_rhs, iters, last_res);
+  rc = wbem_solve_system_dev(ctx, d_phi, d_dphi_dn, d_tmp_rhs, iters, last_res);
   if (rc < 0) return rc;
   const int rc2 = assemble_timings(ctx);
   return rc2 ? rc2 : rc;
@@ -929,6 +1015,7 @@ __global__ void k_residual_combine(uint32_t N, const double *__restrict__ av, co
 int wbem_residual(wbem_ctx *ctx, double *res, const double *phi, const double *dphi_dn)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_residual(s, res, phi, dphi_dn));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "residual before wbem_set_masks");
   int rc = ensure_alpha(ctx);
@@ -949,7 +1036,7 @@ int wbem_residual(wbem_ctx *ctx, double *res, const double *phi, const double *d
                                                      ctx->n_lines ? ctx->d_con_line_of : nullptr,
                                                      ctx->d_con_inhom, ctx->d_tmp[1]);
   ctx->launches++;
-  CUDA_OK(ctx, cudaMemcpyAsync(res, ctx->d_tmp[1], nb, cudaMemcpyDeviceToHost, st));
+  if (wbem_is_root(ctx)) CUDA_OK(ctx, cudaMemcpyAsync(res, ctx->d_tmp[1], nb, cudaMemcpyDeviceToHost, st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   return 0;
 }
@@ -972,15 +1059,22 @@ int wbem_get_sol(wbem_ctx *ctx, double *out)
 int wbem_get_timings(wbem_ctx *ctx, wbem_timings *out)
 {
   CHECK_CTX(ctx);
-  ctx->tm.kernel_launches = ctx->launches;
+  ctx->tm.kernel_launches = 0;
+  const bool all = wbem_group_forward(ctx); // timings of the first row block, launches of all of them
+  for (int r = 0; r < (all ? wbem_group_size(ctx) : 1); ++r) ctx->tm.kernel_launches += wbem_group_shard(ctx, r)->launches;
   *out = ctx->tm;
   return 0;
 }
 int wbem_reset_counters(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
-  ctx->launches = 0;
-  memset(&ctx->tm, 0, sizeof(ctx->tm));
+  const bool all = wbem_group_forward(ctx);
+  for (int r = 0; r < (all ? wbem_group_size(ctx) : 1); ++r)
+    {
+      wbem_ctx *s = wbem_group_shard(ctx, r);
+      s->launches = 0;
+      memset(&s->tm, 0, sizeof(s->tm));
+    }
   return 0;
 }
 
@@ -988,6 +1082,7 @@ int wbem_reset_counters(wbem_ctx *ctx)
 int wbem_timer_start(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_timer_start(s));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[10], ctx->stream));
@@ -996,6 +1091,13 @@ int wbem_timer_start(wbem_ctx *ctx)
 int wbem_timer_stop(wbem_ctx *ctx, double *ms)
 {
   CHECK_CTX(ctx);
+  if (wbem_group_forward(ctx))
+    { // device time of the slowest row block
+      std::vector<double> v(wbem_group_size(ctx), 0.0);
+      const int rc = wbem_group_run(ctx, [&](wbem_ctx *s) -> int { return wbem_timer_stop(s, &v[s->p.rank]); });
+      *ms = *std::max_element(v.begin(), v.end());
+      return rc;
+    }
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[11], ctx->stream));
   CUDA_OK(ctx, cudaEventSynchronize(ctx->ev[11]));
@@ -1018,6 +1120,7 @@ int wbem_comm_unique_id(void *id128)
 int wbem_comm_ipc_export(wbem_ctx *ctx, void *handle64)
 {
   CHECK_CTX(ctx);
+  if (ctx->group) WBEM_FAIL(ctx, -3, "a single-process context (n_gpus > 1) needs no IPC exchange");
   if (ctx->p.world_size <= 1 || !ctx->d_p2p) WBEM_FAIL(ctx, -3, "ipc_export needs world_size > 1 and wbem_set_topology");
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
@@ -1030,6 +1133,7 @@ int wbem_comm_ipc_export(wbem_ctx *ctx, void *handle64)
 int wbem_comm_ipc_import(wbem_ctx *ctx, const void *handles)
 {
   CHECK_CTX(ctx);
+  if (ctx->group) WBEM_FAIL(ctx, -3, "a single-process context (n_gpus > 1) needs no IPC exchange");
   const int P = ctx->p.world_size;
   if (P <= 1 || !ctx->d_p2p) WBEM_FAIL(ctx, -3, "ipc_import needs world_size > 1 and wbem_set_topology");
   if (P > WBEM_MAX_PEERS) WBEM_FAIL(ctx, -1, "at most %d ranks for the peer-to-peer gather", WBEM_MAX_PEERS);
@@ -1062,6 +1166,7 @@ int wbem_comm_ipc_import(wbem_ctx *ctx, const void *handles)
 int wbem_comm_ipc_close(wbem_ctx *ctx)
 {
   CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_comm_ipc_close(s)); // a group falls back to the stream-ordered peer copies
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   wbem_p2p_close(ctx);
@@ -1071,6 +1176,7 @@ int wbem_comm_ipc_close(wbem_ctx *ctx)
 int wbem_comm_init(wbem_ctx *ctx, const void *id128)
 {
   CHECK_CTX(ctx);
+  if (ctx->group) WBEM_FAIL(ctx, -3, "a single-process context (n_gpus > 1) has no NCCL communicator");
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   return wbem_nccl_init(ctx, id128);
 }
@@ -1204,6 +1310,15 @@ int wbem_measure_copy_bw(wbem_ctx *ctx, double *gbs)
 int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, double *bytes)
 {
   CHECK_CTX(ctx);
+  if (wbem_group_forward(ctx))
+    {
+      std::vector<double> v(wbem_group_size(ctx), 0.0), b(wbem_group_size(ctx), 0.0);
+      const int rc = wbem_group_run(
+        ctx, [&](wbem_ctx *s) -> int { return wbem_time_operator(s, reps, flush_l2, &v[s->p.rank], &b[s->p.rank]); });
+      *ms_avg = *std::max_element(v.begin(), v.end());
+      if (bytes) *bytes = b[0];
+      return rc;
+    }
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   int rc = ensure_alpha(ctx);
   if (rc) return rc;
@@ -1234,6 +1349,13 @@ int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, do
 int wbem_time_assemble(wbem_ctx *ctx, int reps, double *ms_avg)
 {
   CHECK_CTX(ctx);
+  if (wbem_group_forward(ctx))
+    {
+      std::vector<double> v(wbem_group_size(ctx), 0.0);
+      const int rc = wbem_group_run(ctx, [&](wbem_ctx *s) -> int { return wbem_time_assemble(s, reps, &v[s->p.rank]); });
+      *ms_avg = *std::max_element(v.begin(), v.end());
+      return rc;
+    }
   double total = 0;
   for (int r = 0; r < reps + 1; ++r)
     {

@@ -13,6 +13,8 @@
 //                        261-525): QGaussOneOverR rule, one warp per row, shuffle reduction
 //   k_alpha_rowsum       alpha = -row sums of the Neumann matrix (:594-618)
 #include <cstdio>
+#include <cstring>
+#include <vector>
 
 #include "internal.h"
 #include "q1map.cuh"
@@ -27,11 +29,13 @@ struct DevTables
   double g1_x[8];
   double s_u[4][WBEM_MAX_NS], s_v[4][WBEM_MAX_NS], s_w[4][WBEM_MAX_NS];
 };
-__constant__ DevTables c_qt;
+// The tables live in global memory, one copy per context (two contexts with different
+// quadrature orders may share a device); kernels get the pointer as an argument.
 
 int wbem_upload_tables(wbem_ctx *ctx)
 {
-  static DevTables t; // large: keep off the stack
+  std::vector<DevTables> tv(1); // large: keep off the stack
+  DevTables &t = tv[0];
   const QuadTables &q = ctx->qt;
   t.nq = q.nq;
   t.ns = q.ns;
@@ -45,14 +49,15 @@ int wbem_upload_tables(wbem_ctx *ctx)
   memcpy(t.s_u, q.s_u, sizeof(t.s_u));
   memcpy(t.s_v, q.s_v, sizeof(t.s_v));
   memcpy(t.s_w, q.s_w, sizeof(t.s_w));
-  CUDA_OK(ctx, cudaMemcpyToSymbol(c_qt, &t, sizeof(t)));
+  if (!ctx->d_tables) CUDA_OK(ctx, cudaMalloc(&ctx->d_tables, sizeof(DevTables)));
+  CUDA_OK(ctx, cudaMemcpy(ctx->d_tables, &t, sizeof(t), cudaMemcpyHostToDevice));
   return 0;
 }
 
 // One thread per (cell position, q).  Output layout per cell: [7][nq] =
 // y_x, y_y, y_z, nJ_x, nJ_y, nJ_z, wJ   with  nJ = n JxW / (-4 pi),  wJ = JxW / (4 pi).
 // n JxW = +-(d_u x d_v) w_q exactly (no normalisation needed).
-__global__ void k_cell_geometry(uint32_t C, int nq, const double *__restrict__ xyz,
+__global__ void k_cell_geometry(const DevTables *__restrict__ qt, uint32_t C, int nq, const double *__restrict__ xyz,
                                 const uint32_t *__restrict__ cell_dofs,
                                 const uint8_t *__restrict__ dir, double *__restrict__ geo)
 {
@@ -63,8 +68,8 @@ __global__ void k_cell_geometry(uint32_t C, int nq, const double *__restrict__ x
   QuadVerts X;
   load_verts(xyz, cell_dofs + 4 * (size_t)c, X);
   double y[3], cr[3], phi[4];
-  map_q1(X, c_qt.g_u[q], c_qt.g_v[q], y, cr, phi);
-  const double w = c_qt.g_w[q];
+  map_q1(X, qt->g_u[q], qt->g_v[q], y, cr, phi);
+  const double w = qt->g_w[q];
   const double sgn = dir[c] ? 1.0 : -1.0;
   const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
   double *g = geo + (size_t)c * 7 * nq;
@@ -126,7 +131,7 @@ int wbem_launch_geometry(wbem_ctx *ctx)
   const int nq = ctx->qt.nq;
   const uint32_t total = ctx->C * nq;
   if (total == 0) return 0;
-  k_cell_geometry<<<(total + 255) / 256, 256, 0, ctx->stream>>>(ctx->C, nq, ctx->d_xyz,
+  k_cell_geometry<<<(total + 255) / 256, 256, 0, ctx->stream>>>((const DevTables *)ctx->d_tables, ctx->C, nq, ctx->d_xyz,
                                                                ctx->d_cell_dofs, ctx->d_dir,
                                                                ctx->d_cellgeo);
   ctx->launches++;
@@ -267,6 +272,7 @@ struct TiledArgs
   double *Nm, *Dm;
   double *alpha_part; // [n_clusters + 1][nloc]: per-cluster partial of sum_j N_ij (row sum = sum of moments S)
   uint32_t ld, row0, nloc, cluster_base, n_clusters;
+  double g1_x[4]; // nodes of the 1-D Gauss rule (kernel parameters sit in the constant bank)
 };
 
 constexpr size_t tiled_smem_bytes()
@@ -357,7 +363,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
   for (int s = 0; s < nslot; ++s) accM[s * ACC_STRIDE] = 0.0;
   __syncthreads(); // barriers initialised, slot tables visible
 
-  const double vq0 = c_qt.g1_x[2 * h], vq1 = c_qt.g1_x[2 * h + 1];
+  const double vq0 = a.g1_x[2 * h], vq1 = a.g1_x[2 * h + 1];
   double row_sum = 0.0; // sum over this cluster's regular cells of the zeroth moment (h = 0: Neumann)
   for (int c = 0; c < nchunk; ++c)
     {
@@ -393,7 +399,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
                   const double Rn = fma(Rz, g[80 + q], fma(Ry, g[64 + q], Rx * g[48 + q]));
                   const double av = Rn * ri3;       // (D . n) JxW
                   const double bv = g[96 + q] * ri; // d JxW
-                  const double uq = c_qt.g1_x[qx];
+                  const double uq = a.g1_x[qx];
                   if (qx == 0)
                     {
                       t0n = av;
@@ -527,7 +533,7 @@ __global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_til
 #define SIMPLE_TC 4
 
 __global__ void __launch_bounds__(SIMPLE_ROWS)
-  k_assemble_simple(int nq, uint32_t C, uint32_t cells_per_chunk, const double *__restrict__ xyz,
+  k_assemble_simple(const DevTables *__restrict__ qt, int nq, uint32_t C, uint32_t cells_per_chunk, const double *__restrict__ xyz,
                     const double *__restrict__ geo, const uint32_t *__restrict__ cell_dofs,
                     const uint32_t *__restrict__ colpos, const uint32_t *__restrict__ sing_ptr,
                     const uint32_t *__restrict__ sing_cellpos, double *Nm, double *Dm, uint32_t ld,
@@ -577,8 +583,8 @@ __global__ void __launch_bounds__(SIMPLE_ROWS)
 #pragma unroll
               for (int j = 0; j < 4; ++j)
                 {
-                  ln[j] += Dn * c_qt.g_shape[j][q];
-                  ldd[j] += s * c_qt.g_shape[j][q];
+                  ln[j] += Dn * qt->g_shape[j][q];
+                  ldd[j] += s * qt->g_shape[j][q];
                 }
             }
           if (row_ok)
@@ -601,7 +607,7 @@ __global__ void __launch_bounds__(SIMPLE_ROWS)
 // kernels have finished on this stream; no other warp touches row i).
 // ---------------------------------------------------------------------------------------
 __global__ void __launch_bounds__(256)
-  k_assemble_singular(const double *__restrict__ xyz, const uint32_t *__restrict__ cell_dofs,
+  k_assemble_singular(const DevTables *__restrict__ qt, const double *__restrict__ xyz, const uint32_t *__restrict__ cell_dofs,
                       const uint8_t *__restrict__ dir, const uint32_t *__restrict__ colpos,
                       const uint32_t *__restrict__ sing_ptr,
                       const uint32_t *__restrict__ sing_cellpos,
@@ -614,7 +620,7 @@ __global__ void __launch_bounds__(256)
   double row_sum = 0.0;
   const double *px = xyz + 3 * (size_t)(row0 + lrow);
   const double xi[3] = {px[0], px[1], px[2]};
-  const int ns = c_qt.ns;
+  const int ns = qt->ns;
   for (uint32_t k = sing_ptr[lrow]; k < sing_ptr[lrow + 1]; ++k)
     {
       const uint32_t cpos = sing_cellpos[k];
@@ -627,9 +633,9 @@ __global__ void __launch_bounds__(256)
       for (int q = lane; q < ns; q += 32)
         {
           double y[3], cr[3], phi[4];
-          map_q1(X, c_qt.s_u[sj][q], c_qt.s_v[sj][q], y, cr, phi);
+          map_q1(X, qt->s_u[sj][q], qt->s_v[sj][q], y, cr, phi);
           const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
-          const double jxw = cn * c_qt.s_w[sj][q];
+          const double jxw = cn * qt->s_w[sj][q];
           const double nx = sgn * cr[0] / cn, ny = sgn * cr[1] / cn, nz = sgn * cr[2] / cn;
           const double Rx = y[0] - xi[0], Ry = y[1] - xi[1], Rz = y[2] - xi[2];
           const double r = sqrt(Rx * Rx + Ry * Ry + Rz * Rz);
@@ -724,8 +730,6 @@ __global__ void __launch_bounds__(256)
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
-static bool g_tiled_attr_set = false;
-
 int wbem_launch_assemble(wbem_ctx *ctx)
 {
   cudaStream_t st = ctx->stream;
@@ -736,12 +740,12 @@ int wbem_launch_assemble(wbem_ctx *ctx)
   if (tiled)
     {
       const AssemblyPlan &pl = ctx->plan;
-      if (!g_tiled_attr_set)
-        {
+      if (!ctx->tiled_attr_set)
+        { // per device: a second context on another GPU needs its own opt-in
           CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_tiled,
                                             cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)tiled_smem_bytes()));
-          g_tiled_attr_set = true;
+          ctx->tiled_attr_set = true;
         }
       // columns no cell touches (none on deal.II meshes) stay zero
       if (pl.n_cols_written < ctx->ld)
@@ -770,6 +774,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       a.ld = ctx->ld;
       a.row0 = ctx->row0;
       a.nloc = ctx->nloc;
+      for (int i = 0; i < 4; ++i) a.g1_x[i] = ctx->qt.g1_x[i];
       const uint32_t row_tiles = (ctx->nloc + TILE_ROWS - 1) / TILE_ROWS;
       for (uint32_t c = 0; c < pl.n_colors; ++c)
         {
@@ -794,7 +799,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       chunks = (ctx->C + per - 1) / per;
       dim3 grid(row_blocks, chunks);
       const size_t sm = sizeof(double) * SIMPLE_TC * 7 * nq;
-      k_assemble_simple<<<grid, SIMPLE_ROWS, sm, st>>>(nq, ctx->C, per, ctx->d_xyz, ctx->d_cellgeo,
+      k_assemble_simple<<<grid, SIMPLE_ROWS, sm, st>>>((const DevTables *)ctx->d_tables, nq, ctx->C, per, ctx->d_xyz, ctx->d_cellgeo,
                                                        ctx->d_cell_dofs, ctx->d_colpos,
                                                        ctx->d_sing_ptr, ctx->d_sing_cellpos,
                                                        ctx->d_Nm, ctx->d_Dm, ctx->ld, ctx->row0,
@@ -807,7 +812,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
     {
       const uint32_t warps_per_block = 8;
       k_assemble_singular<<<(ctx->nloc + warps_per_block - 1) / warps_per_block, 256, 0, st>>>(
-        ctx->d_xyz, ctx->d_cell_dofs, ctx->d_dir, ctx->d_colpos, ctx->d_sing_ptr,
+        (const DevTables *)ctx->d_tables, ctx->d_xyz, ctx->d_cell_dofs, ctx->d_dir, ctx->d_colpos, ctx->d_sing_ptr,
         ctx->d_sing_cellpos, ctx->d_sing_idx, ctx->d_Nm, ctx->d_Dm, ctx->ld, ctx->row0, ctx->nloc,
         tiled ? ctx->d_alpha_part + (size_t)ctx->plan.n_clusters * ctx->nloc : nullptr);
       ctx->launches++;

@@ -40,7 +40,6 @@ struct GaussTable
   int nq, pad;
   double u[WBEM_MAX_NQ], v[WBEM_MAX_NQ], w[WBEM_MAX_NQ];
 };
-__constant__ GaussTable c_gq;
 
 struct ConState
 {
@@ -99,13 +98,15 @@ void wbem_constraints_free(wbem_ctx *ctx)
 
 int wbem_constraints_upload_tables(wbem_ctx *ctx)
 {
-  static GaussTable t;
+  GaussTable t;
   t.nq = ctx->qt.nq;
   t.pad = 0;
   memcpy(t.u, ctx->qt.g_u, sizeof(t.u));
   memcpy(t.v, ctx->qt.g_v, sizeof(t.v));
   memcpy(t.w, ctx->qt.g_w, sizeof(t.w));
-  CUDA_OK(ctx, cudaMemcpyToSymbol(c_gq, &t, sizeof(t)));
+  // global memory, one copy per context (contexts with different orders may share a device)
+  if (!ctx->d_gauss) CUDA_OK(ctx, cudaMalloc(&ctx->d_gauss, sizeof(GaussTable)));
+  CUDA_OK(ctx, cudaMemcpy(ctx->d_gauss, &t, sizeof(t), cudaMemcpyHostToDevice));
   return 0;
 }
 
@@ -116,7 +117,7 @@ int wbem_constraints_upload_tables(wbem_ctx *ctx)
 // the adjacent cells in ascending cell order (the reference's cell loop, :1566-1600: local
 // matrix summed over q, then added to the global entries).
 __global__ void __launch_bounds__(128)
-  k_mass_rows(uint32_t N, uint32_t MW, const double *__restrict__ xyz, const uint32_t *__restrict__ cells,
+  k_mass_rows(const GaussTable *__restrict__ gq, uint32_t N, uint32_t MW, const double *__restrict__ xyz, const uint32_t *__restrict__ cells,
               const uint8_t *__restrict__ dir, const uint32_t *__restrict__ nc_ptr,
               const uint32_t *__restrict__ nc_cell, const uint8_t *__restrict__ nc_local,
               const uint8_t *__restrict__ nc_pos, double *__restrict__ mval, double *__restrict__ diag,
@@ -127,7 +128,7 @@ __global__ void __launch_bounds__(128)
   double *row = mval + (size_t)i * MW;
   for (uint32_t k = 0; k < MW; ++k) row[k] = 0.0;
   double bn[3] = {0, 0, 0}, dg = 0.0;
-  const int nq = c_gq.nq;
+  const int nq = gq->nq;
   for (uint32_t a = nc_ptr[i]; a < nc_ptr[i + 1]; ++a)
     {
       const uint32_t c = nc_cell[a];
@@ -139,9 +140,9 @@ __global__ void __launch_bounds__(128)
       for (int q = 0; q < nq; ++q)
         {
           double y[3], cr[3], phi[4];
-          map_q1(X, c_gq.u[q], c_gq.v[q], y, cr, phi);
+          map_q1(X, gq->u[q], gq->v[q], y, cr, phi);
           const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
-          const double jxw = cn * c_gq.w[q];
+          const double jxw = cn * gq->w[q];
 #pragma unroll
           for (int j = 0; j < 4; ++j) m[j] += phi[li] * phi[j] * jxw;
           // normal = sgn (d_u x d_v)/|.| (cell->direction_flag()), times JxW
@@ -169,7 +170,7 @@ __global__ void __launch_bounds__(128)
 // grad_s phi = [t_u t_v] G^-1 [d_u phi, d_v phi]^T with G the first fundamental form (the
 // covariant transformation deal.II applies to the reference gradients in codimension one).
 __global__ void __launch_bounds__(128)
-  k_gradient_rhs(uint32_t N, const double *__restrict__ xyz, const uint32_t *__restrict__ cells,
+  k_gradient_rhs(const GaussTable *__restrict__ gq, uint32_t N, const double *__restrict__ xyz, const uint32_t *__restrict__ cells,
                  const uint32_t *__restrict__ nc_ptr, const uint32_t *__restrict__ nc_cell,
                  const uint8_t *__restrict__ nc_local, const double *__restrict__ phi_nodes,
                  double *__restrict__ b /* [3][N] */)
@@ -177,7 +178,7 @@ __global__ void __launch_bounds__(128)
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   double bg[3] = {0, 0, 0};
-  const int nq = c_gq.nq;
+  const int nq = gq->nq;
   for (uint32_t a = nc_ptr[i]; a < nc_ptr[i + 1]; ++a)
     {
       const uint32_t c = nc_cell[a];
@@ -189,7 +190,7 @@ __global__ void __launch_bounds__(128)
       double r[3] = {0, 0, 0};
       for (int q = 0; q < nq; ++q)
         {
-          const double u = c_gq.u[q], v = c_gq.v[q];
+          const double u = gq->u[q], v = gq->v[q];
           double tu[3], tv[3];
           q1_tangents(X, u, v, tu, tv);
           const double E = tu[0] * tu[0] + tu[1] * tu[1] + tu[2] * tu[2];
@@ -199,7 +200,7 @@ __global__ void __launch_bounds__(128)
           const double du = (1 - v) * (f1 - f0) + v * (f3 - f2);
           const double dv = (1 - u) * (f2 - f0) + u * (f3 - f1);
           const double ca = (G * du - F * dv) / det, cb = (E * dv - F * du) / det;
-          const double jxw = sqrt(det) * c_gq.w[q];
+          const double jxw = sqrt(det) * gq->w[q];
           const double ph = li == 0 ? (1 - u) * (1 - v) : li == 1 ? u * (1 - v) : li == 2 ? (1 - u) * v : u * v;
 #pragma unroll
           for (int d = 0; d < 3; ++d) r[d] += ph * (tu[d] * ca + tv[d] * cb) * jxw;
@@ -501,7 +502,7 @@ static int con_mass(wbem_ctx *ctx)
 { // mass matrix + normal rhs for the current geometry (left in d_b)
   ConState *s = con_state(ctx);
   if (!ctx->have_geometry) WBEM_FAIL(ctx, -3, "normals / surface gradients need the geometry (wbem_set_geometry)");
-  k_mass_rows<<<(s->N + 127) / 128, 128, 0, ctx->stream>>>(s->N, s->MW, ctx->d_xyz, s->d_cells, s->d_dir, s->d_nc_ptr,
+  k_mass_rows<<<(s->N + 127) / 128, 128, 0, ctx->stream>>>((const GaussTable *)ctx->d_gauss, s->N, s->MW, ctx->d_xyz, s->d_cells, s->d_dir, s->d_nc_ptr,
                                                           s->d_nc_cell, s->d_nc_local, s->d_nc_pos, s->d_mval,
                                                           s->d_diag, s->d_b);
   ctx->launches++;
@@ -556,7 +557,7 @@ static int con_gradients(wbem_ctx *ctx, const double *d_tmp_rhs)
       if ((rc = con_mass(ctx))) return rc;
     }
   k_mask_product<<<(s->N + 255) / 256, 256, 0, st>>>(s->N, d_tmp_rhs, ctx->d_surf, s->d_phi);
-  k_gradient_rhs<<<(s->N + 127) / 128, 128, 0, st>>>(s->N, ctx->d_xyz, s->d_cells, s->d_nc_ptr, s->d_nc_cell,
+  k_gradient_rhs<<<(s->N + 127) / 128, 128, 0, st>>>((const GaussTable *)ctx->d_gauss, s->N, ctx->d_xyz, s->d_cells, s->d_nc_ptr, s->d_nc_cell,
                                                     s->d_nc_local, s->d_phi, s->d_b);
   ctx->launches += 2;
   CUDA_OK(ctx, cudaGetLastError());
@@ -726,6 +727,7 @@ extern "C" {
 int wbem_compute_normals(wbem_ctx *ctx, double *normals)
 {
   if (!ctx) return -1;
+  GROUP_FORWARD(ctx, wbem_compute_normals(s, wbem_is_root(s) ? normals : nullptr));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   int rc = con_normals(ctx);
   if (rc) return rc;
@@ -736,6 +738,7 @@ int wbem_compute_normals(wbem_ctx *ctx, double *normals)
 int wbem_compute_surface_gradients(wbem_ctx *ctx, const double *tmp_rhs, double *gradients)
 {
   if (!ctx || !tmp_rhs) return -1;
+  GROUP_FORWARD(ctx, wbem_compute_surface_gradients(s, tmp_rhs, wbem_is_root(s) ? gradients : nullptr));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_compute_surface_gradients before wbem_set_topology");
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[1], tmp_rhs, sizeof(double) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));
@@ -750,6 +753,7 @@ int wbem_set_hanging_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t
 {
   if (!ctx) return -1;
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_set_hanging_constraints before wbem_set_topology");
+  GROUP_FORWARD(ctx, wbem_set_hanging_constraints(s, n_lines, lines, ptr, col, val));
   ConState *s = con_state(ctx);
   for (uint32_t k = 0; k < n_lines; ++k)
     if (lines[k] >= ctx->N) WBEM_FAIL(ctx, -1, "hanging-node line out of range");
@@ -767,6 +771,7 @@ int wbem_set_hanging_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t
 int wbem_compute_constraints(wbem_ctx *ctx, const double *tmp_rhs)
 {
   if (!ctx || !tmp_rhs) return -1;
+  GROUP_FORWARD(ctx, wbem_compute_constraints(s, tmp_rhs));
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   if (!ctx->N) WBEM_FAIL(ctx, -3, "wbem_compute_constraints before wbem_set_topology");
   CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_tmp[1], tmp_rhs, sizeof(double) * ctx->N, cudaMemcpyHostToDevice, ctx->stream));

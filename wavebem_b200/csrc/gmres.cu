@@ -456,6 +456,12 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   rc = wbem_build_preconditioner(ctx);
   g_timer.end();
   if (rc) return rc;
+  if (ctx->group)
+    { // Row blocks that share a device: a block still inside its set-up may sit in a
+      // device-synchronising call (cudaMalloc) -- it must not find a peer's mat-vec epilogue
+      // already spinning for rows it has yet to launch.  One host rendezvous per solve.
+      if ((rc = wbem_group_barrier(ctx))) return rc;
+    }
 
   // solver.solve(cc, sol, system_rhs, preconditioner) (:853), x0 = 0 (:830)
   const int ntmp = ctx->p.gmres_n_tmp_vectors;
@@ -567,6 +573,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], st));
   CUDA_OK(ctx, cudaStreamSynchronize(st));
   CUDA_OK(ctx, cudaGetLastError());
+  if ((rc = wbem_check_gather_timeout(ctx))) return rc;
   double sums[T_NTAGS];
   int counts[T_NTAGS];
   g_timer.resolve(sums, counts, T_NTAGS);

@@ -28,6 +28,7 @@ struct QuadTables
 int wbem_build_quadrature(int quad_order, int sing_order, QuadTables *qt);
 
 struct NcclApi; // comm.cpp
+struct WbemGroup; // group.cpp: one context driving several row blocks (GPUs) from one host thread
 
 // Tiling plan of the regular-pair kernel, built once per topology (plan.cpp).
 struct AssemblyPlan
@@ -121,6 +122,11 @@ struct wbem_ctx
   cudaStream_t stream = nullptr;
   cudaEvent_t ev[16] = {};
   QuadTables qt;
+  void *d_tables = nullptr; // DevTables (assemble.cu) in global memory: per context, not __constant__
+  void *d_gauss = nullptr;  // GaussTable (constraints.cu)
+  // per-device launch state (a context on another GPU needs its own opt-ins / occupancy)
+  bool tiled_attr_set = false, bcr_attr_done = false;
+  int gemv_ctas_per_sm = 0, n_sm = 0;
 
   // sizes
   uint32_t N = 0, C = 0, ld = 0;
@@ -199,6 +205,8 @@ struct wbem_ctx
   std::vector<double> h_con_val;
 
   // comm
+  WbemGroup *group = nullptr; // wbem_params.n_gpus > 1: this shard belongs to a single-process group
+  unsigned int *d_gather_timeout = nullptr; // set by k_epilogue when a peer's flag never arrived
   NcclApi *nccl = nullptr;
   void *nccl_comm = nullptr;
   // peer-to-peer gather fused into k_bem_gemv: every rank's gather buffer mapped through
@@ -245,6 +253,7 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double
                         double *d_dst, bool constrained);
 int wbem_allgather_rows(wbem_ctx *ctx, double *d_buf /* [chunk*world], own block filled */);
 int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank);
+int wbem_check_gather_timeout(wbem_ctx *ctx);
 // gmres.cu
 int wbem_build_preconditioner(wbem_ctx *ctx);
 int wbem_apply_preconditioner(wbem_ctx *ctx, const double *d_in, double *d_out);
@@ -264,6 +273,31 @@ int wbem_compute_constraints_device(wbem_ctx *ctx, const double *d_tmp_rhs);
 void wbem_constraints_free(wbem_ctx *ctx);
 // api.cu
 void wbem_p2p_close(wbem_ctx *ctx);
+// group.cpp -- single-process multi-GPU: the caller's one host thread hands every collective call
+// to one worker thread per row block; the workers run the same per-rank code as the
+// one-process-per-GPU mode and meet in wbem_group_barrier / wbem_group_allgather
+bool wbem_group_forward(const wbem_ctx *ctx);             // true: the call must be handed to the workers
+bool wbem_is_root(const wbem_ctx *ctx);                   // writes the caller's host / device outputs
+int wbem_group_create(const wbem_params *p, wbem_ctx **out, std::string *err);
+int wbem_group_destroy(wbem_ctx *leader);
+int wbem_group_size(const wbem_ctx *ctx);
+wbem_ctx *wbem_group_shard(const wbem_ctx *ctx, int r);
+int wbem_group_run_impl(wbem_ctx *leader, int (*fn)(wbem_ctx *, void *), void *arg);
+int wbem_group_barrier(wbem_ctx *ctx);
+int wbem_group_allgather(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank);
+int wbem_group_p2p_setup(wbem_ctx *ctx);
+template <typename F>
+int wbem_group_run(wbem_ctx *leader, F f)
+{ // f: int(wbem_ctx *shard), run on every shard's worker thread; first error wins
+  return wbem_group_run_impl(
+    leader, [](wbem_ctx *s, void *a) -> int { return (*reinterpret_cast<F *>(a))(s); }, &f);
+}
+#define GROUP_FORWARD(ctx, expr)                                   \
+  if (wbem_group_forward(ctx))                                     \
+  return wbem_group_run(ctx, [&](wbem_ctx *s) -> int { return (expr); })
+// api.cu
+int wbem_create_single(const wbem_params *p, wbem_ctx **out, std::string *err);
+int wbem_destroy_single(wbem_ctx *ctx);
 // comm.cpp
 int wbem_nccl_unique_id(void *id128, std::string *err);
 int wbem_nccl_init(wbem_ctx *ctx, const void *id128);

@@ -231,18 +231,30 @@ __global__ void k_epilogue(uint32_t N, const double *y, const double *__restrict
                            const int32_t *__restrict__ line_of, const uint32_t *__restrict__ cptr,
                            const uint32_t *__restrict__ ccol, const double *__restrict__ cval,
                            double shift, double *__restrict__ dst, const unsigned long long *flags, int n_peers,
-                           unsigned long long epoch)
+                           unsigned long long epoch, unsigned int *timeout_flag)
 {
   if (flags)
-    { // fused gather: wait until every rank has raised its flag for this epoch
+    { // fused gather: wait until every rank has raised its flag for this epoch.  The wait is
+      // bounded (20 s): a peer that died must surface as an error, not as a hung device
       if (threadIdx.x < n_peers)
         {
-          unsigned long long v;
-          do
+          unsigned long long v, t0 = 0, t1;
+          unsigned int spins = 0;
+          for (;;)
             {
               asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(flags + threadIdx.x) : "memory");
+              if (v >= epoch) break;
+              if ((++spins & 0x3ffu) == 0)
+                {
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                  if (!t0) t0 = t1;
+                  if (t1 - t0 > 20000000000ull)
+                    {
+                      atomicExch(timeout_flag, 1u);
+                      break;
+                    }
+                }
             }
-          while (v < epoch);
         }
       __syncthreads();
     }
@@ -295,6 +307,7 @@ int wbem_allgather_rows(wbem_ctx *ctx, double *d_buf)
 int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank)
 {
   if (ctx->p.world_size <= 1) return 0;
+  if (ctx->group) return wbem_group_allgather(ctx, d_buf, bytes_per_rank); // one process: peer copies
   if (!ctx->nccl_comm)
     {
       // diagnostics only: time one rank's share of a sharded run on a single GPU
@@ -303,6 +316,17 @@ int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank)
     }
   const char *base = (const char *)d_buf;
   return wbem_nccl_allgather(ctx, base + bytes_per_rank * ctx->p.rank, d_buf, bytes_per_rank);
+}
+
+// after a synchronisation point: did a fused gather give up waiting for a peer?
+int wbem_check_gather_timeout(wbem_ctx *ctx)
+{
+  if (!ctx->d_gather_timeout) return 0;
+  unsigned int f = 0;
+  CUDA_OK(ctx, cudaMemcpyAsync(&f, ctx->d_gather_timeout, sizeof(f), cudaMemcpyDeviceToHost, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  if (f) WBEM_FAIL(ctx, -5, "fused mat-vec gather: a peer row block never delivered its rows (20 s)");
+  return 0;
 }
 
 // chunk lists (see header comment): d_list_o = chunks with any other_nodes != 0, d_list_s =
@@ -331,7 +355,7 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   if (ctx->nloc || use_p2p)
     {
       ctx->timer.begin(T_GEMV);
-      static int ctas_per_sm = 0, n_sm = 0;
+      int &ctas_per_sm = ctx->gemv_ctas_per_sm, &n_sm = ctx->n_sm;
       if (!ctas_per_sm)
         {
           CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_bem_gemv, GEMV_WARPS * 32, 0));
@@ -398,6 +422,13 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
       ctx->timer.end();
       if (rc) return rc;
     }
+  if (use_p2p && ctx->group && ctx->p.fused_gather_on_shared_device)
+    { // test mode, row blocks sharing a device: two streams of one device may share a hardware
+      // queue, and an epilogue spinning for a mat-vec queued behind it would never end.  So every
+      // block launches its mat-vec before any block launches its (waiting) epilogue.
+      const int brc = wbem_group_barrier(ctx);
+      if (brc) return brc;
+    }
   const bool shift = (mode == 0) && ctx->pure_neumann;
   if (shift)
     {
@@ -409,7 +440,8 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   const bool con = constrained && ctx->n_lines > 0;
   k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(
     N, ygather, d_src, con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0, d_dst,
-    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_len) : nullptr, P, ctx->p2p_epoch);
+    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_len) : nullptr, P, ctx->p2p_epoch,
+    ctx->d_gather_timeout);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return 0;

@@ -531,7 +531,7 @@ __global__ void __launch_bounds__(256, 1) k_bcr_solve_fused(const BcrSolveArgs a
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
-static bool g_attr_done = false;
+
 
 int wbem_device_precond_factor(wbem_ctx *ctx)
 {
@@ -584,13 +584,13 @@ int wbem_device_precond_factor(wbem_ctx *ctx)
       cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, k_bcr_solve_fused, 256, 0);
       dp->fused_grid = (coop && per_sm >= 1 && dp->lev.size() <= BCR_MAX_LEVELS) ? n_sm : 0;
     }
-  if (!g_attr_done)
+  if (!ctx->bcr_attr_done)
     {
       CUDA_OK(ctx, cudaFuncSetAttribute(k_bcr_invert, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(sizeof(double) * 2 * BS * LDP)));
       CUDA_OK(ctx, cudaFuncSetAttribute(k_bcr_update, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                         (int)(sizeof(double) * 4 * BS * LDP)));
-      g_attr_done = true;
+      ctx->bcr_attr_done = true;
     }
   cudaStream_t st = ctx->stream;
   CUDA_OK(ctx, cudaMemsetAsync(dp->info, 0, sizeof(int), st));
