@@ -1,22 +1,25 @@
-"""Quick assembly timing + parity spot check on the GPU box (development helper)."""
+"""Quick assembly timing + parity spot check on the GPU box (development helper).
+usage: quick_asm.py [nodes] [--variant V] [--check]"""
 import sys, os, time
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import numpy as np
 import wavebem_b200 as wb
 from wavebem_b200 import meshgen
-n = int(sys.argv[1]) if len(sys.argv) > 1 else 20000
+args = [a for a in sys.argv[1:] if not a.startswith("--")]
+n = int(args[0]) if args else 20000
+variant = int(sys.argv[sys.argv.index("--variant") + 1]) if "--variant" in sys.argv else 0
 m = meshgen.wigley_tank_for_nodes(n)
-ctx = wb.Context()
+ctx = wb.Context(assemble_variant=variant)
 ctx.set_topology(m.n_nodes, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx)
 ctx.set_geometry(m.xyz)
 ms = ctx.time_assemble(5)
 t = ctx.timings()
 evals = 16.0 * m.n_nodes * m.n_cells
-print(f"N={m.n_nodes} assemble {ms:.3f} ms regular {t['assemble_regular_ms']:.3f} ms -> "
+print(f"{os.path.basename(wb.LIB_PATH)} variant {variant}: N={m.n_nodes} assemble {ms:.3f} ms regular {t['assemble_regular_ms']:.3f} ms -> "
       f"{34 * evals / (t['assemble_regular_ms'] * 1e-3) / 1e12:.2f} TFLOP/s algorithmic; peak {ctx.measure_fp64_peak():.2f}")
 if "--check" in sys.argv:
     from oracle import oracle as orc
     r0 = m.n_nodes // 3
     on, od = orc.assemble_rows(m.xyz, m.cells, m.dir_flag, m.dn_ptr, m.dn_idx, r0, r0 + 64)
     gn, gd = ctx.get_rows(0, r0, r0 + 64), ctx.get_rows(1, r0, r0 + 64)
-    print("max abs err N", np.abs(gn - on).max(), "D rel", (np.abs(gd - od) / np.abs(od).max()).max())
+    print("   max abs err N", np.abs(gn - on).max(), "D rel", (np.abs(gd - od) / np.abs(od).max()).max())

@@ -260,10 +260,8 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_sing_cellpos);
   FREE_DEV(ctx->d_sing_idx);
   FREE_DEV(ctx->d_tile_sing);
-  FREE_DEV(ctx->d_cl_cell_ptr);
-  FREE_DEV(ctx->d_cl_slot_ptr);
   FREE_DEV(ctx->d_slot_col);
-  FREE_DEV(ctx->d_color_clusters);
+  FREE_DEV(ctx->d_cta_desc);
   FREE_DEV(ctx->d_cell_slots);
   FREE_DEV(ctx->d_xyz);
   FREE_DEV(ctx->d_cellgeo);
@@ -379,7 +377,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
       for (int i = 0; i < j; ++i)
         if (cell_dofs[4 * (size_t)c + i] == cell_dofs[4 * (size_t)c + j]) ctx->has_degenerate_cells = true;
   // tiling plan (plan.cpp); W and the cell cap match k_assemble_tiled's shared-memory tile
-  int rc = wbem_build_plan(N, C, cell_dofs, WBEM_TILE_W, 64, &ctx->plan);
+  int rc = wbem_build_plan(N, C, cell_dofs, wbem_tile_width(), 64, &ctx->plan);
   if (rc) WBEM_FAIL(ctx, -1, "wbem_build_plan failed (%d): cell dof out of range?", rc);
   const AssemblyPlan &pl = ctx->plan;
 
@@ -433,11 +431,22 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   std::vector<uint32_t> cluster_of_pos(C);
   for (uint32_t k = 0; k < pl.n_clusters; ++k)
     for (uint32_t p = pl.cl_cell_ptr[k]; p < pl.cl_cell_ptr[k + 1]; ++p) cluster_of_pos[p] = k;
-  const uint32_t row_tiles = (ctx->nloc + WBEM_TILE_ROWS - 1) / WBEM_TILE_ROWS;
+  const uint32_t tile_rows = wbem_tile_rows();
+  const uint32_t row_tiles = (ctx->nloc + tile_rows - 1) / tile_rows;
   std::vector<uint8_t> tile_sing((size_t)std::max(1u, row_tiles) * std::max(1u, pl.n_clusters), 0);
   for (uint32_t r = 0; r < ctx->nloc; ++r)
     for (uint32_t k = sing_ptr[r]; k < sing_ptr[r + 1]; ++k)
-      tile_sing[(size_t)(r / WBEM_TILE_ROWS) * pl.n_clusters + cluster_of_pos[sing_pos[k]]] = 1;
+      tile_sing[(size_t)(r / tile_rows) * pl.n_clusters + cluster_of_pos[sing_pos[k]]] = 1;
+  // work items of the regular-pair kernel in launch (colour) order
+  std::vector<uint32_t> cta_desc(4 * (size_t)std::max(1u, pl.n_clusters), 0);
+  for (uint32_t k = 0; k < pl.n_clusters; ++k)
+    {
+      const uint32_t cl = pl.color_clusters[k];
+      cta_desc[4 * (size_t)k + 0] = pl.cl_cell_ptr[cl];
+      cta_desc[4 * (size_t)k + 1] = pl.cl_slot_ptr[cl];
+      cta_desc[4 * (size_t)k + 2] = (pl.cl_cell_ptr[cl + 1] - pl.cl_cell_ptr[cl]) | ((pl.cl_slot_ptr[cl + 1] - pl.cl_slot_ptr[cl]) << 8);
+      cta_desc[4 * (size_t)k + 3] = cl;
+    }
 
   // uploads
   if ((rc = dev_upload(ctx, &ctx->d_cell_dofs, dofs_po))) return rc;
@@ -449,10 +458,8 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_upload(ctx, &ctx->d_sing_cellpos, sing_pos))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_sing_idx, sing_idx))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_tile_sing, tile_sing))) return rc;
-  if ((rc = dev_upload(ctx, &ctx->d_cl_cell_ptr, pl.cl_cell_ptr))) return rc;
-  if ((rc = dev_upload(ctx, &ctx->d_cl_slot_ptr, pl.cl_slot_ptr))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_slot_col, pl.slot_col))) return rc;
-  if ((rc = dev_upload(ctx, &ctx->d_color_clusters, pl.color_clusters))) return rc;
+  if ((rc = dev_upload(ctx, &ctx->d_cta_desc, cta_desc))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_cell_slots, pl.cell_slots))) return rc;
 
   // storage (BEMProblem::reinit, :55-71)
@@ -460,7 +467,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   const int ntmp = ctx->p.gmres_n_tmp_vectors;
   const int band = std::max(ctx->p.preconditioner_band, 2);
   if ((rc = dev_alloc(ctx, &ctx->d_xyz, 3 * (size_t)N))) return rc;
-  if ((rc = dev_alloc(ctx, &ctx->d_cellgeo, (size_t)C * 7 * ctx->qt.nq + 16))) return rc;
+  if ((rc = dev_alloc(ctx, &ctx->d_cellgeo, (size_t)C * 8 * ctx->qt.nq + 16))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_Nm, nloc * ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_Dm, nloc * ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_alpha, ld))) return rc;

@@ -2,11 +2,12 @@
 // (reference source/bem_problem.cc:106-590) and compute_alpha (:594-618).
 //
 //   k_cell_geometry      FEValues of the regular rule for every cell (:133-137, 192-196),
-//                        folded into per-(cell,q) constants:  y_q, n_q JxW_q /(-4 pi), JxW_q/(4 pi)
-//   k_assemble_tiled     regular (node, cell) pairs (:241-260, 531-537): one CTA per
-//                        (256-row tile, cell cluster); panel data staged in shared memory by a
-//                        TMA bulk copy; per-column accumulators in shared memory; deterministic
-//                        STORE/ADD flush (see plan.cpp)
+//                        folded into per-(cell,q) constants:  y_q, n_q JxW_q /(-4 pi), JxW_q/(4 pi),
+//                        JxW_q u_q/(4 pi)
+//   k_assemble_rows      regular (node, cell) pairs (:241-260, 531-537): one CTA per
+//                        (128-row tile, cell cluster), one thread per row; panel data staged in
+//                        shared memory by a TMA bulk copy; per-column accumulators in shared
+//                        memory; deterministic STORE/ADD flush (see plan.cpp)
 //   k_assemble_simple    same integrals, literal reference arithmetic, global atomics: the
 //                        independent cross-check and the fallback for quadrature orders != 4
 //   k_assemble_singular  pairs whose cell holds a dof of double_nodes_set[i] (:223-230,
@@ -20,6 +21,7 @@
 #include "q1map.cuh"
 
 #define FOUR_PI 12.566370614359172953850573533118
+#define GEO_REC 8 // doubles per (cell, q): y[3], n JxW/(-4 pi)[3], JxW/(4 pi), JxW u_q/(4 pi)
 
 struct DevTables
 {
@@ -54,8 +56,9 @@ int wbem_upload_tables(wbem_ctx *ctx)
   return 0;
 }
 
-// One thread per (cell position, q).  Output layout per cell: [7][nq] =
-// y_x, y_y, y_z, nJ_x, nJ_y, nJ_z, wJ   with  nJ = n JxW / (-4 pi),  wJ = JxW / (4 pi).
+// One thread per (cell position, q).  Output layout per cell: [GEO_REC = 8][nq] =
+// y_x, y_y, y_z, nJ_x, nJ_y, nJ_z, wJ, wJ u_q   with  nJ = n JxW / (-4 pi),  wJ = JxW / (4 pi)
+// (u_q = the point's first reference coordinate: the first-moment weight of the row kernel).
 // n JxW = +-(d_u x d_v) w_q exactly (no normalisation needed).
 __global__ void k_cell_geometry(const DevTables *__restrict__ qt, uint32_t C, int nq, const double *__restrict__ xyz,
                                 const uint32_t *__restrict__ cell_dofs,
@@ -72,7 +75,7 @@ __global__ void k_cell_geometry(const DevTables *__restrict__ qt, uint32_t C, in
   const double w = qt->g_w[q];
   const double sgn = dir[c] ? 1.0 : -1.0;
   const double cn = sqrt(cr[0] * cr[0] + cr[1] * cr[1] + cr[2] * cr[2]);
-  double *g = geo + (size_t)c * 7 * nq;
+  double *g = geo + (size_t)c * GEO_REC * nq;
   g[0 * nq + q] = y[0];
   g[1 * nq + q] = y[1];
   g[2 * nq + q] = y[2];
@@ -81,12 +84,14 @@ __global__ void k_cell_geometry(const DevTables *__restrict__ qt, uint32_t C, in
   g[4 * nq + q] = cr[1] * f;
   g[5 * nq + q] = cr[2] * f;
   g[6 * nq + q] = cn * w * (1.0 / FOUR_PI);
+  g[7 * nq + q] = (cn * w * (1.0 / FOUR_PI)) * qt->g_u[q];
 }
 
 // The literal FEValues of the regular rule handed over by the caller (reference :192-196:
 // get_quadrature_points / get_normal_vectors / JxW), caller's cell order, folded into the same
 // per-(cell,q) constants as k_cell_geometry.
-__global__ void k_fevalues_to_geometry(uint32_t C, int nq, const uint32_t *__restrict__ cell_order,
+__global__ void k_fevalues_to_geometry(const DevTables *__restrict__ qt, uint32_t C, int nq,
+                                       const uint32_t *__restrict__ cell_order,
                                        const double *__restrict__ qp, const double *__restrict__ nrm,
                                        const double *__restrict__ jxw, double *__restrict__ geo)
 {
@@ -95,7 +100,7 @@ __global__ void k_fevalues_to_geometry(uint32_t C, int nq, const uint32_t *__res
   const int q = t - p * nq;
   if (p >= C) return;
   const size_t src = (size_t)cell_order[p] * nq + q;
-  double *g = geo + (size_t)p * 7 * nq;
+  double *g = geo + (size_t)p * GEO_REC * nq;
   const double w = jxw[src];
   g[0 * nq + q] = qp[3 * src + 0];
   g[1 * nq + q] = qp[3 * src + 1];
@@ -104,6 +109,7 @@ __global__ void k_fevalues_to_geometry(uint32_t C, int nq, const uint32_t *__res
   g[4 * nq + q] = nrm[3 * src + 1] * w * (-1.0 / FOUR_PI);
   g[5 * nq + q] = nrm[3 * src + 2] * w * (-1.0 / FOUR_PI);
   g[6 * nq + q] = w * (1.0 / FOUR_PI);
+  g[7 * nq + q] = (w * (1.0 / FOUR_PI)) * qt->g_u[q];
 }
 
 int wbem_upload_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW)
@@ -117,7 +123,8 @@ int wbem_upload_fevalues(wbem_ctx *ctx, const double *q_points, const double *no
   CUDA_OK(ctx, cudaMemcpyAsync(d, q_points, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
   CUDA_OK(ctx, cudaMemcpyAsync(d + 3 * n, normals, sizeof(double) * 3 * n, cudaMemcpyHostToDevice, st));
   CUDA_OK(ctx, cudaMemcpyAsync(d + 6 * n, JxW, sizeof(double) * n, cudaMemcpyHostToDevice, st));
-  k_fevalues_to_geometry<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(ctx->C, nq, ctx->d_cell_order, d, d + 3 * n,
+  k_fevalues_to_geometry<<<(unsigned)((n + 255) / 256), 256, 0, st>>>((const DevTables *)ctx->d_tables, ctx->C, nq,
+                                                                     ctx->d_cell_order, d, d + 3 * n,
                                                                      d + 6 * n, ctx->d_cellgeo);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
@@ -153,29 +160,6 @@ __device__ __forceinline__ double rsqrt_h3(double a)
   const double p = fma(0.375, e, 0.5);
   const double ye = y * e;
   return fma(p, ye, y);
-}
-
-// a + b and a - b through the FMA datapath (bit-identical results: a*1 + b is rounded once).
-// WBEM_FMA_ADDS selects it; see the opcode probe (wbem_issue_probe 100..103) for the reason.
-__device__ __forceinline__ double add64(double a, double b)
-{
-#ifdef WBEM_FMA_ADDS
-  double r;
-  asm("fma.rn.f64 %0, %1, 0d3FF0000000000000, %2;" : "=d"(r) : "d"(a), "d"(b));
-  return r;
-#else
-  return a + b;
-#endif
-}
-__device__ __forceinline__ double sub64(double a, double b)
-{
-#ifdef WBEM_FMA_ADDS
-  double r;
-  asm("fma.rn.f64 %0, %1, 0dBFF0000000000000, %2;" : "=d"(r) : "d"(b), "d"(a));
-  return r;
-#else
-  return a - b;
-#endif
 }
 
 __global__ void k_rsqrt_selftest(const double *__restrict__ in, double *__restrict__ out, int n)
@@ -230,43 +214,23 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
   while (!done);
 }
 
-// ---------------------------------------------------------------------------------------
-// Tiled regular-pair kernel, Gauss 4x4.
-//
-// One CTA = (64-row tile) x (one cell cluster), 128 threads: TWO threads per collocation
-// row, each integrating two of the four Gauss lines (8 of the 16 points) of every cell.
-// They swap their partial moments with one shuffle; thread 0 of the pair finishes the
-// Neumann sums, thread 1 the Dirichlet sums, and each adds its 4 values to per-column
-// accumulators in shared memory (acc[matrix][slot][row]).  TILE_MIN_CTAS CTAs are resident
-// per SM (one warp of every CTA on every scheduler) so one CTA's prologue / flush overlaps
-// the others' FP64 loops.  Panel data arrives in chunks of TILE_CHUNK cells through a
-// double-buffered TMA bulk copy; the LAST warp to finish a chunk (shared-memory counter)
-// re-arms the barrier and issues the refill, so no warp ever spins and the integration loop
-// has no CTA-wide barrier.
-// ---------------------------------------------------------------------------------------
-#define TILE_ROWS WBEM_TILE_ROWS          // 64
-#define TILE_THREADS (2 * TILE_ROWS)      // 128
-#define TILE_WARPS (TILE_THREADS / 32)
-#define TILE_W WBEM_TILE_W
-#define TILE_MAX_CELLS 64                 // bit mask of singular cells is 64 bits wide
-#ifndef WBEM_TILE_CHUNK
-#define WBEM_TILE_CHUNK 8
-#endif
-#ifndef WBEM_TILE_MIN_CTAS
-#define WBEM_TILE_MIN_CTAS 3
-#endif
-#define TILE_CHUNK WBEM_TILE_CHUNK
-#define ACC_STRIDE (TILE_ROWS + 1)
-// offset between the two matrices' accumulators: = 8 (mod 16) doubles, so that the N-thread and
-// the D-thread of a row hit disjoint shared-memory banks
-#define ACC_MATOFF (TILE_W * ACC_STRIDE + ((8 - (TILE_W * ACC_STRIDE) % 16) + 16) % 16)
+#define TILE_MAX_CELLS 64 // bit mask of singular cells is 64 bits wide
+
+struct CtaDesc
+{ // one (cluster) work item in launch order: everything the CTA needs from one 16-byte load
+  uint32_t p0;      // first cell (processing position)
+  uint32_t s0;      // first slot
+  uint32_t counts;  // cells | slots << 8
+  uint32_t cluster; // cluster id (alpha partials, singular-pair map)
+};
 
 struct TiledArgs
 {
   const double *xyz;         // [N][3]
-  const double *geo;         // [C][7][16] processing order
+  const double *geo;         // [C][GEO_REC][16] processing order
   const uint8_t *cell_slots; // [C][4]
-  const uint32_t *cl_cell_ptr, *cl_slot_ptr, *slot_col, *color_clusters;
+  const CtaDesc *desc;       // [clusters] in launch (colour) order
+  const uint32_t *slot_col;
   const uint32_t *sing_ptr, *sing_cellpos; // CSR by local row
   const uint8_t *tile_sing;                // [row tiles][clusters]: any singular pair inside?
   double *Nm, *Dm;
@@ -274,14 +238,6 @@ struct TiledArgs
   uint32_t ld, row0, nloc, cluster_base, n_clusters;
   double g1_x[4]; // nodes of the 1-D Gauss rule (kernel parameters sit in the constant bank)
 };
-
-constexpr size_t tiled_smem_bytes()
-{
-  return sizeof(double) * (2 * ACC_MATOFF + 2 * TILE_CHUNK * 7 * 16) + 40 /*mbar + counters*/ + TILE_MAX_CELLS * 4 +
-         ((TILE_W + 3) / 4) * 16;
-}
-
-#define TILE_BLOCK TILE_THREADS
 
 // one column value of the flush: STORE for the first writer of a column, RED.ADD.F64 for later
 // ones -- both predicated, so a warp with mixed lanes runs one instruction stream
@@ -296,232 +252,293 @@ __device__ __forceinline__ void flush_value(double *p, double v, uint32_t is_add
                : "memory");
 }
 
-__global__ void __launch_bounds__(TILE_BLOCK, WBEM_TILE_MIN_CTAS) k_assemble_tiled(const TiledArgs a)
+// ---------------------------------------------------------------------------------------
+// Row kernel: the same tiling, ONE thread per collocation row (T1_RPT rows per thread).
+//
+// A thread integrates all 16 Gauss points of a cell for its row(s) and both kernels, so there is
+// no partner thread, no shuffle and no select in the loop: per (cell, row) 16 evaluations cost
+// ~390 FP64 instructions and ~90 others (56 broadcast LDS.128 of the panel record -- shared by
+// the T1_RPT rows of a thread --, 16 MUFU, 4 + 4 128-bit accumulator updates).  The accumulators
+// are acc[slot][row] pairs (N, D) in shared memory: consecutive lanes touch consecutive 16-byte
+// words (no bank conflicts in the loop); the slot stride of ROWS + 1 pairs keeps the flush
+// (lanes over slots) at the minimum of four wavefronts per 128-bit request.
+// ---------------------------------------------------------------------------------------
+#ifndef WBEM_T1_THREADS
+#define WBEM_T1_THREADS 128
+#endif
+#ifndef WBEM_T1_RPT
+#define WBEM_T1_RPT 1
+#endif
+#ifndef WBEM_T1_W
+#define WBEM_T1_W 32
+#endif
+#ifndef WBEM_T1_MINCTAS
+#define WBEM_T1_MINCTAS 3
+#endif
+#ifndef WBEM_T1_CHUNK
+#define WBEM_T1_CHUNK 4
+#endif
+#define T1_THREADS WBEM_T1_THREADS
+#define T1_RPT WBEM_T1_RPT
+#define T1_ROWS (T1_THREADS * T1_RPT)
+#define T1_W WBEM_T1_W
+#define T1_CHUNK WBEM_T1_CHUNK
+#define T1_WARPS (T1_THREADS / 32)
+#define T1_STRIDE (T1_ROWS + 1) // double2 units between consecutive slots
+#define T1_REC (GEO_REC * 16)   // doubles per cell record
+
+constexpr size_t rows_smem_bytes()
+{
+  return sizeof(double) * (2 * (size_t)T1_W * T1_STRIDE + 2 * T1_CHUNK * T1_REC) + 40 + TILE_MAX_CELLS * 4 +
+         ((T1_W + 3) / 4) * 16;
+}
+
+__global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(const TiledArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  double *acc = reinterpret_cast<double *>(smem_raw);              // [2][ACC_MATOFF]
-  double *geo = acc + 2 * ACC_MATOFF;                              // [2][CHUNK][7][16]
-  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * TILE_CHUNK * 112); // [2] "full" + [2] "empty" barriers
-  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(bar + 4);         // [2] warps done with a buffer
-  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 5);       // [cells] packed 4 x u8
-  uint32_t *s_col = s_slots + TILE_MAX_CELLS;                      // [W]
+  double2 *acc = reinterpret_cast<double2 *>(smem_raw);                    // [W][T1_STRIDE] (N, D)
+  double *geo = reinterpret_cast<double *>(acc + (size_t)T1_W * T1_STRIDE); // [2][CHUNK][8][16]
+  uint64_t *bar = reinterpret_cast<uint64_t *>(geo + 2 * T1_CHUNK * T1_REC); // [2] full + [2] empty
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(bar + 4);
+  uint32_t *s_slots = reinterpret_cast<uint32_t *>(bar + 5);
+  uint32_t *s_col = s_slots + TILE_MAX_CELLS;
 
   const int tid = threadIdx.x;
-  const int row_l = tid >> 1, h = tid & 1;
-  const uint32_t cluster = a.color_clusters[a.cluster_base + blockIdx.x];
-  const uint32_t p0 = a.cl_cell_ptr[cluster], p1 = a.cl_cell_ptr[cluster + 1];
-  const uint32_t s0 = a.cl_slot_ptr[cluster], s1 = a.cl_slot_ptr[cluster + 1];
-  const int ncell = (int)(p1 - p0), nslot = (int)(s1 - s0);
-  const int nchunk = (ncell + TILE_CHUNK - 1) / TILE_CHUNK;
-  const uint32_t lrow_base = blockIdx.y * TILE_ROWS;
-  const uint32_t lrow = lrow_base + row_l;
-  const uint32_t lrow_c = lrow < a.nloc ? lrow : a.nloc - 1;
+  // one 16-byte load tells the CTA its work item: the first panel chunk is on its way one
+  // global-memory latency after the CTA starts
+  const uint4 dsc = *reinterpret_cast<const uint4 *>(a.desc + a.cluster_base + blockIdx.x);
+  const uint32_t p0 = dsc.x, s0 = dsc.y, cluster = dsc.w;
+  const int ncell = (int)(dsc.z & 0xffu), nslot = (int)(dsc.z >> 8);
+  const uint32_t p1 = p0 + ncell;
+  const int nchunk = (ncell + T1_CHUNK - 1) / T1_CHUNK;
+  const uint32_t lrow_base = blockIdx.y * T1_ROWS;
 
   auto issue_chunk = [&](int c) {
-    const int nc = min(TILE_CHUNK, ncell - c * TILE_CHUNK);
-    const uint32_t bytes = (uint32_t)nc * 112 * sizeof(double);
+    const int nc = min(T1_CHUNK, ncell - c * T1_CHUNK);
+    const uint32_t bytes = (uint32_t)nc * T1_REC * sizeof(double);
     mbar_expect_tx(&bar[c & 1], bytes);
-    bulk_copy_g2s(geo + (c & 1) * TILE_CHUNK * 112, a.geo + ((size_t)p0 + (size_t)c * TILE_CHUNK) * 112, bytes,
+    bulk_copy_g2s(geo + (c & 1) * T1_CHUNK * T1_REC, a.geo + ((size_t)p0 + (size_t)c * T1_CHUNK) * T1_REC, bytes,
                   &bar[c & 1]);
   };
   if (tid == 0)
     {
-      mbar_init(&bar[0], 1); // "full": TMA bytes landed
+      mbar_init(&bar[0], 1);
       mbar_init(&bar[1], 1);
-      mbar_init(&bar[2], TILE_THREADS); // "empty": every thread is done reading the buffer
-      mbar_init(&bar[3], TILE_THREADS);
+      mbar_init(&bar[2], T1_THREADS);
+      mbar_init(&bar[3], T1_THREADS);
       s_cnt[0] = 0;
       s_cnt[1] = 0;
       issue_chunk(0);
       if (nchunk > 1) issue_chunk(1);
     }
-  // singular cells of this row inside the cluster -> bit mask (they are integrated by
-  // k_assemble_singular only, reference :241/:261).  Most (row tile, cluster) pairs hold no
-  // singular pair at all: a host-built byte map lets them skip the list walk.
-  unsigned long long smask = 0ull;
-  if (a.tile_sing[(size_t)blockIdx.y * a.n_clusters + cluster])
+  // thread t owns the tile's rows t, t + T1_THREADS, ... (lanes stay on consecutive rows)
+  unsigned long long smask[T1_RPT];
+  double xi0[T1_RPT], xi1[T1_RPT], xi2[T1_RPT], row_sum[T1_RPT];
+  const bool any_sing = a.tile_sing[(size_t)blockIdx.y * a.n_clusters + cluster] != 0;
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
     {
-      const uint32_t b = a.sing_ptr[lrow_c], e = a.sing_ptr[lrow_c + 1];
-      for (uint32_t k = b; k < e; k += 4)
-        {
-          uint32_t pos[4];
-#pragma unroll
-          for (int i = 0; i < 4; ++i) pos[i] = (k + i < e) ? a.sing_cellpos[k + i] : 0xffffffffu;
-#pragma unroll
-          for (int i = 0; i < 4; ++i)
-            if (pos[i] >= p0 && pos[i] < p1) smask |= 1ull << (pos[i] - p0);
-        }
+      const uint32_t lrow = lrow_base + r * T1_THREADS + tid;
+      const uint32_t lrow_c = lrow < a.nloc ? lrow : a.nloc - 1;
+      smask[r] = 0ull;
+      if (any_sing)
+        for (uint32_t k = a.sing_ptr[lrow_c]; k < a.sing_ptr[lrow_c + 1]; ++k)
+          {
+            const uint32_t pos = a.sing_cellpos[k];
+            if (pos >= p0 && pos < p1) smask[r] |= 1ull << (pos - p0);
+          }
+      xi0[r] = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 0];
+      xi1[r] = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 1];
+      xi2[r] = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 2];
+      row_sum[r] = 0.0;
     }
-  const double xi0 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 0];
-  const double xi1 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 1];
-  const double xi2 = a.xyz[3 * (size_t)(a.row0 + lrow_c) + 2];
-  for (int i = tid; i < ncell; i += TILE_THREADS)
-    s_slots[i] = reinterpret_cast<const uint32_t *>(a.cell_slots)[p0 + i];
-  for (int i = tid; i < nslot; i += TILE_THREADS) s_col[i] = a.slot_col[s0 + i];
-  // zero the accumulators in use: thread (row, h) clears matrix h of its row
-  double *accM = acc + h * ACC_MATOFF + row_l;
-  for (int s = 0; s < nslot; ++s) accM[s * ACC_STRIDE] = 0.0;
-  __syncthreads(); // barriers initialised, slot tables visible
+  for (int i = tid; i < ncell; i += T1_THREADS) s_slots[i] = reinterpret_cast<const uint32_t *>(a.cell_slots)[p0 + i];
+  for (int i = tid; i < nslot; i += T1_THREADS) s_col[i] = a.slot_col[s0 + i];
+  double2 *accT = acc + tid;
+  for (int s = 0; s < nslot; ++s)
+#pragma unroll
+    for (int r = 0; r < T1_RPT; ++r) accT[s * T1_STRIDE + r * T1_THREADS] = make_double2(0.0, 0.0);
+  __syncthreads();
 
-  const double vq0 = a.g1_x[2 * h], vq1 = a.g1_x[2 * h + 1];
-  double row_sum = 0.0; // sum over this cluster's regular cells of the zeroth moment (h = 0: Neumann)
+  const double u0 = a.g1_x[0], u1 = a.g1_x[1], u2 = a.g1_x[2], u3 = a.g1_x[3];
+#ifdef WBEM_EXP_NOLOOP
+  for (int c = 0; c < (a.ld == 1 ? nchunk : 0); ++c)
+#else
   for (int c = 0; c < nchunk; ++c)
+#endif
     {
       mbar_wait(&bar[c & 1], (c >> 1) & 1);
-      const double *gc = geo + (c & 1) * TILE_CHUNK * 112 + 8 * h; // this thread's 8 points
-      const int kend = min(TILE_CHUNK, ncell - c * TILE_CHUNK);
+      const double *gc = geo + (c & 1) * T1_CHUNK * T1_REC;
+      const int kend = min(T1_CHUNK, ncell - c * T1_CHUNK);
       for (int kk = 0; kk < kend; ++kk)
         {
-          const int k = c * TILE_CHUNK + kk;
-          const double *g = gc + kk * 112;
-          // accumulator slots of this cell: loaded now, added to after the integration (the
-          // host routes meshes whose cells repeat a dof to the simple kernel)
+          const int k = c * T1_CHUNK + kk;
+          const double *g = gc + kk * T1_REC;
           const uint32_t sl = s_slots[k];
-          double *const pa = accM + (sl & 0xff) * ACC_STRIDE, *const pb = accM + ((sl >> 8) & 0xff) * ACC_STRIDE,
-                        *const pc = accM + ((sl >> 16) & 0xff) * ACC_STRIDE, *const pd = accM + (sl >> 24) * ACC_STRIDE;
-          const double oa = *pa, ob = *pb, oc = *pc, od = *pd;
-          double SN, SuN, SvN, SuvN, SD, SuD, SvD, SuvD;
+          double SN[T1_RPT], SuN[T1_RPT], SvN[T1_RPT], SuvN[T1_RPT], SD[T1_RPT], SuD[T1_RPT], SvD[T1_RPT], SuvD[T1_RPT];
 #pragma unroll
-          for (int j = 0; j < 2; ++j)
+          for (int j = 0; j < 4; ++j)
             {
-              double t0n = 0, t1n = 0, t0d = 0, t1d = 0;
+              const double vq = j == 0 ? u0 : j == 1 ? u1 : j == 2 ? u2 : u3;
+              double t0n[T1_RPT], t1n[T1_RPT], t0d[T1_RPT], t1d[T1_RPT];
 #pragma unroll
               for (int qx = 0; qx < 4; ++qx)
                 {
                   const int q = j * 4 + qx;
-                  const double Rx = sub64(g[q], xi0);
-                  const double Ry = sub64(g[16 + q], xi1);
-                  const double Rz = sub64(g[32 + q], xi2);
-                  const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
-                  const double ri = rsqrt_h3(r2);
-                  const double ri2 = ri * ri;
-                  const double ri3 = ri2 * ri;
-                  const double Rn = fma(Rz, g[80 + q], fma(Ry, g[64 + q], Rx * g[48 + q]));
-                  const double av = Rn * ri3;       // (D . n) JxW
-                  const double bv = g[96 + q] * ri; // d JxW
-                  const double uq = a.g1_x[qx];
-                  if (qx == 0)
+                  const double uq = qx == 0 ? u0 : qx == 1 ? u1 : qx == 2 ? u2 : u3;
+                  const double y0 = g[q], y1 = g[16 + q], y2 = g[32 + q];
+                  const double n0 = g[48 + q], n1 = g[64 + q], n2 = g[80 + q], wj = g[96 + q], wju = g[112 + q];
+#pragma unroll
+                  for (int r = 0; r < T1_RPT; ++r)
                     {
-                      t0n = av;
-                      t1n = av * uq;
-                      t0d = bv;
-                      t1d = bv * uq;
+                      const double Rx = y0 - xi0[r], Ry = y1 - xi1[r], Rz = y2 - xi2[r];
+                      const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
+                      const double ri = rsqrt_h3(r2);
+                      const double ri2 = ri * ri;
+                      const double ri3 = ri2 * ri;
+                      const double Rn = fma(Rz, n2, fma(Ry, n1, Rx * n0));
+                      const double av = Rn * ri3; // (D . n) JxW; the single-layer d JxW = wj ri goes
+                      if (qx == 0)                // straight into its two line moments (wju = wj u_q)
+                        {
+                          t0n[r] = av;
+                          t1n[r] = av * uq;
+                          t0d[r] = wj * ri;
+                          t1d[r] = wju * ri;
+                        }
+                      else
+                        {
+                          t0n[r] += av;
+                          t1n[r] = fma(av, uq, t1n[r]);
+                          t0d[r] = fma(wj, ri, t0d[r]);
+                          t1d[r] = fma(wju, ri, t1d[r]);
+                        }
                     }
-                  else
-                    {
-                      t0n = add64(t0n, av);
-                      t1n = fma(av, uq, t1n);
-                      t0d = add64(t0d, bv);
-                      t1d = fma(bv, uq, t1d);
-                    }
                 }
-              if (j == 0)
-                {
-                  SN = t0n;
-                  SuN = t1n;
-                  SvN = vq0 * t0n;
-                  SuvN = vq0 * t1n;
-                  SD = t0d;
-                  SuD = t1d;
-                  SvD = vq0 * t0d;
-                  SuvD = vq0 * t1d;
-                }
-              else
-                {
-                  SN = add64(SN, t0n);
-                  SuN = add64(SuN, t1n);
-                  SvN = fma(vq1, t0n, SvN);
-                  SuvN = fma(vq1, t1n, SuvN);
-                  SD = add64(SD, t0d);
-                  SuD = add64(SuD, t1d);
-                  SvD = fma(vq1, t0d, SvD);
-                  SuvD = fma(vq1, t1d, SuvD);
-                }
+#pragma unroll
+              for (int r = 0; r < T1_RPT; ++r)
+                if (j == 0)
+                  {
+                    SN[r] = t0n[r];
+                    SuN[r] = t1n[r];
+                    SvN[r] = vq * t0n[r];
+                    SuvN[r] = vq * t1n[r];
+                    SD[r] = t0d[r];
+                    SuD[r] = t1d[r];
+                    SvD[r] = vq * t0d[r];
+                    SuvD[r] = vq * t1d[r];
+                  }
+                else
+                  {
+                    SN[r] += t0n[r];
+                    SuN[r] += t1n[r];
+                    SvN[r] = fma(vq, t0n[r], SvN[r]);
+                    SuvN[r] = fma(vq, t1n[r], SuvN[r]);
+                    SD[r] += t0d[r];
+                    SuD[r] += t1d[r];
+                    SvD[r] = fma(vq, t0d[r], SvD[r]);
+                    SuvD[r] = fma(vq, t1d[r], SuvD[r]);
+                  }
             }
-          // swap with the other thread of the row: h = 0 keeps Neumann, h = 1 keeps Dirichlet
-          const double o0 = __shfl_xor_sync(0xffffffffu, h ? SN : SD, 1);
-          const double o1 = __shfl_xor_sync(0xffffffffu, h ? SuN : SuD, 1);
-          const double o2 = __shfl_xor_sync(0xffffffffu, h ? SvN : SvD, 1);
-          const double o3 = __shfl_xor_sync(0xffffffffu, h ? SuvN : SuvD, 1);
-          const double m0 = add64(h ? SD : SN, o0), m1 = add64(h ? SuD : SuN, o1), m2 = add64(h ? SvD : SvN, o2),
-                       m3 = add64(h ? SuvD : SuvN, o3);
-          // moments -> the four Q1 shape-function sums
-          const double v3 = m3, v1 = sub64(m1, m3), v2 = sub64(m2, m3), v0 = sub64(sub64(m0, m1), v2);
-          if (!((smask >> k) & 1ull))
+          // moments -> the four Q1 shape-function sums, added to the cell's four column slots
+          double2 *const pa = accT + (sl & 0xff) * T1_STRIDE, *const pb = accT + ((sl >> 8) & 0xff) * T1_STRIDE,
+                        *const pc = accT + ((sl >> 16) & 0xff) * T1_STRIDE, *const pd = accT + (sl >> 24) * T1_STRIDE;
+#pragma unroll
+          for (int r = 0; r < T1_RPT; ++r)
             {
-              row_sum = add64(row_sum, m0); // sum_j phi_j = 1: the row sum of the cell's four entries is its S moment
-              *pa = add64(oa, v0);
-              *pb = add64(ob, v1);
-              *pc = add64(oc, v2);
-              *pd = add64(od, v3);
+              if ((smask[r] >> k) & 1ull) continue; // singular pair: k_assemble_singular integrates it
+              const double n3 = SuvN[r], n1 = SuN[r] - n3, n2 = SvN[r] - n3, n0 = (SN[r] - SuN[r]) - n2;
+              const double d3 = SuvD[r], d1 = SuD[r] - d3, d2 = SvD[r] - d3, d0 = (SD[r] - SuD[r]) - d2;
+              row_sum[r] += SN[r];
+              double2 v;
+              v = pa[r * T1_THREADS];
+              v.x += n0;
+              v.y += d0;
+              pa[r * T1_THREADS] = v;
+              v = pb[r * T1_THREADS];
+              v.x += n1;
+              v.y += d1;
+              pb[r * T1_THREADS] = v;
+              v = pc[r * T1_THREADS];
+              v.x += n2;
+              v.y += d2;
+              pc[r * T1_THREADS] = v;
+              v = pd[r * T1_THREADS];
+              v.x += n3;
+              v.y += d3;
+              pd[r * T1_THREADS] = v;
             }
         }
       if (c + 2 < nchunk)
-        { // this warp is done with the buffer; the last of the CTA's warps refills it
-          // every thread releases its reads on the "empty" barrier; the shared counter only
-          // elects the warp that arrived last -- its wait on the completed phase returns at
-          // once and acquires all the releases
+        {
           mbar_arrive(&bar[2 + (c & 1)]);
           __syncwarp();
           if ((tid & 31) == 0)
             {
-              if (atomicAdd(&s_cnt[c & 1], 1u) == TILE_WARPS - 1)
+              if (atomicAdd(&s_cnt[c & 1], 1u) == T1_WARPS - 1)
                 {
                   s_cnt[c & 1] = 0;
                   mbar_wait(&bar[2 + (c & 1)], (c >> 1) & 1);
-                  // generic-proxy reads of the buffer are ordered before the async-proxy refill
                   asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
                   issue_chunk(c + 2);
                 }
             }
         }
     }
-  if (h == 0 && lrow < a.nloc) a.alpha_part[(size_t)cluster * a.nloc + lrow] = row_sum;
-  __syncwarp(); // a warp flushes exactly the 16 rows its own lanes accumulated
-
-  // flush: warp w owns rows [16w, 16w+16) of the tile; lanes run over the cluster's column
-  // slots (STORE slots first: one coalesced row segment), 8 rows per lane in flight.
-  const int warp = tid >> 5, lane = tid & 31;
-  const uint32_t row_w = lrow_base + warp * 16;
-  if (row_w >= a.nloc) return;
-  const int nrw = min(16, (int)(a.nloc - row_w));
-  for (int s = lane; s < nslot; s += 32)
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
     {
-      const uint32_t cc = s_col[s];
-      const uint32_t is_add = cc >> 31, is_store = is_add ^ 1u;
-      double *gN = a.Nm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
-      double *gD = a.Dm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
-      const double *an = acc + s * ACC_STRIDE + warp * 16;
-      if (nrw == 16)
+      const uint32_t lrow = lrow_base + r * T1_THREADS + tid;
+      if (lrow < a.nloc) a.alpha_part[(size_t)cluster * a.nloc + lrow] = row_sum[r];
+    }
+  __syncwarp(); // a warp flushes exactly the rows its own lanes accumulated
+#ifdef WBEM_EXP_NOFLUSH
+  if (a.ld != 1) return;
+#endif
+
+  // flush: warp w owns rows r * T1_THREADS + [32 w, 32 w + 32) of the tile; lanes run over the
+  // cluster's column slots (STORE slots first: one coalesced row segment per row)
+  const int warp = tid >> 5, lane = tid & 31;
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    {
+      const uint32_t row_w = lrow_base + r * T1_THREADS + warp * 32;
+      if (row_w >= a.nloc) continue;
+      const int nrw = min(32, (int)(a.nloc - row_w));
+      for (int s = lane; s < nslot; s += 32)
         {
-#pragma unroll
-          for (int rb = 0; rb < 16; rb += 8)
+          const uint32_t cc = s_col[s];
+          const uint32_t is_add = cc >> 31, is_store = is_add ^ 1u;
+          double *gN = a.Nm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
+          double *gD = a.Dm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
+          const double2 *an = acc + s * T1_STRIDE + r * T1_THREADS + warp * 32;
+          if (nrw == 32)
             {
-              double vn[8], vd[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
+              for (int rb = 0; rb < 32; rb += 8)
                 {
-                  vn[i] = an[rb + i];
-                  vd[i] = an[ACC_MATOFF + rb + i];
-                }
+                  double2 v[8];
 #pragma unroll
-              for (int i = 0; i < 8; ++i)
-                {
-                  flush_value(gN, vn[i], is_add, is_store);
-                  flush_value(gD, vd[i], is_add, is_store);
-                  gN += a.ld;
-                  gD += a.ld;
+                  for (int i = 0; i < 8; ++i) v[i] = an[rb + i];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    {
+                      flush_value(gN, v[i].x, is_add, is_store);
+                      flush_value(gD, v[i].y, is_add, is_store);
+                      gN += a.ld;
+                      gD += a.ld;
+                    }
                 }
             }
+          else
+            for (int i = 0; i < nrw; ++i)
+              {
+                const double2 v = an[i];
+                flush_value(gN, v.x, is_add, is_store);
+                flush_value(gD, v.y, is_add, is_store);
+                gN += a.ld;
+                gD += a.ld;
+              }
         }
-      else
-        for (int i = 0; i < nrw; ++i)
-          {
-            flush_value(gN, an[i], is_add, is_store);
-            flush_value(gD, an[ACC_MATOFF + i], is_add, is_store);
-            gN += a.ld;
-            gD += a.ld;
-          }
     }
 }
 
@@ -539,7 +556,7 @@ __global__ void __launch_bounds__(SIMPLE_ROWS)
                     const uint32_t *__restrict__ sing_cellpos, double *Nm, double *Dm, uint32_t ld,
                     uint32_t row0, uint32_t nloc)
 {
-  extern __shared__ __align__(16) double sgeo[]; // [TC][7][nq]
+  extern __shared__ __align__(16) double sgeo[]; // [TC][GEO_REC][nq]
   __shared__ uint32_t scol[SIMPLE_TC][4];
   const int tid = threadIdx.x;
   const uint32_t lrow = blockIdx.x * SIMPLE_ROWS + tid;
@@ -558,7 +575,7 @@ __global__ void __launch_bounds__(SIMPLE_ROWS)
     {
       const int nc = min((uint32_t)SIMPLE_TC, c_end - cb);
       __syncthreads();
-      for (int i = tid; i < nc * 7 * nq; i += SIMPLE_ROWS) sgeo[i] = geo[(size_t)cb * 7 * nq + i];
+      for (int i = tid; i < nc * GEO_REC * nq; i += SIMPLE_ROWS) sgeo[i] = geo[(size_t)cb * GEO_REC * nq + i];
       if (tid < nc * 4) scol[tid / 4][tid % 4] = colpos[cell_dofs[4 * (size_t)cb + tid]];
       __syncthreads();
       for (int k = 0; k < nc; ++k)
@@ -570,7 +587,7 @@ __global__ void __launch_bounds__(SIMPLE_ROWS)
               next_sing = sp < se ? sing_cellpos[sp] : 0xffffffffu;
               continue;
             }
-          const double *g = sgeo + k * 7 * nq;
+          const double *g = sgeo + k * GEO_REC * nq;
           double ln[4] = {0, 0, 0, 0}, ldd[4] = {0, 0, 0, 0};
           for (int q = 0; q < nq; ++q)
             {
@@ -742,9 +759,8 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       const AssemblyPlan &pl = ctx->plan;
       if (!ctx->tiled_attr_set)
         { // per device: a second context on another GPU needs its own opt-in
-          CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_tiled,
-                                            cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                            (int)tiled_smem_bytes()));
+          CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)rows_smem_bytes()));
           ctx->tiled_attr_set = true;
         }
       // columns no cell touches (none on deal.II meshes) stay zero
@@ -760,10 +776,8 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       a.xyz = ctx->d_xyz;
       a.geo = ctx->d_cellgeo;
       a.cell_slots = ctx->d_cell_slots;
-      a.cl_cell_ptr = ctx->d_cl_cell_ptr;
-      a.cl_slot_ptr = ctx->d_cl_slot_ptr;
+      a.desc = (const CtaDesc *)ctx->d_cta_desc;
       a.slot_col = ctx->d_slot_col;
-      a.color_clusters = ctx->d_color_clusters;
       a.sing_ptr = ctx->d_sing_ptr;
       a.sing_cellpos = ctx->d_sing_cellpos;
       a.tile_sing = ctx->d_tile_sing;
@@ -775,14 +789,15 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       a.row0 = ctx->row0;
       a.nloc = ctx->nloc;
       for (int i = 0; i < 4; ++i) a.g1_x[i] = ctx->qt.g1_x[i];
-      const uint32_t row_tiles = (ctx->nloc + TILE_ROWS - 1) / TILE_ROWS;
+      const uint32_t tile_rows = T1_ROWS;
+      const uint32_t row_tiles = (ctx->nloc + tile_rows - 1) / tile_rows;
       for (uint32_t c = 0; c < pl.n_colors; ++c)
         {
           const uint32_t nclu = pl.color_ptr[c + 1] - pl.color_ptr[c];
           if (nclu == 0) continue;
           a.cluster_base = pl.color_ptr[c];
           dim3 grid(nclu, row_tiles);
-          k_assemble_tiled<<<grid, TILE_BLOCK, tiled_smem_bytes(), st>>>(a);
+          k_assemble_rows<<<grid, T1_THREADS, rows_smem_bytes(), st>>>(a);
           ctx->launches++;
         }
       CUDA_OK(ctx, cudaGetLastError());
@@ -798,7 +813,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
       per = ((per + SIMPLE_TC - 1) / SIMPLE_TC) * SIMPLE_TC;
       chunks = (ctx->C + per - 1) / per;
       dim3 grid(row_blocks, chunks);
-      const size_t sm = sizeof(double) * SIMPLE_TC * 7 * nq;
+      const size_t sm = sizeof(double) * SIMPLE_TC * GEO_REC * nq;
       k_assemble_simple<<<grid, SIMPLE_ROWS, sm, st>>>((const DevTables *)ctx->d_tables, nq, ctx->C, per, ctx->d_xyz, ctx->d_cellgeo,
                                                        ctx->d_cell_dofs, ctx->d_colpos,
                                                        ctx->d_sing_ptr, ctx->d_sing_cellpos,
@@ -867,3 +882,7 @@ extern "C" int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out,
   cudaFree(d_out);
   return 0;
 }
+
+// tile geometry of the regular-pair kernel, for the host-side maps built in wbem_set_topology
+uint32_t wbem_tile_rows(void) { return T1_ROWS; }
+uint32_t wbem_tile_width(void) { return T1_W; }

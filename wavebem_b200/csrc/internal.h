@@ -11,10 +11,6 @@
 #define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
 #define WBEM_MAX_PEERS 16
 #define WBEM_GMRES_KMAX 1024 // largest gmres_n_tmp_vectors
-#ifndef WBEM_TILE_W
-#define WBEM_TILE_W 56      // column slots (dofs) per cell cluster
-#endif
-#define WBEM_TILE_ROWS 64 // rows per CTA of the tiled regular-pair kernel
 
 struct QuadTables
 { // host copies of the reference-cell tables (uploaded to __constant__ memory)
@@ -148,8 +144,8 @@ struct wbem_ctx
   uint8_t *d_tile_sing = nullptr; // [row tiles][clusters]
   uint32_t n_sing = 0;
   // plan on device
-  uint32_t *d_cl_cell_ptr = nullptr, *d_cl_slot_ptr = nullptr, *d_slot_col = nullptr,
-           *d_color_clusters = nullptr;
+  uint32_t *d_slot_col = nullptr;
+  uint32_t *d_cta_desc = nullptr; // [clusters][4] in launch order: first cell, first slot, counts, cluster id
   uint8_t *d_cell_slots = nullptr;
 
   // geometry
@@ -248,6 +244,8 @@ int wbem_launch_geometry(wbem_ctx *ctx);
 int wbem_upload_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW);
 int wbem_launch_assemble(wbem_ctx *ctx);
 int wbem_launch_alpha(wbem_ctx *ctx, bool from_matrix = false);
+uint32_t wbem_tile_rows(void);
+uint32_t wbem_tile_width(void);
 // operator.cu
 int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double *d_src,
                         double *d_dst, bool constrained);
