@@ -29,7 +29,7 @@ if [ "$MODE" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/summary.log
   echo "== ncu full: assembly + gemv" | tee -a $OUT/summary.log
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_assemble_tiled -s 5 -c 5 -f -o $OUT/prof_assemble \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_assemble_rows -s 5 -c 5 -f -o $OUT/prof_assemble \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_asm.log 2>&1; echo "ncu asm rc=$?" | tee -a $OUT/summary.log
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bem_gemv -s 4 -c 2 -f -o $OUT/prof_gemv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_gemv.log 2>&1; echo "ncu gemv rc=$?" | tee -a $OUT/summary.log

@@ -12,7 +12,9 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "gpurun_out")
 PROF = os.path.join(ROOT, "profiles")
-tag = sys.argv[1] if len(sys.argv) > 1 else "r1"
+tag = sys.argv[1] if len(sys.argv) > 1 else "r2"
+sys.path.insert(0, ROOT)
+from bench import kernel_source_hash  # noqa: E402  (the hash bench.py checks before quoting these numbers)
 os.makedirs(PROF, exist_ok=True)
 
 KEYS = [
@@ -94,13 +96,15 @@ launch_list()
 t = summarize(os.path.join(OUT, "prof_gemv.ncu-rep"), "gemv")
 if t:
     json.dump({"bytes_per_launch": sum(t) / len(t), "launches_captured": len(t),
+               "kernel_source_sha1_16": kernel_source_hash(),
                "source": "dram__bytes_read.sum + dram__bytes_write.sum, ncu --set full"},
               open(os.path.join(PROF, "gemv_dram_bytes_per_launch.json"), "w"))
 t = summarize(os.path.join(OUT, "prof_assemble.ncu-rep"), "assemble")
 if t:
     # the capture holds the launches (one per colour) of ONE assembly: the step's traffic is their sum
     json.dump({"bytes_per_step": sum(t), "launches_captured": len(t),
-               "source": "sum over the k_assemble_tiled launches of one assembly of dram__bytes_read.sum + "
+               "kernel_source_sha1_16": kernel_source_hash(),
+               "source": "sum over the k_assemble_rows launches of one assembly of dram__bytes_read.sum + "
                          "dram__bytes_write.sum, ncu --set full"},
               open(os.path.join(PROF, "assemble_dram_bytes_per_step.json"), "w"))
 for f in ("bench.json", "gpu_info.csv"):

@@ -361,11 +361,7 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
   __syncthreads();
 
   const double u0 = a.g1_x[0], u1 = a.g1_x[1], u2 = a.g1_x[2], u3 = a.g1_x[3];
-#ifdef WBEM_EXP_NOLOOP
-  for (int c = 0; c < (a.ld == 1 ? nchunk : 0); ++c)
-#else
   for (int c = 0; c < nchunk; ++c)
-#endif
     {
       mbar_wait(&bar[c & 1], (c >> 1) & 1);
       const double *gc = geo + (c & 1) * T1_CHUNK * T1_REC;
@@ -491,9 +487,6 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
       if (lrow < a.nloc) a.alpha_part[(size_t)cluster * a.nloc + lrow] = row_sum[r];
     }
   __syncwarp(); // a warp flushes exactly the rows its own lanes accumulated
-#ifdef WBEM_EXP_NOFLUSH
-  if (a.ld != 1) return;
-#endif
 
   // flush: warp w owns rows r * T1_THREADS + [32 w, 32 w + 32) of the tile; lanes run over the
   // cluster's column slots (STORE slots first: one coalesced row segment per row)
