@@ -215,6 +215,20 @@ int wbem_solve_system_dev(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn,
 /* BEMProblem<3>::residual (source/bem_problem.cc:903-961). */
 int wbem_residual(wbem_ctx *ctx, double *res, const double *phi, const double *dphi_dn);
 
+/* Post-processing integrals that share the assembly's integrand (they read the geometry of the last
+ * wbem_set_geometry, no matrix; quad_order = 4 only).
+ * FreeSurface<3>::compute_internal_velocities (source/free_surface.cc:10426-10537): grad phi at
+ * n_points field points x[n_points][3] from the boundary traces (the reference reads the points from
+ * points.txt and writes velocities.txt): velocities[n_points][3]. */
+int wbem_internal_velocities(wbem_ctx *ctx, const double *phi, const double *dphi_dn, uint32_t n_points,
+                             const double *points, double *velocities);
+/* The hull integrals of FreeSurface<3>::compute_pressure (source/free_surface.cc:9534-9598), steady
+ * terms, over the cells with cell_marked[c] != 0 (the reference: material_id == wall_sur_ID1..3):
+ * out11 = press_force_test_1[3], press_force_test_2[3], press_moment[3] about baricenter (NULL = origin),
+ * marked area, integral of phi over the marked cells.  vinf[3] = the wind. */
+int wbem_pressure_force(wbem_ctx *ctx, const double *phi, const double *dphi_dn, const uint8_t *cell_marked,
+                        const double *vinf, double rho, double g, const double *baricenter, double *out11);
+
 /* system_rhs / sol of the last solve_system (public members, include/bem_problem.h:155-158) */
 int wbem_get_system_rhs(wbem_ctx *ctx, double *out);
 int wbem_get_sol(wbem_ctx *ctx, double *out);

@@ -10,7 +10,7 @@ import pytest
 
 from conftest import make_problem, rel_err_rowscaled
 from wavebem_b200 import meshgen
-from wavebem_b200.postproc import hull_pressure_force
+from oracle.postproc import hull_pressure_force
 
 pytestmark = pytest.mark.gpu
 

@@ -413,3 +413,41 @@ def test_regular_rule_on_a_warped_cell_against_adaptive_quadrature(orc):
                 d, _ = integrate.dblquad(f, 0, 1, 0, 1, args=(j, 0, i), epsabs=1e-14, epsrel=1e-12)
                 nn, _ = integrate.dblquad(f, 0, 1, 0, 1, args=(j, 1, i), epsabs=1e-14, epsrel=1e-12)
                 assert abs(od[i, j] / d - 1) < 5e-7 and abs(on[i, j] / nn - 1) < 5e-6
+
+
+# ---------------------------------------------------------------------------------------------
+# post-processing integrals (oracle/postproc.py, the checkers of csrc/postproc.cu)
+# ---------------------------------------------------------------------------------------------
+def test_internal_velocities_are_the_gradient_of_the_representation_formula():
+    """compute_internal_velocities (free_surface.cc:10426-10537) differentiates G and dG/dn with Sacado;
+    the restatement writes the gradients out: check them against central differences of the potential."""
+    from oracle import postproc
+    from wavebem_b200 import meshgen
+    m = meshgen.cube(3)
+    rng = np.random.default_rng(3)
+    phi, dphi = rng.normal(size=m.n_nodes), rng.normal(size=m.n_nodes)
+    pts = np.array([[0.6, 0.45, 0.7], [0.2, 0.75, 0.4]])      # inside the unit cube
+    v = postproc.internal_velocities(m, phi, dphi, pts)
+    h = 1e-5
+    fd = np.zeros_like(v)
+    for d in range(3):
+        e = np.zeros(3)
+        e[d] = h
+        fd[:, d] = (postproc.potential_at(m, phi, dphi, pts + e) - postproc.potential_at(m, phi, dphi, pts - e)) / (2 * h)
+    assert np.abs(v - fd).max() < 1e-8 * max(1.0, np.abs(v).max())
+
+
+def test_internal_velocity_of_a_linear_potential_inside_a_cube():
+    """phi = x is harmonic: Green's representation returns phi and grad phi = (1,0,0) at interior points
+    (outward normals; exact up to the quadrature of the 1/r kernels over the flat faces)."""
+    from oracle import postproc
+    from wavebem_b200 import meshgen
+    m = meshgen.cube(8)
+    nn = meshgen.cell_normals_at_nodes(m)     # face normals (double nodes on the edges keep them per face)
+    phi = m.xyz[:, 0].copy()
+    dphi = nn[:, 0].copy()
+    pts = np.array([[0.0, 0.0, 0.0], [0.1, -0.15, 0.05]]) + m.xyz.mean(axis=0)
+    v = postproc.internal_velocities(m, phi, dphi, pts)
+    p = postproc.potential_at(m, phi, dphi, pts)
+    assert np.abs(v - np.array([1.0, 0.0, 0.0])).max() < 2e-3
+    assert np.abs(p - pts[:, 0]).max() < 2e-3

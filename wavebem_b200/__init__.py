@@ -11,7 +11,8 @@ include/wbem.h).  This package is the thin host side used by the tests and the b
                  residual -- same names, argument meaning and error behaviour (a GMRES that
                  hits `Max steps` raises NoConvergence, like deal.II's SolverControl);
 * `meshgen`      synthetic tank/Wigley/cube/sphere meshes (the reference needs OpenCASCADE);
-* `constraints`  host restatement of compute_constraints (bem_problem.cc:990-1105).
+* `constraints`  host restatement of compute_constraints (bem_problem.cc:990-1105), used by callers
+                 that hand their own ConstraintMatrix lines over (the library has its own, csrc/constraints.cu).
 """
 from __future__ import annotations
 
@@ -81,7 +82,7 @@ ABI_SYMBOLS = [
     "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
     "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",
     "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations", "wbem_gmres",
-    "wbem_set_fevalues", "wbem_generate_double_nodes_set",
+    "wbem_set_fevalues", "wbem_generate_double_nodes_set", "wbem_internal_velocities", "wbem_pressure_force",
 ]
 
 
@@ -346,6 +347,22 @@ class Context:
         res = np.empty(self.n)
         self._chk(lib().wbem_residual(self._h, _dp(res), _dp(phi), _dp(dphi_dn)))
         return res
+
+    def internal_velocities(self, phi, dphi_dn, points):
+        """FreeSurface<3>::compute_internal_velocities (free_surface.cc:10426-10537) on the device."""
+        pts = _f64(points).reshape(-1, 3)
+        out = np.empty_like(pts)
+        self._chk(lib().wbem_internal_velocities(self._h, _dp(_f64(phi)), _dp(_f64(dphi_dn)), C.c_uint32(len(pts)),
+                                                 _dp(pts), _dp(out)))
+        return out
+
+    def pressure_force(self, phi, dphi_dn, cell_marked, vinf, rho=1025.1, g=9.81, baricenter=(0.0, 0.0, 0.0)):
+        """The hull integrals of compute_pressure (free_surface.cc:9534-9598): 11 numbers, see wbem.h."""
+        out = np.empty(11)
+        mk = np.ascontiguousarray(cell_marked, dtype=np.uint8)
+        self._chk(lib().wbem_pressure_force(self._h, _dp(_f64(phi)), _dp(_f64(dphi_dn)), _dp(mk), _dp(_f64(vinf)),
+                                            C.c_double(rho), C.c_double(g), _dp(_f64(baricenter)), _dp(out)))
+        return out
 
     def get_system_rhs(self):
         a = np.empty(self.n)

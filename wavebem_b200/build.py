@@ -10,7 +10,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OUT = os.path.join(HERE, "lib")
 LIB = os.path.join(OUT, "libwbem.so")
-SOURCES = ["api.cu", "assemble.cu", "operator.cu", "gmres.cu", "precond.cu", "spai.cu", "constraints.cu", "plan.cpp",
+SOURCES = ["api.cu", "assemble.cu", "operator.cu", "gmres.cu", "precond.cu", "spai.cu", "constraints.cu", "postproc.cu", "plan.cpp",
            "quadrature.cpp", "comm.cpp", "domain.cpp", "group.cpp"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
