@@ -174,6 +174,10 @@ int wbem_vmult(wbem_ctx *ctx, double *dst, const double *src);
 /* ConstrainedOperator::vmult / distribute_rhs (include/constrained_matrix.h:73-94). */
 int wbem_constrained_vmult(wbem_ctx *ctx, double *dst, const double *src);
 int wbem_distribute_rhs(wbem_ctx *ctx, double *rhs);
+/* ConstrainedOperator::vmult on nvec <= 8 vectors (dst, src: [nvec][N]) with ONE pass over the matrices:
+ * the block mat-vec wbem_solve_system_multi is built on. */
+int wbem_constrained_vmult_multi(wbem_ctx *ctx, int nvec, double *dst, const double *src);
+int wbem_compute_rhs_multi(wbem_ctx *ctx, int nvec, double *dst, const double *src); /* compute_rhs, same way */
 /* BEMProblem<3>::compute_rhs (source/bem_problem.cc:673-707). */
 int wbem_compute_rhs(wbem_ctx *ctx, double *dst, const double *src);
 /* BEMProblem<3>::assemble_preconditioner (source/bem_problem.cc:1107-1149). */
@@ -198,6 +202,15 @@ int wbem_spai_pattern_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *c
  * Returns 1 when GMRES hits max_steps (SolverControl::NoConvergence). */
 int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double *tmp_rhs,
                       int *iters, double *last_res);
+/* nrhs calls of solve_system on the SAME matrices in one: FreeSurface::jacobian runs one inner GMRES per
+ * Jacobian-vector product (source/free_surface.cc:4918-4993, source/dae_time_integrator.cc:375-377) with only
+ * tmp_rhs changing.  phi / dphi_dn / tmp_rhs are [nrhs][N] row-major, iters / last_res [nrhs] (may be NULL).
+ * Every system is the same left-preconditioned GMRES with its own Krylov space and stopping test; up to 8
+ * of them share each pass over the matrices (block mat-vec), so the bytes streamed per solve drop by up to
+ * 8x.  With auto_constraints = 1 the constraint inhomogeneities follow each system's tmp_rhs; with
+ * caller-installed lines (wbem_set_constraints) all systems share them.  Returns 1 if any system hit max_steps. */
+int wbem_solve_system_multi(wbem_ctx *ctx, int nrhs, double *phi, double *dphi_dn, const double *tmp_rhs,
+                            int *iters, double *last_res);
 /* solver.solve(cc, sol, system_rhs, preconditioner) alone (source/bem_problem.cc:853): GMRES on the
  * constrained operator for a right-hand side the caller prepared (compute_rhs + distribute_rhs),
  * x0 = 0, with the preconditioner wbem_params selects.  Same return convention as solve_system. */

@@ -83,6 +83,7 @@ ABI_SYMBOLS = [
     "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",
     "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations", "wbem_gmres",
     "wbem_set_fevalues", "wbem_generate_double_nodes_set", "wbem_internal_velocities", "wbem_pressure_force",
+    "wbem_solve_system_multi", "wbem_constrained_vmult_multi", "wbem_compute_rhs_multi",
 ]
 
 
@@ -245,6 +246,15 @@ class Context:
     def constrained_vmult(self, src):
         return self._apply(lib().wbem_constrained_vmult, src)
 
+    def constrained_vmult_multi(self, src, fn="wbem_constrained_vmult_multi"):
+        src = _f64(src).reshape(-1, self.n)
+        dst = np.empty_like(src)
+        self._chk(getattr(lib(), fn)(self._h, C.c_int(src.shape[0]), _dp(dst), _dp(src)))
+        return dst
+
+    def compute_rhs_multi(self, src):
+        return self.constrained_vmult_multi(src, "wbem_compute_rhs_multi")
+
     def compute_rhs(self, src):
         return self._apply(lib().wbem_compute_rhs, src)
 
@@ -331,6 +341,23 @@ class Context:
         if rc > 0 and raise_on_no_convergence:
             raise NoConvergence(it.value, res.value)
         return phi, dphi_dn, it.value, res.value
+
+    def solve_system_multi(self, phi, dphi_dn, tmp_rhs, raise_on_no_convergence=True):
+        """nrhs solve_system calls on the same matrices (the J.v pattern) sharing each pass over them.
+        tmp_rhs: (nrhs, N); phi / dphi_dn: (N,) broadcast or (nrhs, N).  Returns phi, dphi_dn, iters, residuals."""
+        tmp_rhs = _f64(tmp_rhs).reshape(-1, self.n)
+        nrhs = tmp_rhs.shape[0]
+        # order="C": the default order="K" would copy a broadcast view into an interleaved layout
+        phi = np.array(np.broadcast_to(_f64(phi), (nrhs, self.n)), dtype=np.float64, order="C")
+        dphi_dn = np.array(np.broadcast_to(_f64(dphi_dn), (nrhs, self.n)), dtype=np.float64, order="C")
+        it = np.zeros(nrhs, dtype=np.int32)
+        res = np.zeros(nrhs)
+        rc = self._chk(lib().wbem_solve_system_multi(self._h, C.c_int(nrhs), _dp(phi), _dp(dphi_dn), _dp(tmp_rhs),
+                                                     _dp(it), _dp(res)), allow_positive=True)
+        if rc > 0 and raise_on_no_convergence:
+            k = int(np.argmax(res))
+            raise NoConvergence(int(it[k]), float(res[k]))
+        return phi, dphi_dn, it, res
 
     def solve(self, xyz, phi, dphi_dn, tmp_rhs, raise_on_no_convergence=True):
         xyz = _f64(xyz)

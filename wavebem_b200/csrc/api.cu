@@ -249,6 +249,8 @@ static void free_topology(wbem_ctx *ctx)
 {
   wbem_p2p_close(ctx);
   FREE_DEV(ctx->d_p2p);
+  FREE_DEV(ctx->d_ymulti);
+  wbem_multi_free(ctx);
   FREE_DEV(ctx->d_done_counter);
   FREE_DEV(ctx->d_gather_timeout);
   FREE_DEV(ctx->d_cell_dofs);
@@ -483,7 +485,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_alloc(ctx, &ctx->d_yloc, (size_t)ctx->chunk * P + 64))) return rc;
   if (P > 1)
     {
-      const size_t nd = 2 * (size_t)ctx->chunk * P + WBEM_MAX_PEERS;
+      const size_t nd = 2 * (size_t)WBEM_MULTI_MAX * ctx->chunk * P + WBEM_MAX_PEERS;
       if ((rc = dev_alloc(ctx, &ctx->d_p2p, nd))) return rc;
       if ((rc = dev_alloc(ctx, &ctx->d_done_counter, 1))) return rc;
       if ((rc = dev_alloc(ctx, &ctx->d_gather_timeout, 1))) return rc;
@@ -929,6 +931,75 @@ int wbem_solve_system(wbem_ctx *ctx, double *phi, double *dphi_dn, const double 
       CUDA_OK(ctx, cudaMemcpyAsync(dphi_dn, d_dphi, nb, cudaMemcpyDeviceToHost, st));
     }
   CUDA_OK(ctx, cudaStreamSynchronize(st));
+  return rc;
+}
+
+static int block_apply(wbem_ctx *ctx, int mode, bool constrained, int nvec, double *dst, const double *src);
+int wbem_constrained_vmult_multi(wbem_ctx *ctx, int nvec, double *dst, const double *src)
+{
+  CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_constrained_vmult_multi(s, nvec, dst, src));
+  return block_apply(ctx, 0, true, nvec, dst, src);
+}
+int wbem_compute_rhs_multi(wbem_ctx *ctx, int nvec, double *dst, const double *src)
+{
+  CHECK_CTX(ctx);
+  GROUP_FORWARD(ctx, wbem_compute_rhs_multi(s, nvec, dst, src));
+  return block_apply(ctx, 1, false, nvec, dst, src);
+}
+static int block_apply(wbem_ctx *ctx, int mode, bool constrained, int nvec, double *dst, const double *src)
+{
+  if (nvec < 1 || nvec > WBEM_MULTI_MAX || !dst || !src) WBEM_FAIL(ctx, -1, "block mat-vec takes 1..%d vectors", WBEM_MULTI_MAX);
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  int rc = ensure_alpha(ctx);
+  if (rc) return rc;
+  cudaStream_t st = ctx->stream;
+  const size_t nd = (size_t)nvec * ctx->N;
+  double *d = nullptr;
+  CUDA_OK(ctx, cudaMalloc((void **)&d, 2 * sizeof(double) * nd));
+  const double *ps[WBEM_MULTI_MAX];
+  double *pd[WBEM_MULTI_MAX];
+  for (int b = 0; b < nvec; ++b)
+    {
+      ps[b] = d + (size_t)b * ctx->N;
+      pd[b] = d + nd + (size_t)b * ctx->N;
+    }
+  cudaError_t e = cudaMemcpyAsync(d, src, sizeof(double) * nd, cudaMemcpyHostToDevice, st);
+  rc = e == cudaSuccess ? wbem_apply_operator_multi(ctx, mode, nvec, ps, pd, constrained) : -2;
+  if (rc == 0 && wbem_is_root(ctx)) e = cudaMemcpyAsync(dst, d + nd, sizeof(double) * nd, cudaMemcpyDeviceToHost, st);
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) WBEM_FAIL(ctx, -2, "CUDA error %s in wbem_constrained_vmult_multi", cudaGetErrorString(e));
+  return rc ? rc : wbem_check_gather_timeout(ctx);
+}
+
+int wbem_solve_system_multi(wbem_ctx *ctx, int nrhs, double *phi, double *dphi_dn, const double *tmp_rhs, int *iters,
+                            double *last_res)
+{
+  CHECK_CTX(ctx);
+  if (!ctx->N) WBEM_FAIL(ctx, -3, "solve_system_multi before wbem_set_topology");
+  if (nrhs < 0 || (nrhs && (!phi || !dphi_dn || !tmp_rhs))) WBEM_FAIL(ctx, -1, "bad argument");
+  if (nrhs == 0) return 0;
+  GROUP_FORWARD(ctx, wbem_solve_system_multi(s, nrhs, phi, dphi_dn, tmp_rhs, wbem_is_root(s) ? iters : nullptr,
+                                             wbem_is_root(s) ? last_res : nullptr));
+  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
+  cudaStream_t st = ctx->stream;
+  const size_t nd = (size_t)nrhs * ctx->N, nbytes = sizeof(double) * nd;
+  double *d = nullptr;
+  CUDA_OK(ctx, cudaMalloc((void **)&d, 3 * nbytes));
+  double *d_phi = d, *d_dphi = d + nd, *d_bc = d + 2 * nd;
+  cudaError_t e = cudaMemcpyAsync(d_phi, phi, nbytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_dphi, dphi_dn, nbytes, cudaMemcpyHostToDevice, st);
+  if (e == cudaSuccess) e = cudaMemcpyAsync(d_bc, tmp_rhs, nbytes, cudaMemcpyHostToDevice, st);
+  int rc = e == cudaSuccess ? wbem_solve_system_multi_device(ctx, nrhs, d_phi, d_dphi, d_bc, iters, last_res) : -2;
+  if (rc >= 0 && wbem_is_root(ctx))
+    {
+      e = cudaMemcpyAsync(phi, d_phi, nbytes, cudaMemcpyDeviceToHost, st);
+      if (e == cudaSuccess) e = cudaMemcpyAsync(dphi_dn, d_dphi, nbytes, cudaMemcpyDeviceToHost, st);
+    }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+  cudaFree(d);
+  if (e != cudaSuccess) WBEM_FAIL(ctx, -2, "CUDA error %s in wbem_solve_system_multi", cudaGetErrorString(e));
   return rc;
 }
 

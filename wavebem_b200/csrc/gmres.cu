@@ -8,6 +8,7 @@
 // scalars, fetched with one small D2H copy per iteration.  Orthogonalisation is classical
 // Gram-Schmidt applied twice (CGS2) -- two batched kernels per pass instead of the 2k vector
 // kernels of deal.II's modified Gram-Schmidt loop; same Arnoldi relation to rounding.
+#include <algorithm>
 #include <cmath>
 #include <cstdio>
 #include <cstring>
@@ -595,4 +596,335 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   if (iters_out) *iters_out = accumulated;
   if (last_res_out) *last_res_out = rho;
   return state == 1 ? 0 : 1;
+}
+
+// ---------------------------------------------------------------------------------------
+// wbem_solve_system_multi: nrhs right-hand sides, ONE pass over the matrices per GMRES iteration.
+//
+// FreeSurface::jacobian (reference source/free_surface.cc:4918-4993) runs one full inner GMRES
+// (bem.solve_system, :4993) per Jacobian-vector product the outer SPGMR asks for
+// (source/dae_time_integrator.cc:375-377), always on the SAME matrices: each of those solves
+// re-streams 8 N^2 bytes per iteration.  Here up to WBEM_MULTI_MAX systems advance in lock step:
+// every system keeps its own Krylov basis, Hessenberg matrix and stopping test (it is the same
+// left-preconditioned GMRES as above, system by system), but the operator is applied to all
+// active systems by ONE block mat-vec (k_bem_gemv_multi).  A system that has converged leaves the
+// block; the others go on.
+// ---------------------------------------------------------------------------------------
+namespace
+{
+struct MultiState
+{
+  MultiWork w = {nullptr, nullptr, nullptr};
+  double *d_V = nullptr;                                // [MAX][ntmp-1][ld]
+  double *d_p = nullptr, *d_x = nullptr, *d_rhs = nullptr; // [MAX][ld]
+  double *d_inhom = nullptr;                            // [MAX][inhom_cap]
+  double *d_small = nullptr;                            // [MAX][small_stride]: y | dot partials | |w|^2 partials | h
+  double *d_norm = nullptr;                             // [MAX]
+  double *h_pin = nullptr;                              // pinned [MAX][pin_stride]
+  size_t small_stride = 0, pin_stride = 0, inhom_cap = 0;
+  uint32_t ld = 0;
+  int ntmp = 0;
+};
+} // namespace
+
+void wbem_multi_free(wbem_ctx *ctx)
+{
+  MultiState *m = reinterpret_cast<MultiState *>(ctx->multi);
+  if (!m) return;
+  for (double *p : {m->w.d_xn, m->w.d_xd, m->w.d_xdiag, m->d_V, m->d_p, m->d_x, m->d_rhs, m->d_inhom, m->d_small, m->d_norm})
+    if (p) cudaFree(p);
+  if (m->h_pin) cudaFreeHost(m->h_pin);
+  delete m;
+  ctx->multi = nullptr;
+}
+
+static MultiState *multi_state(wbem_ctx *ctx)
+{
+  MultiState *m = reinterpret_cast<MultiState *>(ctx->multi);
+  if (m && m->ld == ctx->ld && m->ntmp == ctx->p.gmres_n_tmp_vectors) return m;
+  wbem_multi_free(ctx);
+  m = new MultiState();
+  ctx->multi = m;
+  m->ld = ctx->ld;
+  m->ntmp = ctx->p.gmres_n_tmp_vectors;
+  const size_t ld = ctx->ld, B = WBEM_MULTI_MAX;
+  const size_t nb128 = (ctx->N + 127) / 128;
+  m->small_stride = GM_KMAX + DOT_SEGS * GM_KMAX + nb128 + GM_KMAX + 8;
+  m->pin_stride = nb128 + GM_KMAX + 8;
+  bool ok = true;
+  auto al = [&](double **p, size_t n) { ok = ok && cudaMalloc((void **)p, sizeof(double) * n) == cudaSuccess; };
+  al(&m->w.d_xn, B * ld);
+  al(&m->w.d_xd, B * ld);
+  al(&m->w.d_xdiag, B * ld);
+  al(&m->d_V, B * (size_t)(m->ntmp - 1) * ld);
+  al(&m->d_p, B * ld);
+  al(&m->d_x, B * ld);
+  al(&m->d_rhs, B * ld);
+  al(&m->d_small, B * m->small_stride);
+  al(&m->d_norm, B);
+  ok = ok && cudaMallocHost((void **)&m->h_pin, sizeof(double) * B * m->pin_stride) == cudaSuccess;
+  if (ok)
+    { // padding entries [N, ld) of the multiplier slabs are read by the mat-vec: zero for good
+      cudaMemsetAsync(m->w.d_xn, 0, sizeof(double) * B * ld, ctx->stream);
+      cudaMemsetAsync(m->w.d_xd, 0, sizeof(double) * B * ld, ctx->stream);
+      cudaMemsetAsync(m->w.d_xdiag, 0, sizeof(double) * B * ld, ctx->stream);
+    }
+  if (!ok)
+    {
+      cudaGetLastError();
+      wbem_multi_free(ctx);
+      ctx->err = "wbem_solve_system_multi: out of device memory for the block work vectors";
+      return nullptr;
+    }
+  return m;
+}
+
+MultiWork *wbem_multi_work(wbem_ctx *ctx)
+{
+  MultiState *m = multi_state(ctx);
+  return m ? &m->w : nullptr;
+}
+
+static int solve_group(wbem_ctx *ctx, int nb, double *d_phi, double *d_dphi_dn, const double *d_bc, int *iters_out,
+                       double *res_out, int *rc_out)
+{
+  cudaStream_t st = ctx->stream;
+  const uint32_t N = ctx->N;
+  const unsigned nbk = (N + 255) / 256, nb128 = (N + 127) / 128;
+  MultiState *ms = multi_state(ctx);
+  if (!ms) return -2;
+  const size_t ld = ctx->ld, ldv = ctx->ld;
+  const int ntmp = ctx->p.gmres_n_tmp_vectors, m = ntmp - 2;
+  const double tol = ctx->p.gmres_tol;
+  const int max_steps = ctx->p.gmres_max_steps;
+  int rc;
+  const double *src[WBEM_MULTI_MAX];
+  double *dst[WBEM_MULTI_MAX];
+  // system_rhs of every system (:839): one block application of the rhs operator
+  for (int b = 0; b < nb; ++b)
+    {
+      src[b] = d_bc + (size_t)b * N;
+      dst[b] = ms->d_rhs + b * ld;
+    }
+  if ((rc = wbem_apply_operator_multi(ctx, 1, nb, src, dst, false))) return rc;
+  // constrained rows (:845): the lines are the same for every system, the inhomogeneities follow tmp_rhs
+  bool own_inhom = false;
+  if (ctx->p.auto_constraints)
+    {
+      for (int b = 0; b < nb; ++b)
+        {
+          if ((rc = wbem_compute_constraints_device(ctx, d_bc + (size_t)b * N))) return rc;
+          if (ctx->n_lines > ms->inhom_cap)
+            {
+              if (b != 0) WBEM_FAIL(ctx, -4, "constraint lines changed between the systems of one block");
+              if (ms->d_inhom) cudaFree(ms->d_inhom);
+              ms->inhom_cap = ctx->n_lines;
+              CUDA_OK(ctx, cudaMalloc((void **)&ms->d_inhom, sizeof(double) * WBEM_MULTI_MAX * ms->inhom_cap));
+            }
+          if (ctx->n_lines)
+            CUDA_OK(ctx, cudaMemcpyAsync(ms->d_inhom + b * ms->inhom_cap, ctx->d_con_inhom, sizeof(double) * ctx->n_lines,
+                                         cudaMemcpyDeviceToDevice, st));
+        }
+      own_inhom = true;
+    }
+  if (ctx->n_lines)
+    for (int b = 0; b < nb; ++b)
+      {
+        k_distribute_rhs<<<(ctx->n_lines + 255) / 256, 256, 0, st>>>(
+          ctx->n_lines, ctx->d_con_lines, own_inhom ? ms->d_inhom + b * ms->inhom_cap : ctx->d_con_inhom, ms->d_rhs + b * ld);
+        ctx->launches++;
+      }
+  if ((rc = wbem_build_preconditioner(ctx))) return rc;
+  if (ctx->group && (rc = wbem_group_barrier(ctx))) return rc;
+
+  // per-system GMRES state (host)
+  struct Sys
+  {
+    std::vector<double> H, gamma, ci, si, h, y;
+    int accumulated = 0, state = 0, dim = 0;
+    double rho = 0;
+    bool in_cycle = false;
+  };
+  std::vector<Sys> sys(nb);
+  for (Sys &q : sys)
+    {
+      q.H.assign((size_t)ntmp * ntmp, 0.0);
+      q.gamma.assign(ntmp + 1, 0.0);
+      q.ci.assign(ntmp + 1, 0.0);
+      q.si.assign(ntmp + 1, 0.0);
+      q.h.assign(ntmp + 1, 0.0);
+      q.y.assign(ntmp + 1, 0.0);
+    }
+  auto Vb = [&](int b) { return ms->d_V + (size_t)b * (ntmp - 1) * ldv; };
+  auto small = [&](int b) { return ms->d_small + (size_t)b * ms->small_stride; };
+  CUDA_OK(ctx, cudaMemsetAsync(ms->d_x, 0, sizeof(double) * WBEM_MULTI_MAX * ld, st));
+  bool first_cycle = true;
+  for (;;)
+    {
+      std::vector<int> act;
+      for (int b = 0; b < nb; ++b)
+        if (sys[b].state == 0) act.push_back(b);
+      if (act.empty()) break;
+      // residuals of the active systems -> V[0]
+      if (first_cycle)
+        for (int b : act)
+          CUDA_OK(ctx, cudaMemcpyAsync(ms->d_p + b * ld, ms->d_rhs + b * ld, sizeof(double) * N, cudaMemcpyDeviceToDevice, st));
+      else
+        {
+          for (size_t k = 0; k < act.size(); ++k)
+            {
+              src[k] = ms->d_x + act[k] * ld;
+              dst[k] = ms->d_p + act[k] * ld;
+            }
+          if ((rc = wbem_apply_operator_multi(ctx, 0, (int)act.size(), src, dst, true))) return rc;
+          for (int b : act)
+            {
+              k_residual<<<nbk, 256, 0, st>>>(N, ms->d_rhs + b * ld, ms->d_p + b * ld, ms->d_p + b * ld);
+              ctx->launches++;
+            }
+        }
+      for (int b : act)
+        {
+          if ((rc = wbem_apply_preconditioner(ctx, ms->d_p + b * ld, Vb(b)))) return rc;
+          k_norm2<<<1, 1024, 0, st>>>(N, Vb(b), ms->d_norm + b);
+          ctx->launches++;
+        }
+      CUDA_OK(ctx, cudaMemcpyAsync(ms->h_pin, ms->d_norm, sizeof(double) * WBEM_MULTI_MAX, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaStreamSynchronize(st));
+      for (int b : act)
+        {
+          Sys &q = sys[b];
+          q.rho = ms->h_pin[b];
+          q.state = (q.rho <= tol) ? 1 : ((q.accumulated >= max_steps) ? 2 : 0);
+          if (!(q.rho == q.rho)) q.state = 2;
+          q.dim = 0;
+          q.in_cycle = q.state == 0;
+          if (q.state == 0)
+            {
+              q.gamma[0] = q.rho;
+              k_scale<<<nbk, 256, 0, st>>>(N, Vb(b), 1.0 / q.rho);
+              ctx->launches++;
+            }
+        }
+      for (int inner = 0; inner < m; ++inner)
+        {
+          act.clear();
+          for (int b = 0; b < nb; ++b)
+            if (sys[b].state == 0 && sys[b].in_cycle) act.push_back(b);
+          if (act.empty()) break;
+          for (size_t k = 0; k < act.size(); ++k)
+            {
+              src[k] = Vb(act[k]) + (size_t)inner * ldv;
+              dst[k] = ms->d_p + act[k] * ld;
+            }
+          if ((rc = wbem_apply_operator_multi(ctx, 0, (int)act.size(), src, dst, true))) return rc;
+          const int dim = inner + 1;
+          for (int b : act)
+            {
+              double *vv = Vb(b) + (size_t)(inner + 1) * ldv;
+              if ((rc = wbem_apply_preconditioner(ctx, ms->d_p + b * ld, vv))) return rc;
+              double *d_part = small(b) + GM_KMAX, *d_nrm = d_part + DOT_SEGS * GM_KMAX, *d_hacc = d_nrm + nb128;
+              for (int pass = 0; pass < 2; ++pass)
+                {
+                  k_dots<<<dim3(dim, DOT_SEGS), 256, 0, st>>>(N, Vb(b), ldv, vv, d_part);
+                  k_project_out<<<nb128, 128, sizeof(double) * dim, st>>>(N, dim, Vb(b), ldv, d_part, vv, d_hacc, pass, d_nrm);
+                  ctx->launches += 2;
+                }
+              CUDA_OK(ctx, cudaMemcpyAsync(ms->h_pin + b * ms->pin_stride, d_nrm, sizeof(double) * (nb128 + dim),
+                                           cudaMemcpyDeviceToHost, st));
+            }
+          CUDA_OK(ctx, cudaStreamSynchronize(st)); // ONE host round trip per block iteration
+          for (int b : act)
+            {
+              Sys &q = sys[b];
+              const double *hp = ms->h_pin + b * ms->pin_stride;
+              ++q.accumulated;
+              for (int i = 0; i < dim; ++i) q.h[i] = hp[nb128 + i];
+              double ss = 0;
+              for (unsigned i = 0; i < nb128; ++i) ss += hp[i];
+              q.h[dim] = std::sqrt(ss);
+              k_scale<<<nbk, 256, 0, st>>>(N, Vb(b) + (size_t)(inner + 1) * ldv, 1.0 / q.h[dim]);
+              ctx->launches++;
+              givens(q.h, q.gamma, q.ci, q.si, inner);
+              for (int i = 0; i < dim; ++i) q.H[(size_t)i * ntmp + inner] = q.h[i];
+              q.rho = std::fabs(q.gamma[dim]);
+              q.dim = dim;
+              q.state = (q.rho <= tol) ? 1 : ((q.accumulated >= max_steps) ? 2 : 0);
+              if (!(q.rho == q.rho)) q.state = 2;
+            }
+        }
+      // H y = gamma, x += V y for every system that took part in this cycle
+      for (int b = 0; b < nb; ++b)
+        {
+          Sys &q = sys[b];
+          if (!q.in_cycle) continue;
+          q.in_cycle = false;
+          const int dim = q.dim;
+          if (dim == 0) continue;
+          for (int i = dim - 1; i >= 0; --i)
+            {
+              double t = q.gamma[i];
+              for (int k = i + 1; k < dim; ++k) t -= q.H[(size_t)i * ntmp + k] * q.y[k];
+              q.y[i] = t / q.H[(size_t)i * ntmp + i];
+            }
+          double *hp = ms->h_pin + b * ms->pin_stride;
+          for (int i = 0; i < dim; ++i) hp[i] = q.y[i];
+          CUDA_OK(ctx, cudaMemcpyAsync(small(b), hp, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+          k_update_solution<<<nbk, 256, sizeof(double) * dim, st>>>(N, dim, Vb(b), ldv, small(b), ms->d_x + b * ld);
+          ctx->launches++;
+        }
+      CUDA_OK(ctx, cudaStreamSynchronize(st)); // the pinned staging is reused by the next cycle
+      first_cycle = false;
+    }
+  // unpack (:869-879)
+  for (int b = 0; b < nb; ++b)
+    {
+      k_unpack<<<nbk, 256, 0, st>>>(N, ctx->d_surf, ms->d_x + b * ld, d_phi + (size_t)b * N, d_dphi_dn + (size_t)b * N);
+      ctx->launches++;
+      if (iters_out) iters_out[b] = sys[b].accumulated;
+      if (res_out) res_out[b] = sys[b].rho;
+      if (sys[b].state != 1) *rc_out = 1;
+    }
+  return 0;
+}
+
+int wbem_solve_system_multi_device(wbem_ctx *ctx, int nrhs, double *d_phi, double *d_dphi_dn, const double *d_bc,
+                                   int *iters, double *last_res)
+{
+  if (!ctx->assembled) WBEM_FAIL(ctx, -3, "solve_system before assemble_system");
+  if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "solve_system before wbem_set_masks");
+  if (nrhs < 1) return 0;
+  cudaStream_t st = ctx->stream;
+  ctx->timer.st = st;
+  ctx->timer.on = true;
+  ctx->timer.reset();
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[4], st));
+  int rc;
+  if (!ctx->have_alpha && (rc = wbem_launch_alpha(ctx))) return rc;
+  int not_converged = 0, max_iters = 0;
+  for (int g0 = 0; g0 < nrhs; g0 += WBEM_MULTI_MAX)
+    {
+      const int nb = std::min(WBEM_MULTI_MAX, nrhs - g0);
+      rc = solve_group(ctx, nb, d_phi + (size_t)g0 * ctx->N, d_dphi_dn + (size_t)g0 * ctx->N, d_bc + (size_t)g0 * ctx->N,
+                       iters ? iters + g0 : nullptr, last_res ? last_res + g0 : nullptr, &not_converged);
+      if (rc) return rc;
+    }
+  CUDA_OK(ctx, cudaEventRecord(ctx->ev[5], st));
+  CUDA_OK(ctx, cudaStreamSynchronize(st));
+  CUDA_OK(ctx, cudaGetLastError());
+  if ((rc = wbem_check_gather_timeout(ctx))) return rc;
+  double sums[T_NTAGS];
+  int counts[T_NTAGS];
+  ctx->timer.resolve(sums, counts, T_NTAGS);
+  ctx->timer.on = false;
+  float msf = 0;
+  cudaEventElapsedTime(&msf, ctx->ev[4], ctx->ev[5]);
+  if (iters)
+    for (int b = 0; b < nrhs; ++b) max_iters = std::max(max_iters, iters[b]);
+  ctx->tm.gemv_ms_sum = sums[T_GEMV];
+  ctx->tm.gemv_calls = counts[T_GEMV];
+  ctx->tm.allgather_ms_sum = sums[T_ALLGATHER];
+  ctx->tm.solve_system_total_ms = msf;
+  ctx->tm.gmres_iters = max_iters;
+  return not_converged;
 }

@@ -11,6 +11,7 @@
 #define WBEM_MAX_NS 288  // singular rule: up to 2 * 12^2
 #define WBEM_MAX_PEERS 16
 #define WBEM_GMRES_KMAX 1024 // largest gmres_n_tmp_vectors
+#define WBEM_MULTI_MAX 8     // right-hand sides one block mat-vec streams the matrices for (wbem_solve_system_multi)
 
 struct QuadTables
 { // host copies of the reference-cell tables (uploaded to __constant__ memory)
@@ -122,7 +123,7 @@ struct wbem_ctx
   void *d_gauss = nullptr;  // GaussTable (constraints.cu)
   // per-device launch state (a context on another GPU needs its own opt-ins / occupancy)
   bool tiled_attr_set = false, bcr_attr_done = false;
-  int gemv_ctas_per_sm = 0, n_sm = 0;
+  int gemv_ctas_per_sm = 0, gemv_multi_ctas_per_sm[3] = {0, 0, 0}, n_sm = 0;
 
   // sizes
   uint32_t N = 0, C = 0, ld = 0;
@@ -206,7 +207,8 @@ struct wbem_ctx
   NcclApi *nccl = nullptr;
   void *nccl_comm = nullptr;
   // peer-to-peer gather fused into k_bem_gemv: every rank's gather buffer mapped through
-  // CUDA IPC.  d_p2p = [2][chunk*P] doubles (double-buffered by epoch) + WBEM_MAX_PEERS flags
+  // CUDA IPC.  d_p2p = [2][WBEM_MULTI_MAX][chunk*P] doubles (double-buffered by epoch; one slab per
+  // right-hand side of a block mat-vec) + WBEM_MAX_PEERS flags
   double *d_p2p = nullptr;
   double *peer_base[WBEM_MAX_PEERS] = {};
   bool peer_opened[WBEM_MAX_PEERS] = {};
@@ -214,6 +216,8 @@ struct wbem_ctx
   unsigned long long p2p_epoch = 0, gemv_done_total = 0;
   unsigned long long *d_done_counter = nullptr;
 
+  void *multi = nullptr; // gmres.cu: work vectors of wbem_solve_system_multi (allocated at first use)
+  double *d_ymulti = nullptr; // [WBEM_MULTI_MAX][chunk*world] gather buffers of the block mat-vec (no peer stores)
   wbem_timings tm = {};
   long long launches = 0;
 };
@@ -249,6 +253,8 @@ uint32_t wbem_tile_width(void);
 // operator.cu
 int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double *d_src,
                         double *d_dst, bool constrained);
+int wbem_apply_operator_multi(wbem_ctx *ctx, int mode, int nb, const double *const *d_src, double *const *d_dst,
+                              bool constrained);
 int wbem_allgather_rows(wbem_ctx *ctx, double *d_buf /* [chunk*world], own block filled */);
 int wbem_allgather_bytes(wbem_ctx *ctx, void *d_buf, size_t bytes_per_rank);
 int wbem_check_gather_timeout(wbem_ctx *ctx);
@@ -257,6 +263,14 @@ int wbem_build_preconditioner(wbem_ctx *ctx);
 int wbem_apply_preconditioner(wbem_ctx *ctx, const double *d_in, double *d_out);
 int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn,
                              const double *d_bc, int *iters, double *last_res);
+int wbem_solve_system_multi_device(wbem_ctx *ctx, int nrhs, double *d_phi, double *d_dphi_dn, const double *d_bc,
+                                   int *iters, double *last_res);
+void wbem_multi_free(wbem_ctx *ctx);
+struct MultiWork
+{ // multiplier slabs of the block mat-vec, [WBEM_MULTI_MAX][ld] each (owned by gmres.cu's block state)
+  double *d_xn, *d_xd, *d_xdiag;
+};
+MultiWork *wbem_multi_work(wbem_ctx *ctx);
 // precond.cu
 int wbem_device_precond_factor(wbem_ctx *ctx);
 int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out);

@@ -10,6 +10,7 @@
 // operator application reads ~8 N^2 bytes instead of the reference's 16 N^2.
 // Each warp owns 4 rows: the x chunk is loaded once and reused for 4 streamed 128-bit
 // matrix loads per lane.
+#include <algorithm>
 #include <cstdio>
 #include <cstdlib>
 
@@ -349,9 +350,9 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   double *yloc = ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk;
   const int P = ctx->p.world_size;
   const bool use_p2p = P > 1 && ctx->p2p_ready && !((mode == 0) && ctx->pure_neumann);
-  const size_t p2p_len = (size_t)ctx->chunk * P;
+  const size_t p2p_len = (size_t)ctx->chunk * P, p2p_half = (size_t)WBEM_MULTI_MAX * p2p_len;
   if (use_p2p) ctx->p2p_epoch++;
-  const double *ygather = use_p2p ? ctx->d_p2p + (ctx->p2p_epoch & 1ull) * p2p_len : ctx->d_yloc;
+  const double *ygather = use_p2p ? ctx->d_p2p + (ctx->p2p_epoch & 1ull) * p2p_half : ctx->d_yloc;
   if (ctx->nloc || use_p2p)
     {
       ctx->timer.begin(T_GEMV);
@@ -400,8 +401,8 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
           if (grid == 0) grid = 1; // a rank without rows still has to raise its flag
           ga.n_peers = P;
           for (int q = 0; q < P; ++q) ga.peer_base[q] = ctx->peer_base[q];
-          ga.buf_off = (ctx->p2p_epoch & 1ull) * p2p_len;
-          ga.flag_off = 2 * p2p_len;
+          ga.buf_off = (ctx->p2p_epoch & 1ull) * p2p_half;
+          ga.flag_off = 2 * p2p_half;
           ga.epoch = ctx->p2p_epoch;
           ctx->gemv_done_total += grid;
           ga.done_target = ctx->gemv_done_total;
@@ -440,9 +441,359 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   const bool con = constrained && ctx->n_lines > 0;
   k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(
     N, ygather, d_src, con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0, d_dst,
-    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_len) : nullptr, P, ctx->p2p_epoch,
+    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_half) : nullptr, P, ctx->p2p_epoch,
     ctx->d_gather_timeout);
   ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Block mat-vec: the same operator applied to nb <= WBEM_MULTI_MAX vectors while the matrices are
+// streamed ONCE (the J.v pattern of FreeSurface::jacobian, reference source/free_surface.cc:4918-4993:
+// one inner GMRES per outer Krylov vector, unchanged matrices).  One CTA per group of MV_NR rows;
+// its 8 warps split the column chunks, every lane keeps MV_NR x NB accumulators; fixed-order
+// reduction through shared memory.  Bytes per launch = those of ONE single-vector application.
+// ---------------------------------------------------------------------------------------
+#define MV_MAXR 4 // rows one warp streams in one pass of the block mat-vec
+struct GemvMultiArgs
+{
+  GemvArgs g;            // x1 / x2 / xdiag / y hold the FIRST vector; the others follow at the strides below.
+                         // The signs s1 / s2 / sdiag are already folded into the multiplier vectors.
+  int nb;
+  size_t xstride;        // doubles between consecutive multiplier vectors
+  size_t ystride;        // doubles between consecutive result vectors (local results or gather slabs)
+};
+
+// acc[r][k] += sum over the listed chunks [b, e) of M[rows[r], :] . x_k ; NR rows share every x chunk,
+// NC chunks in flight (NR * NC independent 128-bit matrix loads per lane)
+template <int NR, int NC, int NB>
+__device__ __forceinline__ void gemv_multi_pass(const double *__restrict__ M, const double *__restrict__ x, size_t xstride,
+                                                const uint32_t *__restrict__ list, int b, int e, uint32_t ld,
+                                                const uint32_t rows[MV_MAXR], int lane, double acc[MV_MAXR][NB])
+{
+  const double *base[NR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) base[r] = M + (size_t)rows[r] * ld + lane * 2;
+  int i = b;
+  for (; i + NC <= e; i += NC)
+    {
+      uint32_t c[NC];
+#pragma unroll
+      for (int j = 0; j < NC; ++j) c[j] = list[i + j] * 64;
+      double2 m[NC][NR];
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int r = 0; r < NR; ++r) m[j][r] = ld_stream(base[r] + c[j]);
+#pragma unroll
+      for (int j = 0; j < NC; ++j)
+#pragma unroll
+        for (int k = 0; k < NB; ++k)
+          {
+            const double2 xv = *reinterpret_cast<const double2 *>(x + k * xstride + c[j] + lane * 2);
+#pragma unroll
+            for (int r = 0; r < NR; ++r)
+              {
+                acc[r][k] = fma(m[j][r].x, xv.x, acc[r][k]);
+                acc[r][k] = fma(m[j][r].y, xv.y, acc[r][k]);
+              }
+          }
+    }
+  for (; i < e; ++i)
+    {
+      const uint32_t c0 = list[i] * 64;
+      double2 m0[NR];
+#pragma unroll
+      for (int r = 0; r < NR; ++r) m0[r] = ld_stream(base[r] + c0);
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        {
+          const double2 xv = *reinterpret_cast<const double2 *>(x + k * xstride + c0 + lane * 2);
+#pragma unroll
+          for (int r = 0; r < NR; ++r)
+            {
+              acc[r][k] = fma(m0[r].x, xv.x, acc[r][k]);
+              acc[r][k] = fma(m0[r].y, xv.y, acc[r][k]);
+            }
+        }
+    }
+}
+
+template <int NB>
+__device__ __forceinline__ void gemv_multi_store(const GemvMultiArgs &ma, uint32_t lrow, int k, double v)
+{
+  const GemvArgs &a = ma.g;
+  const uint32_t g = a.row0 + lrow;
+  v += a.alpha[g] * a.xdiag[k * ma.xstride + g];
+  if (a.n_peers > 1)
+    for (int q = 0; q < a.n_peers; ++q) a.peer_base[q][a.buf_off + k * ma.ystride + g] = v; // NVLink stores
+  else
+    a.y[k * ma.ystride + lrow] = v;
+}
+
+template <int NR, int NC, int NB>
+__device__ __forceinline__ void gemv_multi_rows(const GemvMultiArgs &ma, uint32_t r0, int lane)
+{
+  const GemvArgs &a = ma.g;
+  double acc[MV_MAXR][NB];
+#pragma unroll
+  for (int r = 0; r < MV_MAXR; ++r)
+#pragma unroll
+    for (int k = 0; k < NB; ++k) acc[r][k] = 0.0;
+  uint32_t rows[MV_MAXR];
+#pragma unroll
+  for (int r = 0; r < NR; ++r) rows[r] = a.row_list ? a.row_list[r0 + r] : r0 + r;
+  gemv_multi_pass<NR, NC, NB>(a.M1, a.x1, ma.xstride, a.list1, 0, a.n1, a.ld, rows, lane, acc);
+  gemv_multi_pass<NR, NC, NB>(a.M2, a.x2, ma.xstride, a.list2, 0, a.n2, a.ld, rows, lane, acc);
+#pragma unroll
+  for (int r = 0; r < NR; ++r)
+#pragma unroll
+    for (int k = 0; k < NB; ++k)
+      {
+        double v = acc[r][k];
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+        if (lane == (k & 31) && k < ma.nb) gemv_multi_store<NB>(ma, rows[r], k, v);
+      }
+}
+
+// Same work split as k_bem_gemv: one resident wave, every warp streams the same number q of whole
+// rows (passes of <= MV_MAXR rows sharing each x chunk), the remainder rows are split column-wise
+// over the 8 warps of a CTA.
+template <int NB>
+__global__ void __launch_bounds__(GEMV_WARPS * 32, 2) k_bem_gemv_multi(const GemvMultiArgs ma)
+{
+  const GemvArgs &a = ma.g;
+  __shared__ double red[GEMV_WARPS][NB];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const uint32_t G = gridDim.x, c = blockIdx.x;
+  const uint32_t Wt = G * GEMV_WARPS;
+  const uint32_t q = a.n_rows / Wt, rem = a.n_rows - q * Wt;
+  uint32_t r0 = (c * GEMV_WARPS + warp) * q;
+  const uint32_t r1 = r0 + q;
+  while (r0 < r1)
+    {
+      const uint32_t left = r1 - r0;
+      const uint32_t passes = (left + MV_MAXR - 1) / MV_MAXR;
+      const uint32_t take = (left + passes - 1) / passes;
+      switch (take)
+        {
+        case 1: gemv_multi_rows<1, 4, NB>(ma, r0, lane); break;
+        case 2: gemv_multi_rows<2, 2, NB>(ma, r0, lane); break;
+        case 3: gemv_multi_rows<3, 2, NB>(ma, r0, lane); break;
+        default: gemv_multi_rows<4, 2, NB>(ma, r0, lane); break;
+        }
+      r0 += take;
+    }
+  for (uint32_t j = c; j < rem; j += G)
+    { // one row, its column chunks split over the 8 warps
+      uint32_t rows[MV_MAXR];
+      const uint32_t idx = q * Wt + j;
+      rows[0] = a.row_list ? a.row_list[idx] : idx;
+      double acc[MV_MAXR][NB];
+#pragma unroll
+      for (int k = 0; k < NB; ++k) acc[0][k] = 0.0;
+      const int b1 = a.n1 * warp / GEMV_WARPS, e1 = a.n1 * (warp + 1) / GEMV_WARPS;
+      const int b2 = a.n2 * warp / GEMV_WARPS, e2 = a.n2 * (warp + 1) / GEMV_WARPS;
+      gemv_multi_pass<1, 4, NB>(a.M1, a.x1, ma.xstride, a.list1, b1, e1, a.ld, rows, lane, acc);
+      gemv_multi_pass<1, 4, NB>(a.M2, a.x2, ma.xstride, a.list2, b2, e2, a.ld, rows, lane, acc);
+#pragma unroll
+      for (int k = 0; k < NB; ++k)
+        {
+          double v = acc[0][k];
+#pragma unroll
+          for (int off = 16; off > 0; off >>= 1) v += __shfl_xor_sync(0xffffffffu, v, off);
+          if (lane == 0) red[warp][k] = v;
+        }
+      __syncthreads();
+      if ((int)threadIdx.x < ma.nb)
+        {
+          double t = 0.0;
+#pragma unroll
+          for (int w = 0; w < GEMV_WARPS; ++w) t += red[w][threadIdx.x]; // fixed order: deterministic
+          gemv_multi_store<NB>(ma, rows[0], threadIdx.x, t);
+        }
+      __syncthreads();
+    }
+  if (a.n_peers > 1)
+    { // completion: the last CTA of this launch publishes "rank's rows of epoch e are in place"
+      __shared__ bool s_last;
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          __threadfence_system();
+          const unsigned long long prev = atomicAdd(a.done_counter, 1ull);
+          s_last = (prev + 1ull == a.done_target);
+        }
+      __syncthreads();
+      if (s_last && threadIdx.x < a.n_peers)
+        {
+          __threadfence_system();
+          unsigned long long *flag =
+            reinterpret_cast<unsigned long long *>(a.peer_base[threadIdx.x] + a.flag_off) + a.rank;
+          asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(flag), "l"(a.epoch) : "memory");
+        }
+    }
+}
+
+// multipliers of the block mat-vec, signs folded in: x1p = s1 m1 src, x2p = s2 m2 src, xdiag = sdiag m1 src
+__global__ void k_prep_multipliers_signed(uint32_t N, const double *__restrict__ src, const double *__restrict__ m1,
+                                          const double *__restrict__ m2, const uint32_t *__restrict__ colpos,
+                                          double s1, double s2, double sdiag, double *__restrict__ x1p,
+                                          double *__restrict__ x2p, double *__restrict__ xdiag)
+{
+  const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const double s = src[i];
+  const double a = m1[i] * s, b = m2[i] * s;
+  const uint32_t c = colpos[i];
+  x1p[c] = s1 * a;
+  x2p[c] = s2 * b;
+  xdiag[i] = sdiag * a;
+}
+
+// d_dst[b] = operator(d_src[b]) for b < nb, one pass over the matrices.  The multiplier vectors are
+// kept in ctx->multi (allocated by gmres.cu): xn / xd / xdiag slabs of ld doubles each.
+
+int wbem_apply_operator_multi(wbem_ctx *ctx, int mode, int nb, const double *const *d_src, double *const *d_dst,
+                              bool constrained)
+{
+  cudaStream_t st = ctx->stream;
+  const uint32_t N = ctx->N;
+  if (nb < 1 || nb > WBEM_MULTI_MAX) WBEM_FAIL(ctx, -1, "block mat-vec takes 1..%d vectors", WBEM_MULTI_MAX);
+  if (!ctx->assembled || !ctx->have_masks || !ctx->have_alpha) WBEM_FAIL(ctx, -3, "operator applied before assembly / masks / alpha");
+  MultiWork *mw = wbem_multi_work(ctx);
+  if (!mw) return -2;
+  const double *m1 = mode == 0 ? ctx->d_other : ctx->d_surf; // multiplier mask of N
+  const double *m2 = mode == 0 ? ctx->d_surf : ctx->d_other; // multiplier mask of D
+  const size_t ld = ctx->ld;
+  const double sg1 = mode == 0 ? 1.0 : -1.0, sg2 = -sg1, sgd = sg1; // vmult: +N -D +alpha ; rhs: -N +D -alpha
+  for (int b = 0; b < nb; ++b)
+    {
+      k_prep_multipliers_signed<<<(N + 255) / 256, 256, 0, st>>>(N, d_src[b], m1, m2, ctx->d_colpos, sg1, sg2, sgd,
+                                                                mw->d_xn + b * ld, mw->d_xd + b * ld, mw->d_xdiag + b * ld);
+      ctx->launches++;
+    }
+  const int P = ctx->p.world_size;
+  const bool shift = (mode == 0) && ctx->pure_neumann;
+  const bool use_p2p = P > 1 && ctx->p2p_ready && !shift;
+  const size_t p2p_len = (size_t)ctx->chunk * P, p2p_half = (size_t)WBEM_MULTI_MAX * p2p_len;
+  if (use_p2p) ctx->p2p_epoch++;
+  if (!ctx->d_ymulti)
+    {
+      CUDA_OK(ctx, cudaMalloc((void **)&ctx->d_ymulti, sizeof(double) * WBEM_MULTI_MAX * (p2p_len + 64)));
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_ymulti, 0, sizeof(double) * WBEM_MULTI_MAX * (p2p_len + 64), st));
+    }
+  const size_t ystride = use_p2p ? p2p_len : p2p_len + 64;
+  const double *ygather = use_p2p ? ctx->d_p2p + (ctx->p2p_epoch & 1ull) * p2p_half : ctx->d_ymulti;
+  {
+    ctx->timer.begin(T_GEMV);
+    const int variant = nb <= 2 ? 0 : (nb <= 4 ? 1 : 2);
+    int &ctas_per_sm = ctx->gemv_multi_ctas_per_sm[variant], &n_sm = ctx->n_sm;
+    if (!ctas_per_sm)
+      {
+        if (variant == 0)
+          CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_bem_gemv_multi<2>, GEMV_WARPS * 32, 0));
+        else if (variant == 1)
+          CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_bem_gemv_multi<4>, GEMV_WARPS * 32, 0));
+        else
+          CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctas_per_sm, k_bem_gemv_multi<WBEM_MULTI_MAX>,
+                                                                     GEMV_WARPS * 32, 0));
+        CUDA_OK(ctx, cudaDeviceGetAttribute(&n_sm, cudaDevAttrMultiProcessorCount, ctx->dev));
+        if (ctas_per_sm < 1) ctas_per_sm = 1;
+      }
+    GemvMultiArgs ma;
+    GemvArgs &ga = ma.g;
+    ga.M1 = ctx->d_Nm;
+    ga.x1 = mw->d_xn;
+    ga.M2 = ctx->d_Dm;
+    ga.x2 = mw->d_xd;
+    ga.alpha = ctx->d_alpha;
+    ga.xdiag = mw->d_xdiag;
+    ga.ld = ctx->ld;
+    ga.nloc = ctx->nloc;
+    ga.row0 = ctx->row0;
+    ga.y = ctx->d_ymulti + (size_t)ctx->p.rank * ctx->chunk;
+    const bool skip = constrained && ctx->n_lines > 0 && ctx->d_free_rows && !shift;
+    ga.row_list = skip ? ctx->d_free_rows : nullptr;
+    ga.n_rows = skip ? ctx->n_free_rows : ctx->nloc;
+    if (mode == 0)
+      {
+        ga.list1 = ctx->d_list_o; ga.n1 = ctx->n_list_o; ga.s1 = 1.0;
+        ga.list2 = ctx->d_list_s; ga.n2 = ctx->n_list_s; ga.s2 = -1.0;
+        ga.sdiag = 1.0;
+      }
+    else
+      {
+        ga.list1 = ctx->d_list_s; ga.n1 = ctx->n_list_s; ga.s1 = -1.0;
+        ga.list2 = ctx->d_list_o; ga.n2 = ctx->n_list_o; ga.s2 = 1.0;
+        ga.sdiag = -1.0;
+      }
+    ma.nb = nb;
+    ma.xstride = ld;
+    ma.ystride = ystride;
+    uint32_t grid = (uint32_t)(n_sm * ctas_per_sm);
+    if (ga.n_rows == 0) grid = 0;
+    if (grid > ga.n_rows && ga.n_rows > 0) grid = ga.n_rows;
+    ga.n_peers = 1;
+    ga.rank = ctx->p.rank;
+    if (use_p2p)
+      {
+        if (grid == 0) grid = 1;
+        ga.n_peers = P;
+        for (int q = 0; q < P; ++q) ga.peer_base[q] = ctx->peer_base[q];
+        ga.buf_off = (ctx->p2p_epoch & 1ull) * p2p_half;
+        ga.flag_off = 2 * p2p_half;
+        ga.epoch = ctx->p2p_epoch;
+        ctx->gemv_done_total += grid;
+        ga.done_target = ctx->gemv_done_total;
+        ga.done_counter = ctx->d_done_counter;
+      }
+    if (grid)
+      {
+        if (nb <= 2)
+          k_bem_gemv_multi<2><<<grid, GEMV_WARPS * 32, 0, st>>>(ma);
+        else if (nb <= 4)
+          k_bem_gemv_multi<4><<<grid, GEMV_WARPS * 32, 0, st>>>(ma);
+        else
+          k_bem_gemv_multi<WBEM_MULTI_MAX><<<grid, GEMV_WARPS * 32, 0, st>>>(ma);
+        ctx->launches++;
+      }
+    ctx->tm.gemv_bytes_last = 8.0 * 64.0 * (double)(ctx->n_list_o + ctx->n_list_s) * (double)ga.n_rows;
+    ctx->timer.end();
+  }
+  if (use_p2p && ctx->group && ctx->p.fused_gather_on_shared_device)
+    {
+      const int brc = wbem_group_barrier(ctx);
+      if (brc) return brc;
+    }
+  if (P > 1 && !use_p2p)
+    {
+      ctx->timer.begin(T_ALLGATHER);
+      for (int b = 0; b < nb; ++b)
+        {
+          const int rc = wbem_allgather_rows(ctx, ctx->d_ymulti + b * ystride);
+          if (rc) return rc;
+        }
+      ctx->timer.end();
+    }
+  const bool con = constrained && ctx->n_lines > 0;
+  for (int b = 0; b < nb; ++b)
+    {
+      double *yb = const_cast<double *>(ygather) + b * ystride;
+      if (shift)
+        {
+          k_norm2_single<<<1, 1024, 0, st>>>(N, yb, ctx->d_h + 512);
+          k_add_neg_scalar<<<(N + 255) / 256, 256, 0, st>>>(N, yb, ctx->d_h + 512);
+          ctx->launches += 2;
+        }
+      k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(
+        N, yb, d_src[b], con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0, d_dst[b],
+        use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_half) : nullptr, P, ctx->p2p_epoch,
+        ctx->d_gather_timeout);
+      ctx->launches++;
+    }
   CUDA_OK(ctx, cudaGetLastError());
   return 0;
 }
