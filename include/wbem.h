@@ -270,12 +270,6 @@ int wbem_measure_fp64_peak(wbem_ctx *ctx, double *tflops);
 int wbem_measure_copy_bw(wbem_ctx *ctx, double *gbs);
 int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, double *bytes);
 int wbem_time_assemble(wbem_ctx *ctx, int reps, double *ms_avg);
-/* issue-port probe: DFMA TFLOP/s with 2*n_int integer ALU instructions interleaved per 8 DFMAs
- * (n_int in {0,2,4,8,16}); n_int = 100/101/102/103: eight chains of DFMA / DADD / DMUL / alternating
- * DFMA-DADD only (instructions/s reported as 2 flop each); 104: FP64 tensor-core MMA (m8n8k4) rate;
- * 105/106/107: the DFMA rate of 8 chains with 1 / 2 / 0 such MMAs issued beside them per iteration.  Used to calibrate the assembly kernel's
- * instruction budget */
-int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops);
 /* device self test of the fast 1/sqrt used by the regular-pair kernel: out[i] = rsqrt(in[i]) */
 int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out, int n);
 /* host-only check of the assembly tiling plan (no GPU): 0 = all invariants hold */

@@ -588,6 +588,31 @@ def test_compute_constraints_inside_the_library(wb, orc):
     interior = np.nonzero(~c.node_on_patch_boundary)[0]
     hanging = [(int(interior[3]), [(int(interior[0]), 0.5), (int(interior[1]), 0.5)])]
     cases.append((c, sc, np.cos(c.xyz[:, 1]), hanging))
+    # chains, resolved like ConstraintMatrix::close() (:1104): (1) a triple node with one FLAT and one SHARP
+    # Dirichlet edge -- two coplanar free-surface patches and a Dirichlet side wall: the flat double refers
+    # to a dof the sharp edge turns into an inhomogeneous line; (2) a hanging node whose masters are a
+    # double-node pair, one of which is itself constrained
+    s2 = np.isin(t.node_patch, [t.patch_names.index(k) for k in
+                                ("fs_up", "fs_down", "fs_mid_right", "fs_mid_left", "side_left")]).astype(float)
+    cases.append((t, s2, np.sin(t.xyz[:, 0]) + 0.3 * t.xyz[:, 2] + 0.1 * t.xyz[:, 1] ** 2, None))
+    pair = next((int(i), int(t_)) for i in range(c.n_nodes) for t_ in c.dn_idx[c.dn_ptr[i]:c.dn_ptr[i + 1]]
+                if t_ != i and sc[i] == 0 and sc[t_] == 0)
+    cases.append((c, sc, np.cos(c.xyz[:, 1]), [(int(interior[5]), [(pair[0], 0.5), (pair[1], 0.5)])]))
+    n_chain_cases = 0
+    # the two chain cases really contain chains before close(): the walk alone (resolve_chains disabled)
+    # leaves an entry that refers to a constrained dof
+    import wavebem_b200.constraints as _con
+    keep = _con.resolve_chains
+    try:
+        _con.resolve_chains = lambda lines: None
+        for m, s, bc, hanging in cases[-2:]:
+            nrm = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
+            grd = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, bc, s)
+            raw = _lines_dict(compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=nrm,
+                                                  node_surface_gradients=grd, hanging=hanging))
+            assert any(col in raw for e, _ in raw.values() for col, _ in e)
+    finally:
+        _con.resolve_chains = keep
     for m, s, bc, hanging in cases:
         ctx = _ctx(wb, m, gmres_tol=1e-12, gmres_max_steps=400)
         ctx.set_masks(s, 1.0 - s)
@@ -596,6 +621,10 @@ def test_compute_constraints_inside_the_library(wb, orc):
         got = ctx.compute_constraints(bc)
         nrm = orc.compute_normals(m.xyz, m.cells, m.dir_flag)
         grd = orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, bc, s)
+        if hanging:   # the hanging lines are condensed into both projections (computational_domain.cc:1535-1538)
+            from oracle import projections
+            nrm = projections.l2_projection(0, m.xyz, m.cells, m.dir_flag, hanging=hanging)
+            grd = projections.l2_projection(1, m.xyz, m.cells, m.dir_flag, bc * s, hanging=hanging)
         ref = compute_constraints(m.dn_ptr, m.dn_idx, s, bc, nodes_normals=nrm, node_surface_gradients=grd,
                                   hanging=hanging)
         a, b = _lines_dict(got), _lines_dict(ref)
@@ -605,6 +634,8 @@ def test_compute_constraints_inside_the_library(wb, orc):
             assert abs(a[k][1] - b[k][1]) <= 1e-10 * max(1.0, abs(b[k][1])), (k, a[k], b[k])
         if m is c and not hanging:
             assert any(not e and ih != 0.0 for e, ih in a.values())      # sharp-edge inhomogeneities present
+        assert not any(col in a for e, _ in a.values() for col, _ in e)   # closed: no entry refers to a constrained dof
+        n_chain_cases += 1
         # auto_constraints = 1: solve_system computes the lines itself (reference :845) -- same answer
         ctx.assemble()
         z = np.zeros(m.n_nodes)

@@ -451,3 +451,39 @@ def test_internal_velocity_of_a_linear_potential_inside_a_cube():
     p = postproc.potential_at(m, phi, dphi, pts)
     assert np.abs(v - np.array([1.0, 0.0, 0.0])).max() < 2e-3
     assert np.abs(p - pts[:, 0]).max() < 2e-3
+
+
+def test_sparse_projection_restatement_matches_the_c_oracle_and_condenses_hanging_nodes(orc):
+    """oracle/projections.py (scipy.sparse, with hanging-node condensation) against orc_l2_projection on a
+    conforming mesh; on a locally refined FLAT patch the condensed projection of a linear field's gradient
+    is exact, and the hanging nodes end up on the mean of their masters (distribute())."""
+    from oracle import projections
+    from wavebem_b200 import meshgen
+    m = meshgen.wigley_tank(nxm=10, nt=5, nxu=4, nxd=5, nz=3, nzh=3, wave_amp=0.02)
+    f = np.cos(1.3 * m.xyz[:, 0]) + m.xyz[:, 1] * m.xyz[:, 2]
+    assert np.abs(projections.l2_projection(0, m.xyz, m.cells, m.dir_flag) -
+                  orc.compute_normals(m.xyz, m.cells, m.dir_flag)).max() < 1e-11
+    s = m.surface_nodes
+    assert np.abs(projections.l2_projection(1, m.xyz, m.cells, m.dir_flag, f * s) -
+                  orc.compute_surface_gradients(m.xyz, m.cells, m.dir_flag, f, s)).max() < 1e-10
+    # refine part of the (flat) bottom patch: hanging nodes on the interface
+    bottom = m.cell_patch == m.patch_names.index("bottom")
+    cx = m.xyz[m.cells.astype(int)].mean(axis=1)[:, 0]
+    r, hang = meshgen.refine_cells(m, bottom & (cx > np.median(cx[bottom])))
+    assert len(hang) > 0
+    lin = 0.7 * r.xyz[:, 0] - 0.2 * r.xyz[:, 1]            # linear in the plane of the bottom
+    g = projections.l2_projection(1, r.xyz, r.cells, r.dir_flag, lin, hanging=hang)
+    on_bottom = r.node_patch == r.patch_names.index("bottom")
+    assert np.abs(g[on_bottom] - np.array([0.7, -0.2, 0.0])).max() < 1e-10
+    nrm = projections.l2_projection(0, r.xyz, r.cells, r.dir_flag, hanging=hang)
+    assert np.abs(nrm[on_bottom] - nrm[on_bottom][0]).max() < 1e-12
+    # a curved patch (the hull): the constrained solution differs from the unconstrained one, and the
+    # hanging values are the mean of their masters before normalisation
+    hull = np.isin(m.cell_patch, m.meta["hull_patches"])
+    r2, hang2 = meshgen.refine_cells(m, hull & (cx > 0.2))
+    f2 = np.sin(2.0 * r2.xyz[:, 0]) + r2.xyz[:, 2]
+    gc = projections.l2_projection(1, r2.xyz, r2.cells, r2.dir_flag, f2, hanging=hang2)
+    gu = projections.l2_projection(1, r2.xyz, r2.cells, r2.dir_flag, f2)
+    h0, ent = hang2[0]
+    assert np.abs(gc[h0] - sum(w * gc[mm] for mm, w in ent)).max() < 1e-12
+    assert np.abs(gc - gu).max() > 1e-6

@@ -78,7 +78,7 @@ ABI_SYMBOLS = [
     "wbem_get_system_rhs", "wbem_get_sol", "wbem_get_timings", "wbem_reset_counters",
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
     "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
-    "wbem_timer_start", "wbem_timer_stop", "wbem_issue_probe", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
+    "wbem_timer_start", "wbem_timer_stop", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
     "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
     "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",
     "wbem_compute_constraints", "wbem_get_constraints", "wbem_mass_cg_iterations", "wbem_gmres",
@@ -460,11 +460,6 @@ class Context:
     def measure_fp64_peak(self):
         v = C.c_double(0)
         self._chk(lib().wbem_measure_fp64_peak(self._h, C.byref(v)))
-        return v.value
-
-    def issue_probe(self, n_int):
-        v = C.c_double(0)
-        self._chk(lib().wbem_issue_probe(self._h, int(n_int), C.byref(v)))
         return v.value
 
     def measure_copy_bw(self):

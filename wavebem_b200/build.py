@@ -68,6 +68,17 @@ def build_variant(tag: str, defines: list[str]) -> str:
     return lib
 
 
+def build_probes() -> str:
+    """lib/libwbem_probes.so: the FP64 issue-path micro-benchmarks (csrc/probes.cu) -- development only,
+    never loaded by the product."""
+    os.makedirs(OUT, exist_ok=True)
+    lib = os.path.join(OUT, "libwbem_probes.so")
+    src = os.path.join(CSRC, "probes.cu")
+    if _stale(lib, [src]):
+        subprocess.check_call([NVCC] + ARCH + FLAGS + ["-shared", src, "-o", lib])
+    return lib
+
+
 def build_cpp_test() -> str:
     """Compile tests/cpp/host_mirror_test.cc (the C++ host mirror of BEMProblem<3>) against libwbem.so."""
     build()
@@ -83,3 +94,5 @@ def build_cpp_test() -> str:
 
 if __name__ == "__main__":
     print(build(force="--force" in sys.argv, verbose=True, ptxas_info="--ptxas" in sys.argv))
+    if "--probes" in sys.argv:
+        print(build_probes())

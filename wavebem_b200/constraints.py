@@ -33,6 +33,33 @@ class ConstraintLines:
         return ConstraintLines(n, [], [0], [], [], [])
 
 
+def resolve_chains(lines):
+    """ConstraintMatrix::close() (bem_problem.cc:1104): an entry whose column is itself a constrained dof
+    is replaced by that dof's line (entries and inhomogeneity), until no line refers to a constrained
+    dof -- e.g. a flat double d1 -> i of a dof i that a sharp edge turns into an inhomogeneous line, or a
+    hanging node whose master is a double node.  Lines that needed no substitution are left as they are;
+    substituted lines get their entries merged and sorted by column."""
+    for _ in range(16):
+        changed = False
+        for d, (ent, ih) in list(lines.items()):
+            if not any(c in lines and c != d for c, _ in ent):
+                continue
+            acc = {}
+            for c, v in ent:
+                if c in lines and c != d:
+                    sub_ent, sub_ih = lines[c]
+                    for c2, v2 in sub_ent:
+                        acc[c2] = acc.get(c2, 0.0) + v * v2
+                    ih += v * sub_ih
+                else:
+                    acc[c] = acc.get(c, 0.0) + v
+            lines[d] = [sorted(acc.items()), ih]
+            changed = True
+        if not changed:
+            return
+    raise ValueError("constraint lines refer to each other in a cycle")
+
+
 def compute_constraints(dn_ptr, dn_idx, surface_nodes, tmp_rhs, nodes_normals=None,
                         node_surface_gradients=None, hanging=None):
     """Lines in the order deal.II's ConstraintMatrix would hold them after close() (sorted by
@@ -96,6 +123,7 @@ def compute_constraints(dn_ptr, dn_idx, surface_nodes, tmp_rhs, nodes_normals=No
                 add_line(d)
                 lines[d][0].append((i, 1.0))
 
+    resolve_chains(lines)
     keys = sorted(lines)
     ptr = [0]
     col, val, inhom = [], [], []

@@ -42,93 +42,6 @@ static int dev_upload(wbem_ctx *ctx, T **p, const std::vector<T> &v)
     }                   \
   while (0)
 
-// issue-port probe: 8 independent DFMA chains + NI integer/LDS-free ALU ops per iteration
-template <int NI>
-__global__ void k_issue_probe(double *out, int *iout, int iters)
-{
-  double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
-         a6 = a0 + 6, a7 = a0 + 7;
-  const double b = 1.0000001, c = 1e-7;
-  int x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3;
-  for (int i = 0; i < iters; ++i)
-    {
-      a0 = fma(a0, b, c);
-      a1 = fma(a1, b, c);
-      a2 = fma(a2, b, c);
-      a3 = fma(a3, b, c);
-      a4 = fma(a4, b, c);
-      a5 = fma(a5, b, c);
-      a6 = fma(a6, b, c);
-      a7 = fma(a7, b, c);
-#pragma unroll
-      for (int k = 0; k < NI; ++k)
-        {
-          if ((k & 3) == 0) x0 = (x0 ^ i) + 0x9e37;
-          if ((k & 3) == 1) x1 = (x1 ^ i) + 0x79b9;
-          if ((k & 3) == 2) x2 = (x2 ^ i) + 0x7f4a;
-          if ((k & 3) == 3) x3 = (x3 ^ i) + 0x7c15;
-        }
-    }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-  iout[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3;
-}
-
-
-// opcode probe: 8 independent chains of one FP64 opcode (0 DFMA, 1 DADD, 2 DMUL, 3 = 4 DFMA + 4 DADD)
-template <int OP>
-__global__ void k_opcode_probe(double *out, int iters)
-{
-  double a[8];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-9 + k;
-  const double b = 1.0000001, c = 1e-7;
-  for (int i = 0; i < iters; ++i)
-    {
-#pragma unroll
-      for (int k = 0; k < 8; ++k)
-        {
-          if (OP == 0 || (OP == 3 && (k & 1) == 0))
-            asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(b), "d"(c));
-          else if (OP == 1 || OP == 3)
-            asm volatile("add.rn.f64 %0, %0, %1;" : "+d"(a[k]) : "d"(c));
-          else
-            asm volatile("mul.rn.f64 %0, %0, %1;" : "+d"(a[k]) : "d"(b));
-        }
-    }
-  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
-}
-
-
-// DMMA probe: NF independent DFMA chains + NM independent m8n8k4 FP64 tensor-core MMAs per
-// iteration -- does the FP64 tensor pipe run beside the FP64 FMA pipe on this chip?
-template <int NF, int NM>
-__global__ void k_dmma_probe(double *out, int iters)
-{
-  double a[8], c0[4], c1[4];
-#pragma unroll
-  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-9 + k;
-#pragma unroll
-  for (int k = 0; k < 4; ++k) c0[k] = c1[k] = 0.0;
-  const double b = 1.0000001, c = 1e-7, ma = 1e-3 * (threadIdx.x & 3), mb = 1e-3 * (threadIdx.x >> 2);
-  for (int i = 0; i < iters; ++i)
-    {
-#pragma unroll
-      for (int k = 0; k < NF; ++k) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(b), "d"(c));
-#pragma unroll
-      for (int k = 0; k < NM; ++k)
-        asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                     : "+d"(c0[k]), "+d"(c1[k])
-                     : "d"(ma), "d"(mb));
-    }
-  double s = 0;
-#pragma unroll
-  for (int k = 0; k < 8; ++k) s += a[k];
-#pragma unroll
-  for (int k = 0; k < 4; ++k) s += c0[k] + c1[k];
-  out[blockIdx.x * blockDim.x + threadIdx.x] = s;
-}
-
-
 extern "C" {
 
 int wbem_version(void) { return 100; }
@@ -368,10 +281,32 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   ctx->nloc = ctx->row1 - ctx->row0;
   ctx->h_cell_dofs.assign(cell_dofs, cell_dofs + 4 * (size_t)C);
   ctx->h_dir.assign(cell_dir_flag, cell_dir_flag + C);
-  ctx->h_dn_ptr.assign(dn_ptr, dn_ptr + N + 1);
-  ctx->h_dn_idx.assign(dn_idx, dn_idx + dn_ptr[N]);
+  // double_nodes_set is a vector<set<unsigned>> in the reference (computational_domain.h:213): every set
+  // is sorted, duplicate-free and holds its own dof.  A flattened copy may not be: normalise it, so that
+  // a missing i cannot send the self-cells of row i through the regular rule, an empty set cannot be
+  // walked out of range and an unsorted one cannot change which dof compute_constraints picks first.
+  if (dn_ptr[0] != 0) WBEM_FAIL(ctx, -1, "dn_ptr[0] must be 0");
+  for (uint32_t i = 0; i < N; ++i)
+    if (dn_ptr[i + 1] < dn_ptr[i]) WBEM_FAIL(ctx, -1, "dn_ptr is not monotone at dof %u", i);
   for (uint32_t k = 0; k < dn_ptr[N]; ++k)
     if (dn_idx[k] >= N) WBEM_FAIL(ctx, -1, "double_nodes_set entry out of range");
+  ctx->h_dn_ptr.assign(N + 1, 0);
+  ctx->h_dn_idx.clear();
+  ctx->h_dn_idx.reserve((size_t)dn_ptr[N] + N);
+  {
+    std::vector<uint32_t> set;
+    for (uint32_t i = 0; i < N; ++i)
+      {
+        set.assign(dn_idx + dn_ptr[i], dn_idx + dn_ptr[i + 1]);
+        set.push_back(i);
+        std::sort(set.begin(), set.end());
+        set.erase(std::unique(set.begin(), set.end()), set.end());
+        ctx->h_dn_idx.insert(ctx->h_dn_idx.end(), set.begin(), set.end());
+        ctx->h_dn_ptr[i + 1] = (uint32_t)ctx->h_dn_idx.size();
+      }
+  }
+  dn_ptr = ctx->h_dn_ptr.data(); // from here on: the normalised sets
+  dn_idx = ctx->h_dn_idx.data();
 
   ctx->has_degenerate_cells = false;
   for (uint32_t c = 0; c < C && !ctx->has_degenerate_cells; ++c)
@@ -1262,6 +1197,21 @@ int wbem_comm_init(wbem_ctx *ctx, const void *id128)
 // ---------------------------------------------------------------------------------------
 // diagnostics
 // ---------------------------------------------------------------------------------------
+// eight independent DFMA chains written in PTX (the compiler cannot re-associate them)
+__global__ void k_dfma_chains(double *out, int iters)
+{
+  double a[8];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) a[k] = threadIdx.x * 1e-9 + k;
+  const double b = 1.0000001, c = 1e-7;
+  for (int i = 0; i < iters; ++i)
+    {
+#pragma unroll
+      for (int k = 0; k < 8; ++k) asm volatile("fma.rn.f64 %0, %0, %1, %2;" : "+d"(a[k]) : "d"(b), "d"(c));
+    }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = ((a[0] + a[1]) + (a[2] + a[3])) + ((a[4] + a[5]) + (a[6] + a[7]));
+}
+
 __global__ void k_dfma_peak(double *out, int iters)
 {
   double a0 = threadIdx.x * 1e-9, a1 = a0 + 1, a2 = a0 + 2, a3 = a0 + 3, a4 = a0 + 4, a5 = a0 + 5,
@@ -1279,53 +1229,6 @@ __global__ void k_dfma_peak(double *out, int iters)
       a7 = fma(a7, b, c);
     }
   out[blockIdx.x * blockDim.x + threadIdx.x] = ((a0 + a1) + (a2 + a3)) + ((a4 + a5) + (a6 + a7));
-}
-
-// diagnostic: DFMA TFLOP/s when n_int integer ALU ops are interleaved with every 8 DFMAs
-int wbem_issue_probe(wbem_ctx *ctx, int n_int, double *tflops)
-{
-  CHECK_CTX(ctx);
-  CUDA_OK(ctx, cudaSetDevice(ctx->dev));
-  const int blocks = 148 * 4, threads = 512, iters = 1 << 14;
-  double *d = nullptr;
-  int *di = nullptr;
-  CUDA_OK(ctx, cudaMalloc((void **)&d, sizeof(double) * blocks * threads));
-  CUDA_OK(ctx, cudaMalloc((void **)&di, sizeof(int) * blocks * threads));
-  cudaStream_t st = ctx->stream;
-  float best = 1e30f;
-  for (int rep = 0; rep < 4; ++rep)
-    {
-      CUDA_OK(ctx, cudaEventRecord(ctx->ev[8], st));
-      switch (n_int)
-        {
-        case 0: k_issue_probe<0><<<blocks, threads, 0, st>>>(d, di, iters); break;
-        case 2: k_issue_probe<2><<<blocks, threads, 0, st>>>(d, di, iters); break;
-        case 4: k_issue_probe<4><<<blocks, threads, 0, st>>>(d, di, iters); break;
-        case 8: k_issue_probe<8><<<blocks, threads, 0, st>>>(d, di, iters); break;
-        case 16: k_issue_probe<16><<<blocks, threads, 0, st>>>(d, di, iters); break;
-        case 100: k_opcode_probe<0><<<blocks, threads, 0, st>>>(d, iters); break; // DFMA only
-        case 101: k_opcode_probe<1><<<blocks, threads, 0, st>>>(d, iters); break; // DADD only
-        case 102: k_opcode_probe<2><<<blocks, threads, 0, st>>>(d, iters); break; // DMUL only
-        case 103: k_opcode_probe<3><<<blocks, threads, 0, st>>>(d, iters); break; // DFMA/DADD alternating
-        case 104: k_dmma_probe<0, 4><<<blocks, threads, 0, st>>>(d, iters); break; // 4 DMMA, no DFMA
-        case 105: k_dmma_probe<8, 1><<<blocks, threads, 0, st>>>(d, iters); break; // 8 DFMA + 1 DMMA
-        case 106: k_dmma_probe<8, 2><<<blocks, threads, 0, st>>>(d, iters); break; // 8 DFMA + 2 DMMA
-        case 107: k_dmma_probe<8, 0><<<blocks, threads, 0, st>>>(d, iters); break; // 8 DFMA (same loop)
-        default: cudaFree(d); cudaFree(di); WBEM_FAIL(ctx, -1, "n_int must be 0,2,4,8,16 or 100..107");
-        }
-      ctx->launches++;
-      CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], st));
-      CUDA_OK(ctx, cudaStreamSynchronize(st));
-      float ms = 0;
-      cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
-      if (rep >= 1 && ms < best) best = ms;
-    }
-  cudaFree(d);
-  cudaFree(di);
-  *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
-  // 104: report the tensor-pipe rate itself (4 MMAs of 8x8x4 FMAs per warp and iteration)
-  if (n_int == 104) *tflops = 2.0 * 4.0 * 256.0 * (double)iters * blocks * (threads / 32) / (best * 1e-3) / 1e12;
-  return 0;
 }
 
 int wbem_measure_fp64_peak(wbem_ctx *ctx, double *tflops)
@@ -1352,8 +1255,26 @@ int wbem_measure_fp64_peak(wbem_ctx *ctx, double *tflops)
   *tflops = 2.0 * 8.0 * (double)iters * blocks * threads / (best * 1e-3) / 1e12;
   // the hand-scheduled chain loop (inline PTX, 16 warps per SM) runs a little closer to the
   // pipe's 64 FMA/clk/SM: report the better of the two as the roofline denominator
-  double alt = 0;
-  if (wbem_issue_probe(ctx, 100, &alt) == 0 && alt > *tflops) *tflops = alt;
+  {
+    const int pb = 148 * 4, pt = 512, pit = 1 << 14;
+    double *d2 = nullptr;
+    CUDA_OK(ctx, cudaMalloc((void **)&d2, sizeof(double) * pb * pt));
+    float best2 = 1e30f;
+    for (int rep = 0; rep < 4; ++rep)
+      {
+        CUDA_OK(ctx, cudaEventRecord(ctx->ev[8], st));
+        k_dfma_chains<<<pb, pt, 0, st>>>(d2, pit);
+        ctx->launches++;
+        CUDA_OK(ctx, cudaEventRecord(ctx->ev[9], st));
+        CUDA_OK(ctx, cudaStreamSynchronize(st));
+        float ms = 0;
+        cudaEventElapsedTime(&ms, ctx->ev[8], ctx->ev[9]);
+        if (rep >= 1 && ms < best2) best2 = ms;
+      }
+    cudaFree(d2);
+    const double alt = 2.0 * 8.0 * (double)pit * pb * pt / (best2 * 1e-3) / 1e12;
+    if (alt > *tflops) *tflops = alt;
+  }
   return 0;
 }
 

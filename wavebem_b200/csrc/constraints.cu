@@ -75,6 +75,17 @@ struct ConState
   std::vector<uint32_t> master;
   std::vector<double> inhom;
   std::vector<double> h_rhs;       // pinned-size staging of tmp_rhs
+  std::vector<int32_t> line_of_tmp; // chain resolution scratch
+  // hanging-node lines inside the two projections (the reference condenses
+  // DoFTools::make_hanging_node_constraints(vector_dh) into both mass systems,
+  // source/computational_domain.cc:1535-1538, source/bem_problem.cc:1167-1170)
+  uint32_t nh = 0, nm = 0;
+  uint32_t *d_h_dof = nullptr, *d_hm_ptr = nullptr, *d_hm_col = nullptr; // hanging dof -> masters
+  double *d_hm_w = nullptr;
+  uint32_t *d_m_dof = nullptr, *d_mh_ptr = nullptr, *d_mh_h = nullptr;    // master -> hanging dofs
+  double *d_mh_w = nullptr;
+  uint8_t *d_hflag = nullptr;                                             // [N] 1 on hanging dofs
+  bool hang_uploaded = false;
 };
 
 static ConState *con_state(wbem_ctx *ctx)
@@ -89,7 +100,9 @@ void wbem_constraints_free(wbem_ctx *ctx)
   if (!s) return;
   void *ptrs[] = {s->d_cells, s->d_dir,  s->d_nc_ptr, s->d_nc_cell, s->d_nc_local, s->d_nc_pos, s->d_mcol,
                   s->d_mval,  s->d_diag, s->d_b,      s->d_x,       s->d_r,        s->d_p,      s->d_ap,
-                  s->d_part,  s->d_barrier, s->d_iters, s->d_normals, s->d_grads,  s->d_phi};
+                  s->d_part,  s->d_barrier, s->d_iters, s->d_normals, s->d_grads,  s->d_phi,
+                  s->d_h_dof, s->d_hm_ptr, s->d_hm_col, s->d_hm_w, s->d_m_dof, s->d_mh_ptr, s->d_mh_h, s->d_mh_w,
+                  s->d_hflag};
   for (void *p : ptrs)
     if (p) cudaFree(p);
   delete s;
@@ -258,12 +271,56 @@ __device__ __forceinline__ void cta_sum3(double v[3], double (*red)[3])
   __syncthreads();
 }
 
-// Jacobi-preconditioned CG on M x_d = b_d, d = 0..2, in lock step (cooperative launch).
+struct HangArgs
+{ // hanging-node lines x_h = sum_k w_k x_m(k) and their transpose (nh = 0: none)
+  uint32_t nh, nm;
+  const uint32_t *h_dof, *hm_ptr, *hm_col;
+  const double *hm_w;
+  const uint32_t *m_dof, *mh_ptr, *mh_h;
+  const double *mh_w;
+  const uint8_t *hflag;
+};
+
+// b_m += sum_h w_hm b_h, b_h = 0 (the condensed right-hand side C^T b); with_diag: the same fold of the
+// Jacobi diagonal (w^2 weights; the preconditioner need not be exact) and a unit diagonal on hanging dofs
+__global__ void k_con_fold(uint32_t N, HangArgs H, double *__restrict__ b, double *__restrict__ diag, int with_diag)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= H.nm) return;
+  const uint32_t m = H.m_dof[k];
+  double a0 = 0, a1 = 0, a2 = 0, dg = 0;
+  for (uint32_t e = H.mh_ptr[k]; e < H.mh_ptr[k + 1]; ++e)
+    {
+      const uint32_t h = H.mh_h[e];
+      const double w = H.mh_w[e];
+      a0 += w * b[h];
+      a1 += w * b[(size_t)N + h];
+      a2 += w * b[2 * (size_t)N + h];
+      dg += w * w * diag[h];
+    }
+  b[m] += a0;
+  b[(size_t)N + m] += a1;
+  b[2 * (size_t)N + m] += a2;
+  if (with_diag) diag[m] += dg;
+}
+__global__ void k_con_zero_hanging(uint32_t N, HangArgs H, double *__restrict__ b, double *__restrict__ diag, int with_diag)
+{
+  const uint32_t k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= H.nh) return;
+  const uint32_t h = H.h_dof[k];
+  b[h] = b[(size_t)N + h] = b[2 * (size_t)N + h] = 0.0;
+  if (with_diag) diag[h] = 1.0;
+}
+
+// Jacobi-preconditioned CG on M x_d = b_d, d = 0..2, in lock step (cooperative launch).  With hanging
+// nodes the operator is the condensed C^T M C: p is expanded to the hanging dofs before the product and
+// the product's hanging rows are folded into their masters after it; x then holds C x_free, i.e. the
+// distributed solution (ConstraintMatrix::distribute), without a separate pass.
 __global__ void __launch_bounds__(CG_THREADS, 1)
   k_mass_cg(uint32_t N, uint32_t MW, const uint32_t *__restrict__ mcol, const double *__restrict__ mval,
             const double *__restrict__ diag, const double *__restrict__ b, double *__restrict__ x,
-            double *__restrict__ r, double *p, double *__restrict__ ap, double *part,
-            unsigned int *barrier, int *iters_out, double rtol, int max_iters)
+            double *__restrict__ r, double *p, double *ap, double *part,
+            unsigned int *barrier, int *iters_out, double rtol, int max_iters, const HangArgs H)
 {
   __shared__ double red[CG_THREADS / 32][3];
   __shared__ double s_tot[3];
@@ -311,6 +368,17 @@ __global__ void __launch_bounds__(CG_THREADS, 1)
       bool done = true;
       for (int d = 0; d < 3; ++d) done &= !(rz[d] > rtol * rtol * rz0[d]);
       if (done) break; // uniform: every CTA holds the same rz
+      if (H.nh)
+        { // expand: p_h = sum w p_m
+          for (uint32_t k = t0; k < H.nh; k += nthreads)
+            {
+              double e[3] = {0, 0, 0};
+              for (uint32_t q = H.hm_ptr[k]; q < H.hm_ptr[k + 1]; ++q)
+                for (int d = 0; d < 3; ++d) e[d] = fma(H.hm_w[q], __ldcg(p + (size_t)d * N + H.hm_col[q]), e[d]);
+              for (int d = 0; d < 3; ++d) p[(size_t)d * N + H.h_dof[k]] = e[d];
+            }
+          con_grid_barrier(barrier, epoch);
+        }
       // ap = M p, pAp
       double l2[3] = {0, 0, 0};
       for (uint32_t i = t0; i < N; i += nthreads)
@@ -329,6 +397,22 @@ __global__ void __launch_bounds__(CG_THREADS, 1)
               l2[d] = fma(s[d], p[(size_t)d * N + i], l2[d]);
             }
         }
+      if (H.nh)
+        { // fold the hanging rows into their masters, then p.(C^T M C p) over the free dofs
+          con_grid_barrier(barrier, epoch);
+          for (uint32_t k = t0; k < H.nm; k += nthreads)
+            {
+              double e[3] = {0, 0, 0};
+              for (uint32_t q = H.mh_ptr[k]; q < H.mh_ptr[k + 1]; ++q)
+                for (int d = 0; d < 3; ++d) e[d] = fma(H.mh_w[q], __ldcg(ap + (size_t)d * N + H.mh_h[q]), e[d]);
+              for (int d = 0; d < 3; ++d) ap[(size_t)d * N + H.m_dof[k]] += e[d];
+            }
+          con_grid_barrier(barrier, epoch);
+          for (int d = 0; d < 3; ++d) l2[d] = 0.0;
+          for (uint32_t i = t0; i < N; i += nthreads)
+            if (!H.hflag[i])
+              for (int d = 0; d < 3; ++d) l2[d] = fma(__ldcg(ap + (size_t)d * N + i), p[(size_t)d * N + i], l2[d]);
+        }
       cta_sum3(l2, red);
       if (threadIdx.x == 0)
         for (int d = 0; d < 3; ++d) part1[(size_t)blockIdx.x * 3 + d] = l2[d];
@@ -345,7 +429,7 @@ __global__ void __launch_bounds__(CG_THREADS, 1)
             {
               const size_t o = (size_t)d * N + i;
               x[o] = fma(alpha[d], p[o], x[o]);
-              const double rn = fma(-alpha[d], ap[o], r[o]);
+              const double rn = (H.nh && H.hflag[i]) ? 0.0 : fma(-alpha[d], __ldcg(ap + o), r[o]);
               r[o] = rn;
               l3[d] = fma(rn * di, rn, l3[d]);
             }
@@ -498,6 +582,85 @@ static int con_prepare(wbem_ctx *ctx)
   return 0;
 }
 
+static HangArgs con_hang_args(const ConState *s)
+{
+  HangArgs H;
+  H.nh = s->nh;
+  H.nm = s->nm;
+  H.h_dof = s->d_h_dof;
+  H.hm_ptr = s->d_hm_ptr;
+  H.hm_col = s->d_hm_col;
+  H.hm_w = s->d_hm_w;
+  H.m_dof = s->d_m_dof;
+  H.mh_ptr = s->d_mh_ptr;
+  H.mh_h = s->d_mh_h;
+  H.mh_w = s->d_mh_w;
+  H.hflag = s->d_hflag;
+  return H;
+}
+
+// the caller's hanging-node lines (wbem_set_hanging_constraints), flattened for the projections
+static int con_upload_hanging(wbem_ctx *ctx)
+{
+  ConState *s = con_state(ctx);
+  if (s->hang_uploaded) return 0;
+  const uint32_t N = ctx->N;
+  const uint32_t nh = (uint32_t)s->base_lines.size();
+  s->nh = nh;
+  s->nm = 0;
+  if (nh)
+    {
+      std::vector<uint8_t> flag(N, 0);
+      for (uint32_t h : s->base_lines) flag[h] = 1;
+      for (uint32_t c : s->base_col)
+        if (flag[c]) WBEM_FAIL(ctx, -1, "hanging-node lines refer to hanging nodes (more than one refinement level across an edge)");
+      std::vector<std::vector<std::pair<uint32_t, double>>> tr(N);
+      for (uint32_t k = 0; k < nh; ++k)
+        for (uint32_t e = s->base_ptr[k]; e < s->base_ptr[k + 1]; ++e) tr[s->base_col[e]].emplace_back(s->base_lines[k], s->base_val[e]);
+      std::vector<uint32_t> m_dof, mh_ptr(1, 0), mh_h;
+      std::vector<double> mh_w;
+      for (uint32_t m = 0; m < N; ++m)
+        if (!tr[m].empty())
+          {
+            m_dof.push_back(m);
+            for (auto &pr : tr[m])
+              {
+                mh_h.push_back(pr.first);
+                mh_w.push_back(pr.second);
+              }
+            mh_ptr.push_back((uint32_t)mh_h.size());
+          }
+      s->nm = (uint32_t)m_dof.size();
+      int rc;
+      if ((rc = con_upload(ctx, &s->d_h_dof, s->base_lines))) return rc;
+      if ((rc = con_upload(ctx, &s->d_hm_ptr, s->base_ptr))) return rc;
+      if ((rc = con_upload(ctx, &s->d_hm_col, s->base_col))) return rc;
+      if ((rc = con_upload(ctx, &s->d_hm_w, s->base_val))) return rc;
+      if ((rc = con_upload(ctx, &s->d_m_dof, m_dof))) return rc;
+      if ((rc = con_upload(ctx, &s->d_mh_ptr, mh_ptr))) return rc;
+      if ((rc = con_upload(ctx, &s->d_mh_h, mh_h))) return rc;
+      if ((rc = con_upload(ctx, &s->d_mh_w, mh_w))) return rc;
+      if ((rc = con_upload(ctx, &s->d_hflag, flag))) return rc;
+      CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+    }
+  s->hang_uploaded = true;
+  s->mass_geom_version = s->normals_geom_version = ~0ull; // the condensed systems changed
+  return 0;
+}
+
+// condense the right-hand sides in d_b (and, after a new mass matrix, the Jacobi diagonal)
+static int con_condense(wbem_ctx *ctx, int with_diag)
+{
+  ConState *s = con_state(ctx);
+  if (!s->nh) return 0;
+  const HangArgs H = con_hang_args(s);
+  k_con_fold<<<(s->nm + 127) / 128, 128, 0, ctx->stream>>>(s->N, H, s->d_b, s->d_diag, with_diag);
+  k_con_zero_hanging<<<(s->nh + 127) / 128, 128, 0, ctx->stream>>>(s->N, H, s->d_b, s->d_diag, with_diag);
+  ctx->launches += 2;
+  CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
 static int con_mass(wbem_ctx *ctx)
 { // mass matrix + normal rhs for the current geometry (left in d_b)
   ConState *s = con_state(ctx);
@@ -508,7 +671,7 @@ static int con_mass(wbem_ctx *ctx)
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   s->mass_geom_version = ctx->geom_version;
-  return 0;
+  return con_condense(ctx, 1);
 }
 
 static int con_solve3(wbem_ctx *ctx)
@@ -519,8 +682,9 @@ static int con_solve3(wbem_ctx *ctx)
   uint32_t N = s->N, MW = s->MW;
   double rtol = CG_RTOL;
   int max_iters = CG_MAX_ITERS;
+  HangArgs H = con_hang_args(s);
   void *args[] = {&N,       &MW,      &s->d_mcol, &s->d_mval, &s->d_diag,    &s->d_b,     &s->d_x,  &s->d_r,
-                  &s->d_p,  &s->d_ap, &s->d_part, &s->d_barrier, &s->d_iters, &rtol,      &max_iters};
+                  &s->d_p,  &s->d_ap, &s->d_part, &s->d_barrier, &s->d_iters, &rtol,      &max_iters, &H};
   CUDA_OK(ctx, cudaLaunchCooperativeKernel((void *)k_mass_cg, dim3(s->grid), dim3(CG_THREADS), args, 0, st));
   ctx->launches++;
   return 0;
@@ -530,6 +694,7 @@ static int con_normals(wbem_ctx *ctx)
 {
   int rc = con_prepare(ctx);
   if (rc) return rc;
+  if ((rc = con_upload_hanging(ctx))) return rc;
   ConState *s = con_state(ctx);
   if (s->normals_geom_version == ctx->geom_version) return 0;
   if ((rc = con_mass(ctx))) return rc;
@@ -549,6 +714,7 @@ static int con_gradients(wbem_ctx *ctx, const double *d_tmp_rhs)
 {
   int rc = con_prepare(ctx);
   if (rc) return rc;
+  if ((rc = con_upload_hanging(ctx))) return rc;
   ConState *s = con_state(ctx);
   if (!ctx->have_masks) WBEM_FAIL(ctx, -3, "surface gradients need the masks (wbem_set_masks)");
   cudaStream_t st = ctx->stream;
@@ -561,6 +727,7 @@ static int con_gradients(wbem_ctx *ctx, const double *d_tmp_rhs)
                                                     s->d_nc_local, s->d_phi, s->d_b);
   ctx->launches += 2;
   CUDA_OK(ctx, cudaGetLastError());
+  if ((rc = con_condense(ctx, 0))) return rc;
   if ((rc = con_solve3(ctx))) return rc;
   k_interleave3<<<(s->N + 255) / 256, 256, 0, st>>>(s->N, s->d_x, s->d_grads, 0);
   ctx->launches++;
@@ -718,6 +885,70 @@ int wbem_compute_constraints_device(wbem_ctx *ctx, const double *d_tmp_rhs)
       if (dm == i) ++im;
       if (db == i) ++ib;
     }
+  // ConstraintMatrix::close() (:1104): entries that refer to a constrained dof are replaced by that
+  // dof's line until none is left (a flat double of a dof that a sharp edge made inhomogeneous; a hanging
+  // node whose master is a double node).  Lines that need no substitution keep their entries as they are.
+  {
+    std::vector<int32_t> &line_of = s->line_of_tmp;
+    line_of.assign(N, -1);
+    const size_t nl = s->out_lines.size();
+    for (size_t k = 0; k < nl; ++k) line_of[s->out_lines[k]] = (int32_t)k;
+    bool any = false;
+    for (size_t k = 0; k < s->out_col.size() && !any; ++k) any = line_of[s->out_col[k]] >= 0;
+    for (int pass = 0; any && pass < 16; ++pass)
+      {
+        any = false;
+        std::vector<uint32_t> nptr(1, 0), ncol;
+        std::vector<double> nval, ninh(s->out_inhom);
+        std::vector<std::pair<uint32_t, double>> acc;
+        for (size_t k = 0; k < nl; ++k)
+          {
+            bool sub = false;
+            for (uint32_t e = s->out_ptr[k]; e < s->out_ptr[k + 1]; ++e)
+              sub |= line_of[s->out_col[e]] >= 0 && s->out_col[e] != s->out_lines[k];
+            if (!sub)
+              {
+                ncol.insert(ncol.end(), s->out_col.begin() + s->out_ptr[k], s->out_col.begin() + s->out_ptr[k + 1]);
+                nval.insert(nval.end(), s->out_val.begin() + s->out_ptr[k], s->out_val.begin() + s->out_ptr[k + 1]);
+              }
+            else
+              {
+                any = true;
+                acc.clear();
+                for (uint32_t e = s->out_ptr[k]; e < s->out_ptr[k + 1]; ++e)
+                  {
+                    const uint32_t c = s->out_col[e];
+                    const double v = s->out_val[e];
+                    const int32_t L = c != s->out_lines[k] ? line_of[c] : -1;
+                    if (L < 0)
+                      acc.emplace_back(c, v);
+                    else
+                      {
+                        for (uint32_t e2 = s->out_ptr[L]; e2 < s->out_ptr[L + 1]; ++e2)
+                          acc.emplace_back(s->out_col[e2], v * s->out_val[e2]);
+                        ninh[k] += v * s->out_inhom[L];
+                      }
+                  }
+                std::stable_sort(acc.begin(), acc.end(), [](const std::pair<uint32_t, double> &x, const std::pair<uint32_t, double> &y) { return x.first < y.first; });
+                for (size_t a2 = 0; a2 < acc.size();)
+                  {
+                    double v = 0;
+                    size_t b2 = a2;
+                    for (; b2 < acc.size() && acc[b2].first == acc[a2].first; ++b2) v += acc[b2].second;
+                    ncol.push_back(acc[a2].first);
+                    nval.push_back(v);
+                    a2 = b2;
+                  }
+              }
+            nptr.push_back((uint32_t)ncol.size());
+          }
+        s->out_ptr.swap(nptr);
+        s->out_col.swap(ncol);
+        s->out_val.swap(nval);
+        s->out_inhom.swap(ninh);
+        if (pass == 15 && any) WBEM_FAIL(ctx, -1, "constraint lines refer to each other in a cycle");
+      }
+  }
   return wbem_set_constraints(ctx, (uint32_t)s->out_lines.size(), s->out_lines.data(), s->out_ptr.data(),
                               s->out_col.data(), s->out_val.data(), s->out_inhom.data());
 }
@@ -765,6 +996,7 @@ int wbem_set_hanging_constraints(wbem_ctx *ctx, uint32_t n_lines, const uint32_t
   if (n_lines) s->base_ptr.assign(ptr, ptr + n_lines + 1);
   s->base_col.assign(col, col + nnz);
   s->base_val.assign(val, val + nnz);
+  s->hang_uploaded = false; // the projections condense these lines into their mass systems
   return 0;
 }
 

@@ -312,8 +312,19 @@ int wbem_build_preconditioner(wbem_ctx *ctx)
   int rc = wbem_allgather_bytes(ctx, ctx->d_band, sizeof(double) * (size_t)ctx->chunk * band);
   if (rc) return rc;
 
-  // host factorisation (precond_on_host) -- the device variant lives in precond.cu
-  if (ctx->p.precond_on_host)
+  // the device variant (precond.cu) pivots inside 64 x 64 diagonal blocks only; the reference's sparse
+  // LU pivots across the whole band.  Should a diagonal / Schur block come out singular there, this
+  // factorisation falls back to the pivoted band LU on the host instead of failing the solve.
+  ctx->precond_host_active = ctx->p.precond_on_host != 0;
+  if (!ctx->precond_host_active)
+    {
+      rc = wbem_device_precond_factor(ctx);
+      if (rc == -6)
+        ctx->precond_host_active = true;
+      else if (rc)
+        return rc;
+    }
+  if (ctx->precond_host_active)
     {
       std::vector<double> hb((size_t)N * band);
       CUDA_OK(ctx, cudaMemcpyAsync(hb.data(), ctx->d_band, sizeof(double) * (size_t)N * band,
@@ -341,11 +352,6 @@ int wbem_build_preconditioner(wbem_ctx *ctx)
       ctx->h_ku = B.ku;
       ctx->h_ldab = B.ld;
     }
-  else
-    {
-      rc = wbem_device_precond_factor(ctx);
-      if (rc) return rc;
-    }
   ctx->precond_ready = true;
   ctx->precond_version = ctx->op_version;
   return 0;
@@ -363,7 +369,7 @@ int wbem_apply_preconditioner(wbem_ctx *ctx, const double *d_in, double *d_out)
     }
   if (!ctx->precond_ready) WBEM_FAIL(ctx, -3, "preconditioner applied before it was assembled");
   if (ctx->p.precond_kind == 1) return wbem_spai_apply(ctx, d_in, d_out);
-  if (ctx->p.precond_on_host)
+  if (ctx->precond_host_active)
     {
       CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_pinned, d_in, sizeof(double) * N, cudaMemcpyDeviceToHost, st));
       CUDA_OK(ctx, cudaStreamSynchronize(st));
@@ -510,19 +516,17 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
       if (!(rho == rho)) state = 2;
       if (state != 0) break;
       gamma[0] = rho;
-      k_scale<<<nb, 256, 0, st>>>(N, v0, 1.0 / rho);
-      ctx->launches++;
+      // the normalisation of the newest Krylov vector is folded into the mat-vec that consumes it
+      // (k_prep_multipliers scales it in place); the last vector of a cycle is never used again
+      double pending_scale = 1.0 / rho;
       int dim = 0;
       for (int inner = 0; inner < m && state == 0; ++inner)
         {
           ++accumulated;
           double *vv = V + (size_t)(inner + 1) * ldv;
-          rc = wbem_apply_operator(ctx, 0, V + (size_t)inner * ldv, p, true);
+          // vv = M^-1 (A V[inner]): operator, its epilogue and the preconditioner
+          rc = wbem_apply_operator_ex(ctx, 0, V + (size_t)inner * ldv, vv, true, pending_scale, V + (size_t)inner * ldv, true);
           ++n_gemv;
-          if (rc) return rc;
-          g_timer.begin(T_PRECOND_APPLY);
-          rc = wbem_apply_preconditioner(ctx, p, vv);
-          g_timer.end();
           if (rc) return rc;
           dim = inner + 1;
           // CGS2
@@ -540,9 +544,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
           double ss = 0;
           for (unsigned i = 0; i < nb128; ++i) ss += hp[i];
           h[dim] = std::sqrt(ss);
-          const double s = h[dim];
-          k_scale<<<nb, 256, 0, st>>>(N, vv, 1.0 / s);
-          ctx->launches++;
+          pending_scale = 1.0 / h[dim];
           givens(h, gamma, ci, si, inner);
           for (int i = 0; i < dim; ++i) H[(size_t)i * ntmp + inner] = h[i];
           rho = std::fabs(gamma[dim]);

@@ -194,6 +194,7 @@ struct wbem_ctx
   std::vector<int> h_piv;
   int h_kl = 0, h_ku = 0, h_ldab = 0;
   bool precond_ready = false;
+  bool precond_host_active = false; // this factorisation lives on the host (precond_on_host, or the device fallback)
   void *dev_precond = nullptr;  // precond.cu state
   void *spai = nullptr;         // spai.cu state (precond_kind = 1)
   void *con = nullptr;          // constraints.cu state (compute_constraints on the device)
@@ -253,6 +254,20 @@ uint32_t wbem_tile_width(void);
 // operator.cu
 int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double *d_src,
                         double *d_dst, bool constrained);
+int wbem_apply_operator_ex(wbem_ctx *ctx, int mode, const double *d_src, double *d_dst, bool constrained, double src_scale,
+                           double *src_scale_rw, bool with_precond);
+struct EpilogueArgs
+{ // what k_epilogue needs to turn the gathered mat-vec rows into ConstrainedOperator::vmult's result
+  const double *y, *src;
+  const int32_t *line_of;
+  const uint32_t *cptr, *ccol;
+  const double *cval;
+  const unsigned long long *flags; // fused gather: one arrival flag per rank (null: nothing to wait for)
+  int n_peers;
+  unsigned long long epoch;
+  unsigned int *timeout_flag;
+};
+int wbem_spai_apply_fused(wbem_ctx *ctx, const EpilogueArgs &ea, double *d_out);
 int wbem_apply_operator_multi(wbem_ctx *ctx, int mode, int nb, const double *const *d_src, double *const *d_dst,
                               bool constrained);
 int wbem_allgather_rows(wbem_ctx *ctx, double *d_buf /* [chunk*world], own block filled */);

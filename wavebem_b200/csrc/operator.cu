@@ -211,15 +211,25 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
     }
 }
 
-// multipliers: x1p[colpos[i]] = m1[i] src[i], x2p[colpos[i]] = m2[i] src[i], xdiag[i] = m1[i] src[i]
+// multipliers: x1p[colpos[i]] = m1[i] src[i], x2p[colpos[i]] = m2[i] src[i], xdiag[i] = m1[i] src[i].
+// src_rw != null: the source vector is first scaled in place (the normalisation of the newest Krylov
+// vector, folded into the mat-vec that consumes it)
 __global__ void k_prep_multipliers(uint32_t N, const double *__restrict__ src,
                                    const double *__restrict__ m1, const double *__restrict__ m2,
                                    const uint32_t *__restrict__ colpos, double *__restrict__ x1p,
-                                   double *__restrict__ x2p, double *__restrict__ xdiag)
+                                   double *__restrict__ x2p, double *__restrict__ xdiag, double scale = 1.0,
+                                   double *src_rw = nullptr)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
-  const double s = src[i];
+  double s;
+  if (src_rw)
+    {
+      s = src_rw[i] * scale;
+      src_rw[i] = s;
+    }
+  else
+    s = src[i];
   const double a = m1[i] * s, b = m2[i] * s;
   const uint32_t c = colpos[i];
   x1p[c] = a;
@@ -332,8 +342,16 @@ int wbem_check_gather_timeout(wbem_ctx *ctx)
 
 // chunk lists (see header comment): d_list_o = chunks with any other_nodes != 0, d_list_s =
 // chunks with any surface_nodes != 0, in storage-column order; built by wbem_set_masks.
-int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_dst,
-                        bool constrained)
+int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_dst, bool constrained)
+{
+  return wbem_apply_operator_ex(ctx, mode, d_src, d_dst, constrained, 1.0, nullptr, false);
+}
+
+// src_scale_rw != null: scale that vector in place by src_scale first (it is d_src).
+// with_precond: d_dst = M^-1 (operator d_src) -- for the sparse approximate inverse the operator's
+// epilogue and the preconditioner are ONE kernel (wbem_spai_apply_fused), else they run one after the other.
+int wbem_apply_operator_ex(wbem_ctx *ctx, int mode, const double *d_src, double *d_dst, bool constrained, double src_scale,
+                           double *src_scale_rw, bool with_precond)
 {
   cudaStream_t st = ctx->stream;
   const uint32_t N = ctx->N;
@@ -345,7 +363,7 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
   const double *m1 = mode == 0 ? ctx->d_other : ctx->d_surf; // multiplier mask of N
   const double *m2 = mode == 0 ? ctx->d_surf : ctx->d_other; // multiplier mask of D
   k_prep_multipliers<<<(N + 255) / 256, 256, 0, st>>>(N, d_src, m1, m2, ctx->d_colpos, ctx->d_xn,
-                                                     ctx->d_xd, ctx->d_xdiag);
+                                                     ctx->d_xd, ctx->d_xdiag, src_scale, src_scale_rw);
   ctx->launches++;
   double *yloc = ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk;
   const int P = ctx->p.world_size;
@@ -439,12 +457,30 @@ int wbem_apply_operator(wbem_ctx *ctx, int mode, const double *d_src, double *d_
       ctx->launches++;
     }
   const bool con = constrained && ctx->n_lines > 0;
-  k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(
-    N, ygather, d_src, con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr, ctx->d_con_col, ctx->d_con_val, 0.0, d_dst,
-    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_half) : nullptr, P, ctx->p2p_epoch,
-    ctx->d_gather_timeout);
+  const unsigned long long *flags =
+    use_p2p ? reinterpret_cast<const unsigned long long *>(ctx->d_p2p + 2 * p2p_half) : nullptr;
+  if (with_precond && ctx->p.precond_kind == 1 && ctx->p.preconditioner_band > 0)
+    { // epilogue (gather wait, constrained rows) + sparse approximate inverse in one kernel
+      EpilogueArgs ea;
+      ea.y = ygather;
+      ea.src = d_src;
+      ea.line_of = con ? ctx->d_con_line_of : nullptr;
+      ea.cptr = ctx->d_con_ptr;
+      ea.ccol = ctx->d_con_col;
+      ea.cval = ctx->d_con_val;
+      ea.flags = flags;
+      ea.n_peers = P;
+      ea.epoch = ctx->p2p_epoch;
+      ea.timeout_flag = ctx->d_gather_timeout;
+      return wbem_spai_apply_fused(ctx, ea, d_dst);
+    }
+  double *d_mid = with_precond ? ctx->d_tmp[0] : d_dst;
+  k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(N, ygather, d_src, con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr,
+                                             ctx->d_con_col, ctx->d_con_val, 0.0, d_mid, flags, P, ctx->p2p_epoch,
+                                             ctx->d_gather_timeout);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
+  if (with_precond) return wbem_apply_preconditioner(ctx, d_mid, d_dst);
   return 0;
 }
 

@@ -367,6 +367,72 @@ __global__ void __launch_bounds__(256)
   if (i < N && part == 0) z[i] = s;
 }
 
+// The same product with v = ConstrainedOperator::vmult's result taken straight from the gathered
+// mat-vec rows: v_j = y_j, or src_j - sum_k c_jk src_k on a constrained row
+// (include/constrained_matrix.h:73-86) -- the operator's epilogue and the preconditioner in ONE kernel.
+__device__ __forceinline__ double epi_value(const EpilogueArgs &e, uint32_t j)
+{
+  if (e.line_of)
+    {
+      const int l = e.line_of[j];
+      if (l >= 0)
+        {
+          double v = e.src[j];
+          for (uint32_t k = e.cptr[l]; k < e.cptr[l + 1]; ++k) v -= e.cval[k] * e.src[e.ccol[k]];
+          return v;
+        }
+    }
+  return e.y[j];
+}
+
+__global__ void __launch_bounds__(256)
+  k_spai_apply_fused(uint32_t N, const uint32_t *__restrict__ nbr, const double *__restrict__ val, const EpilogueArgs e,
+                     double *__restrict__ z)
+{
+  if (e.flags)
+    { // fused gather: wait (bounded) until every rank has delivered its rows of this epoch
+      if ((int)threadIdx.x < e.n_peers)
+        {
+          unsigned long long v, t0 = 0, t1;
+          unsigned int spins = 0;
+          for (;;)
+            {
+              asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(e.flags + threadIdx.x) : "memory");
+              if (v >= e.epoch) break;
+              if ((++spins & 0x3ffu) == 0)
+                {
+                  asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t1));
+                  if (!t0) t0 = t1;
+                  if (t1 - t0 > 20000000000ull)
+                    {
+                      atomicExch(e.timeout_flag, 1u);
+                      break;
+                    }
+                }
+            }
+        }
+      __syncthreads();
+    }
+  const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+  const uint32_t i = t >> 3, part = t & 7;
+  double s = 0.0;
+  if (i < N)
+    {
+      const uint4 c = reinterpret_cast<const uint4 *>(nbr + (size_t)i * SPAI_K)[part];
+      const double2 m0 = reinterpret_cast<const double2 *>(val + (size_t)i * SPAI_K)[2 * part];
+      const double2 m1 = reinterpret_cast<const double2 *>(val + (size_t)i * SPAI_K)[2 * part + 1];
+      const double a0 = c.x != SPAI_NONE ? m0.x * epi_value(e, c.x) : 0.0;
+      const double a1 = c.y != SPAI_NONE ? m0.y * epi_value(e, c.y) : 0.0;
+      const double a2 = c.z != SPAI_NONE ? m1.x * epi_value(e, c.z) : 0.0;
+      const double a3 = c.w != SPAI_NONE ? m1.y * epi_value(e, c.w) : 0.0;
+      s = (a0 + a1) + (a2 + a3);
+    }
+  s += __shfl_xor_sync(0xffffffffu, s, 1);
+  s += __shfl_xor_sync(0xffffffffu, s, 2);
+  s += __shfl_xor_sync(0xffffffffu, s, 4);
+  if (i < N && part == 0) z[i] = s;
+}
+
 // ---------------------------------------------------------------------------------------
 // host side
 // ---------------------------------------------------------------------------------------
@@ -469,6 +535,17 @@ int wbem_spai_apply(wbem_ctx *ctx, const double *d_in, double *d_out)
   if (!s || !s->pattern_ready) WBEM_FAIL(ctx, -3, "SPAI preconditioner applied before it was assembled");
   if (d_in == d_out) WBEM_FAIL(ctx, -1, "the sparse approximate inverse cannot be applied in place");
   k_spai_apply<<<(unsigned)(((size_t)ctx->N * 8 + 255) / 256), 256, 0, ctx->stream>>>(ctx->N, s->d_nbr, s->d_val, d_in, d_out);
+  ctx->launches++;
+  CUDA_OK(ctx, cudaGetLastError());
+  return 0;
+}
+
+int wbem_spai_apply_fused(wbem_ctx *ctx, const EpilogueArgs &ea, double *d_out)
+{
+  SpaiState *s = reinterpret_cast<SpaiState *>(ctx->spai);
+  if (!s || !s->pattern_ready || !ctx->precond_ready) WBEM_FAIL(ctx, -3, "SPAI preconditioner applied before it was assembled");
+  k_spai_apply_fused<<<(unsigned)(((size_t)ctx->N * 8 + 255) / 256), 256, 0, ctx->stream>>>(ctx->N, s->d_nbr, s->d_val, ea,
+                                                                                           d_out);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return 0;

@@ -366,3 +366,78 @@ def towing_tank_bc(mesh: SurfaceMesh, froude=0.28, g=9.81):
     hull = np.isin(mesh.node_patch, mesh.meta["hull_patches"])
     bc[hull] = -(nn[hull] @ vinf)
     return bc
+
+
+# ----------------------------------------------------------------------------------------
+# local refinement with hanging nodes
+# ----------------------------------------------------------------------------------------
+def refine_cells(mesh: SurfaceMesh, cell_mask):
+    """Split the marked cells into four children each (one level of deal.II's isotropic refinement of a
+    quad).  Edge midpoints shared by two marked cells become ordinary dofs; a midpoint on an edge whose
+    other cell stays coarse is a HANGING node, constrained to the mean of the edge's two vertices
+    (DoFTools::make_hanging_node_constraints for FE_Q(1), reference source/bem_problem.cc:1000 and
+    source/computational_domain.cc:1535-1538).  New nodes sit on the parent's bilinear map.
+    Returns (refined mesh, hanging), hanging = [(dof, [(master, 0.5), (master, 0.5)]), ...]."""
+    cell_mask = np.asarray(cell_mask, dtype=bool)
+    cells = mesh.cells.astype(np.int64)
+    n0 = mesh.n_nodes
+    edges_of = ((0, 1), (0, 2), (1, 3), (2, 3))          # local vertex pairs, lexicographic vertex order
+    edge_cells = {}
+    for c, dofs in enumerate(cells):
+        for a, b in edges_of:
+            key = (min(dofs[a], dofs[b]), max(dofs[a], dofs[b]))
+            edge_cells.setdefault(key, []).append(c)
+    xyz = [mesh.xyz]
+    node_patch = list(mesh.node_patch)
+    on_bnd = list(mesh.node_on_patch_boundary)
+    surf = list(mesh.surface_nodes) if mesh.surface_nodes is not None else None
+    mid = {}
+    hanging = []
+    new_cells, new_dir, new_patch = [], [], []
+    n = n0
+
+    def new_node(pos, patch, bnd, s):
+        nonlocal n
+        xyz.append(np.asarray(pos, dtype=np.float64)[None, :])
+        node_patch.append(patch)
+        on_bnd.append(bnd)
+        if surf is not None:
+            surf.append(s)
+        n += 1
+        return n - 1
+
+    for c, dofs in enumerate(cells):
+        if not cell_mask[c]:
+            new_cells.append(dofs)
+            new_dir.append(mesh.dir_flag[c])
+            new_patch.append(mesh.cell_patch[c])
+            continue
+        X = mesh.xyz[dofs]
+        patch = mesh.cell_patch[c]
+        sval = mesh.surface_nodes[dofs[0]] if surf is not None else 0.0
+        m = []
+        for a, b in edges_of:
+            key = (min(dofs[a], dofs[b]), max(dofs[a], dofs[b]))
+            if key not in mid:
+                owners = edge_cells[key]
+                is_bnd = len(owners) == 1                      # an edge of the patch boundary
+                mid[key] = new_node(0.5 * (X[a] + X[b]), patch, is_bnd, sval)
+                if not is_bnd and not all(cell_mask[o] for o in owners):
+                    hanging.append((mid[key], [(int(key[0]), 0.5), (int(key[1]), 0.5)]))
+            m.append(mid[key])
+        e01, e02, e13, e23 = m
+        ctr = new_node(0.25 * X.sum(axis=0), patch, False, sval)
+        for child in ((dofs[0], e01, e02, ctr), (e01, dofs[1], ctr, e13), (e02, ctr, dofs[2], e23), (ctr, e13, e23, dofs[3])):
+            new_cells.append(np.array(child, dtype=np.int64))
+            new_dir.append(mesh.dir_flag[c])
+            new_patch.append(patch)
+    xyz = np.ascontiguousarray(np.concatenate(xyz), dtype=np.float64)
+    out = SurfaceMesh(xyz=xyz, cells=np.ascontiguousarray(np.array(new_cells), dtype=np.uint32),
+                      dir_flag=np.ascontiguousarray(new_dir, dtype=np.uint8), cell_patch=np.array(new_patch, dtype=np.int32),
+                      node_patch=np.array(node_patch, dtype=np.int32), node_on_patch_boundary=np.array(on_bnd, dtype=bool),
+                      patch_names=list(mesh.patch_names), meta=dict(mesh.meta))
+    out.dn_ptr, out.dn_idx = generate_double_nodes_set(xyz, out.node_on_patch_boundary)
+    if surf is not None:
+        out.surface_nodes = np.array(surf, dtype=np.float64)
+        out.other_nodes = 1.0 - out.surface_nodes
+    return out, sorted(hanging)
