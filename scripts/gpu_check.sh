@@ -34,4 +34,15 @@ if [ "$MODE" != "quick" ]; then
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bem_gemv -s 4 -c 2 -f -o $OUT/prof_gemv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_gemv.log 2>&1; echo "ncu gemv rc=$?" | tee -a $OUT/summary.log
 fi
+if [ "$MODE" != "quick" ]; then
+  echo "== BASELINE configs 3 (one GPU) and 5 (IDA pattern, single and batched J.v)" | tee -a $OUT/summary.log
+  timeout 600 python bench.py --config 3 --steps 3 --no-cpu-baseline 2>/dev/null | tail -1 > $OUT/bench_cfg3_g1.json; echo "cfg3 rc=$?" | tee -a $OUT/summary.log
+  timeout 600 python bench.py --config 5 --nodes 20000 --steps 3 --warmup 1 2>/dev/null | tail -1 > $OUT/bench_cfg5_20k.json
+  timeout 600 python bench.py --config 5 --nodes 20000 --steps 3 --warmup 1 --jv-batched 2>/dev/null | tail -1 > $OUT/bench_cfg5_20k_batched.json
+  timeout 600 python bench.py --config 5 --steps 10 --warmup 2 2>/dev/null | tail -1 > $OUT/bench_cfg5_4k.json
+  timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > $OUT/bench_reference.json
+  echo "== SASS of the two hot kernels" | tee -a $OUT/summary.log
+  cuobjdump -sass wavebem_b200/lib/assemble.o | awk '/Function : .*k_assemble_rows/{f=1} /Function : /{if(!/k_assemble_rows/)f=0} f' > $OUT/sass_k_assemble_rows.txt
+  cuobjdump -sass wavebem_b200/lib/operator.o | awk '/Function : .*k_bem_gemv9GemvArgs/{f=1} /Function : /{if(!/k_bem_gemv9GemvArgs/)f=0} f' > $OUT/sass_k_bem_gemv.txt
+fi
 echo "== done" | tee -a $OUT/summary.log

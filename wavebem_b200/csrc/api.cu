@@ -920,8 +920,8 @@ int wbem_solve_system_multi(wbem_ctx *ctx, int nrhs, double *phi, double *dphi_d
   CUDA_OK(ctx, cudaSetDevice(ctx->dev));
   cudaStream_t st = ctx->stream;
   const size_t nd = (size_t)nrhs * ctx->N, nbytes = sizeof(double) * nd;
-  double *d = nullptr;
-  CUDA_OK(ctx, cudaMalloc((void **)&d, 3 * nbytes));
+  double *d = wbem_multi_io(ctx, 3 * nd);
+  if (!d) return -2;
   double *d_phi = d, *d_dphi = d + nd, *d_bc = d + 2 * nd;
   cudaError_t e = cudaMemcpyAsync(d_phi, phi, nbytes, cudaMemcpyHostToDevice, st);
   if (e == cudaSuccess) e = cudaMemcpyAsync(d_dphi, dphi_dn, nbytes, cudaMemcpyHostToDevice, st);
@@ -933,7 +933,6 @@ int wbem_solve_system_multi(wbem_ctx *ctx, int nrhs, double *phi, double *dphi_d
       if (e == cudaSuccess) e = cudaMemcpyAsync(dphi_dn, d_dphi, nbytes, cudaMemcpyDeviceToHost, st);
     }
   if (e == cudaSuccess) e = cudaStreamSynchronize(st);
-  cudaFree(d);
   if (e != cudaSuccess) WBEM_FAIL(ctx, -2, "CUDA error %s in wbem_solve_system_multi", cudaGetErrorString(e));
   return rc;
 }

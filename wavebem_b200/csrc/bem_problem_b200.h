@@ -173,6 +173,40 @@ public:
     const int rc = wbem_solve_system(ctx, phi.data(), dphi_dn.data(), tmp_rhs.data(), &iters, &res);
     finish(rc, iters, res);
   }
+  // the J.v pattern of FreeSurface::jacobian (source/free_surface.cc:4918-4993): nrhs solve_system calls on
+  // unchanged matrices as one; phi / dphi_dn / tmp_rhs are [nrhs][n_dofs] row-major
+  void solve_system_multi(unsigned int nrhs, std::vector<double> &phi, std::vector<double> &dphi_dn,
+                          const std::vector<double> &tmp_rhs, std::vector<int> *iterations = nullptr)
+  {
+    masks();
+    std::vector<int> it(nrhs, 0);
+    std::vector<double> res(nrhs, 0.0);
+    const int rc = wbem_solve_system_multi(ctx, (int)nrhs, phi.data(), dphi_dn.data(), tmp_rhs.data(), it.data(), res.data());
+    check(rc);
+    if (iterations) *iterations = it;
+    if (rc > 0)
+      {
+        unsigned int worst = 0;
+        for (unsigned int b = 1; b < nrhs; ++b)
+          if (res[b] > res[worst]) worst = b;
+        throw NoConvergence((unsigned int)it[worst], res[worst]);
+      }
+  }
+  // FreeSurface<3>::compute_internal_velocities (source/free_surface.cc:10426-10537): points [n][3] -> velocities [n][3]
+  void compute_internal_velocities(const std::vector<double> &phi, const std::vector<double> &dphi_dn,
+                                   const std::vector<double> &points, std::vector<double> &velocities)
+  {
+    velocities.resize(points.size());
+    check(wbem_internal_velocities(ctx, phi.data(), dphi_dn.data(), (uint32_t)(points.size() / 3), points.data(),
+                                   velocities.data()));
+  }
+  // the hull integrals of FreeSurface<3>::compute_pressure (source/free_surface.cc:9534-9598): out[11], see wbem.h
+  void pressure_force(const std::vector<double> &phi, const std::vector<double> &dphi_dn,
+                      const std::vector<uint8_t> &cell_marked, const double vinf[3], double rho, double g,
+                      const double baricenter[3], double out11[11])
+  {
+    check(wbem_pressure_force(ctx, phi.data(), dphi_dn.data(), cell_marked.data(), vinf, rho, g, baricenter, out11));
+  }
   // source/bem_problem.cc:969-987
   void solve(std::vector<double> &phi, std::vector<double> &dphi_dn, const std::vector<double> &tmp_rhs)
   {

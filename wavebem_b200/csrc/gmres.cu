@@ -623,6 +623,8 @@ struct MultiState
   double *d_small = nullptr;                            // [MAX][small_stride]: y | dot partials | |w|^2 partials | h
   double *d_norm = nullptr;                             // [MAX]
   double *h_pin = nullptr;                              // pinned [MAX][pin_stride]
+  double *d_io = nullptr;                               // staging of the caller's [nrhs][N] arrays (grow-only)
+  size_t io_cap = 0;
   size_t small_stride = 0, pin_stride = 0, inhom_cap = 0;
   uint32_t ld = 0;
   int ntmp = 0;
@@ -633,7 +635,7 @@ void wbem_multi_free(wbem_ctx *ctx)
 {
   MultiState *m = reinterpret_cast<MultiState *>(ctx->multi);
   if (!m) return;
-  for (double *p : {m->w.d_xn, m->w.d_xd, m->w.d_xdiag, m->d_V, m->d_p, m->d_x, m->d_rhs, m->d_inhom, m->d_small, m->d_norm})
+  for (double *p : {m->w.d_xn, m->w.d_xd, m->w.d_xdiag, m->d_V, m->d_p, m->d_x, m->d_rhs, m->d_inhom, m->d_small, m->d_norm, m->d_io})
     if (p) cudaFree(p);
   if (m->h_pin) cudaFreeHost(m->h_pin);
   delete m;
@@ -679,6 +681,28 @@ static MultiState *multi_state(wbem_ctx *ctx)
       return nullptr;
     }
   return m;
+}
+
+// device staging for the host arrays of wbem_solve_system_multi: allocated once and kept (a cudaMalloc /
+// cudaFree pair per call synchronises the device and can stall for hundreds of milliseconds)
+double *wbem_multi_io(wbem_ctx *ctx, size_t doubles)
+{
+  MultiState *m = multi_state(ctx);
+  if (!m) return nullptr;
+  if (doubles > m->io_cap)
+    {
+      if (m->d_io) cudaFree(m->d_io);
+      m->d_io = nullptr;
+      m->io_cap = 0;
+      if (cudaMalloc((void **)&m->d_io, sizeof(double) * doubles) != cudaSuccess)
+        {
+          cudaGetLastError();
+          ctx->err = "wbem_solve_system_multi: out of device memory for the staging arrays";
+          return nullptr;
+        }
+      m->io_cap = doubles;
+    }
+  return m->d_io;
 }
 
 MultiWork *wbem_multi_work(wbem_ctx *ctx)

@@ -286,6 +286,7 @@ struct MultiWork
   double *d_xn, *d_xd, *d_xdiag;
 };
 MultiWork *wbem_multi_work(wbem_ctx *ctx);
+double *wbem_multi_io(wbem_ctx *ctx, size_t doubles);
 // precond.cu
 int wbem_device_precond_factor(wbem_ctx *ctx);
 int wbem_device_precond_solve(wbem_ctx *ctx, const double *d_in, double *d_out);

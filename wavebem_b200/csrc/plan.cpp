@@ -143,16 +143,18 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
 
   // colouring of the cluster conflict graph (clusters sharing a dof)
   std::vector<uint32_t> color(ncl, NONE);
+  // dof -> clusters touching it (ascending cluster id)
+  std::vector<uint32_t> dptr(N + 1, 0);
+  for (uint32_t d : cl_nodes_all) dptr[d + 1]++;
+  for (uint32_t i = 0; i < N; ++i) dptr[i + 1] += dptr[i];
+  std::vector<uint32_t> dcl(cl_nodes_all.size());
   {
-    // dof -> clusters touching it
-    std::vector<uint32_t> dptr(N + 1, 0);
-    for (uint32_t d : cl_nodes_all) dptr[d + 1]++;
-    for (uint32_t i = 0; i < N; ++i) dptr[i + 1] += dptr[i];
-    std::vector<uint32_t> dcl(cl_nodes_all.size());
     std::vector<uint32_t> fill(dptr.begin(), dptr.end() - 1);
     for (uint32_t k = 0; k < ncl; ++k)
       for (uint32_t s = pl->cl_slot_ptr[k]; s < pl->cl_slot_ptr[k + 1]; ++s)
         dcl[fill[cl_nodes_all[s]]++] = k;
+  }
+  {
     std::vector<uint32_t> used; // colour -> last cluster that saw it taken
     uint32_t ncolors = 0;
     for (uint32_t k = 0; k < ncl; ++k)
@@ -191,6 +193,11 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
   // the slots are reordered so that the STORE slots come first (in column order) and the ADD
   // slots last: the flush of one CTA then writes one contiguous row segment per row with
   // (almost) warp-uniform STORE / ADD lanes.
+  // The columns a cluster stores are grouped by WHO ELSE touches the dof: interior dofs first, then
+  // the dofs shared with one neighbour cluster, neighbour by neighbour, then the corners.  A later
+  // cluster's ADD columns inside this segment are then one contiguous run (its common edge), and its
+  // ADD slots are sorted by column: the RED.ADD.F64 of a warp fill whole 32-byte sectors instead of
+  // costing a sector read-modify-write per 8-byte entry.
   pl->colpos.assign(N, NONE);
   pl->colperm.assign(N, 0);
   pl->slot_col.assign(cl_nodes_all.size(), 0);
@@ -199,8 +206,18 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
     {
       const uint32_t k = pl->color_clusters[idx];
       const uint32_t s0 = pl->cl_slot_ptr[k], s1 = pl->cl_slot_ptr[k + 1];
-      std::stable_partition(cl_nodes_all.begin() + s0, cl_nodes_all.begin() + s1,
-                            [&](uint32_t d) { return pl->colpos[d] == NONE; });
+      auto mid = std::stable_partition(cl_nodes_all.begin() + s0, cl_nodes_all.begin() + s1,
+                                       [&](uint32_t d) { return pl->colpos[d] == NONE; });
+      auto signature_less = [&](uint32_t x, uint32_t y) { // other clusters touching the dof, lexicographic
+        const uint32_t nx = dptr[x + 1] - dptr[x], ny = dptr[y + 1] - dptr[y];
+        if ((nx == 1) != (ny == 1)) return nx == 1; // interior dofs (this cluster only) first
+        if (nx != ny) return nx < ny;               // edges before corners
+        for (uint32_t a = 0; a < nx; ++a)
+          if (dcl[dptr[x] + a] != dcl[dptr[y] + a]) return dcl[dptr[x] + a] < dcl[dptr[y] + a];
+        return false;
+      };
+      std::stable_sort(cl_nodes_all.begin() + s0, mid, signature_less);
+      std::stable_sort(mid, cl_nodes_all.begin() + s1, [&](uint32_t x, uint32_t y) { return pl->colpos[x] < pl->colpos[y]; });
       for (uint32_t s = s0; s < s1; ++s)
         {
           const uint32_t d = cl_nodes_all[s];
@@ -244,7 +261,7 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
 
 // Host-only self check of the plan (no GPU needed; used by tests/test_plan.py).
 // stats[0..7] = n_clusters, n_colors, max cells/cluster, max slots/cluster, total slots,
-//               slots flagged ADD, columns written, 0
+//               slots flagged ADD, columns written, 32-byte sectors under the ADD slots
 // Returns 0 when every invariant holds, a positive code naming the first violated one.
 extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t W_max,
                                uint32_t max_cells, double *stats)
@@ -317,7 +334,20 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
       stats[4] = (double)pl.slot_col.size();
       stats[5] = n_add;
       stats[6] = pl.n_cols_written;
-      stats[7] = 0;
+      // distinct 32-byte sectors (4 columns) the ADD slots of a cluster touch per row, summed over clusters
+      size_t sectors = 0;
+      for (uint32_t k = 0; k < ncl; ++k)
+        {
+          uint32_t last = 0xffffffffu;
+          for (uint32_t s = pl.cl_slot_ptr[k]; s < pl.cl_slot_ptr[k + 1]; ++s)
+            if (pl.slot_col[s] >> 31)
+              {
+                const uint32_t sec = (pl.slot_col[s] & 0x7fffffffu) / 4;
+                if (sec != last) ++sectors; // ADD slots are sorted by column
+                last = sec;
+              }
+        }
+      stats[7] = (double)sectors;
     }
   return 0;
 }
