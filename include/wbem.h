@@ -48,7 +48,8 @@ typedef struct wbem_params
   int device;              /* CUDA device ordinal */
   int rank;                /* this context's row block */
   int world_size;          /* number of row blocks (GPUs) */
-  int assemble_variant;    /* 0 = default (tiled, deterministic), 1 = simple atomic kernel */
+  int assemble_variant;    /* 0 = default (single-launch stream kernel, deterministic), 1 = simple atomic kernel,
+                            * 2 = colour-per-launch tiled kernel (per-point arithmetic; also the path of wbem_set_fevalues) */
   int precond_on_host;     /* 1 = band LU + solves on the host (debug), 0 = on the device */
   int precond_kind;        /* 0 = the reference's band preconditioner (default); 1 = local-inverse
                               sparse approximate inverse (spai.cu): same solution within the solver
@@ -272,9 +273,10 @@ int wbem_time_operator(wbem_ctx *ctx, int reps, int flush_l2, double *ms_avg, do
 int wbem_time_assemble(wbem_ctx *ctx, int reps, double *ms_avg);
 /* device self test of the fast 1/sqrt used by the regular-pair kernel: out[i] = rsqrt(in[i]) */
 int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out, int n);
-/* host-only check of the assembly tiling plan (no GPU): 0 = all invariants hold */
+/* host-only check of the assembly tiling plan (no GPU): 0 = all invariants hold; stats9 = clusters, colours,
+ * max cells, max slots, slots, ADD slots, columns written, ADD sectors, longest predecessor list */
 int wbem_plan_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *cell_dofs, uint32_t w_max,
-                    uint32_t max_cells, double *stats8);
+                    uint32_t max_cells, double *stats9);
 
 #ifdef __cplusplus
 }

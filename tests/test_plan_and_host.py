@@ -10,7 +10,7 @@ from wavebem_b200.constraints import compute_constraints
 
 
 def _plan_check(wb, mesh, w=48, mc=64):
-    st = np.zeros(8)
+    st = np.zeros(9)
     rc = wb.lib().wbem_plan_check(C.c_uint32(mesh.n_nodes), C.c_uint32(mesh.n_cells),
                                   mesh.cells.ctypes.data_as(C.c_void_p), C.c_uint32(w), C.c_uint32(mc),
                                   st.ctypes.data_as(C.c_void_p))
@@ -36,7 +36,7 @@ def test_plan_small_tiles_and_degenerate_cells(wb):
         assert rc == 0 and st[3] <= w and st[2] <= mc
     # a cell with a repeated dof (collapsed quad) and a dof no cell uses
     cells = np.array([[0, 1, 2, 2], [1, 3, 2, 4]], dtype=np.uint32)
-    st = np.zeros(8)
+    st = np.zeros(9)
     rc = wb.lib().wbem_plan_check(C.c_uint32(6), C.c_uint32(2), cells.ctypes.data_as(C.c_void_p),
                                   C.c_uint32(48), C.c_uint32(36), st.ctypes.data_as(C.c_void_p))
     assert rc == 0 and st[6] == 5

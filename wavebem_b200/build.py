@@ -53,16 +53,21 @@ def build(force: bool = False, verbose: bool = False, ptxas_info: bool = False) 
     return LIB
 
 
-def build_variant(tag: str, defines: list[str]) -> str:
-    """Development helper: lib/libwbem_<tag>.so compiled with extra -D flags (kernel tuning
-    experiments; select it with the environment variable WBEM_LIB)."""
+def build_variant(tag: str, defines: list[str], sources=("assemble.cu",)) -> str:
+    """Development helper: lib/libwbem_<tag>.so with `sources` recompiled with extra -D flags (kernel
+    tuning experiments; the tile macros live in assemble.cu only) and the other objects of the main
+    build; select it with the environment variable WBEM_LIB."""
+    build()
     vdir = os.path.join(OUT, "variant_" + tag)
     os.makedirs(vdir, exist_ok=True)
     objs = []
     for s in SOURCES:
-        obj = os.path.join(vdir, os.path.splitext(s)[0] + ".o")
+        if s in sources:
+            obj = os.path.join(vdir, os.path.splitext(s)[0] + ".o")
+            subprocess.check_call([NVCC] + ARCH + FLAGS + defines + ["-c", os.path.join(CSRC, s), "-o", obj])
+        else:
+            obj = os.path.join(OUT, os.path.splitext(s)[0] + ".o")
         objs.append(obj)
-        subprocess.check_call([NVCC] + ARCH + FLAGS + defines + ["-c", os.path.join(CSRC, s), "-o", obj])
     lib = os.path.join(OUT, f"libwbem_{tag}.so")
     subprocess.check_call([NVCC] + ARCH + ["-shared", "-ccbin", HOST_CXX, "-o", lib] + objs + ["-ldl"])
     return lib

@@ -178,8 +178,12 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_slot_col);
   FREE_DEV(ctx->d_cta_desc);
   FREE_DEV(ctx->d_cell_slots);
+  FREE_DEV(ctx->d_item_meta);
+  FREE_DEV(ctx->d_item_desc);
+  FREE_DEV(ctx->d_asm_sync);
   FREE_DEV(ctx->d_xyz);
   FREE_DEV(ctx->d_cellgeo);
+  FREE_DEV(ctx->d_cellgeo2);
   FREE_DEV(ctx->d_Nm);
   FREE_DEV(ctx->d_Dm);
   FREE_DEV(ctx->d_alpha);
@@ -206,7 +210,9 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_h);
   FREE_DEV(ctx->d_band);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
+  if (ctx->h_asm_flag) cudaFreeHost(ctx->h_asm_flag);
   ctx->h_pinned = nullptr;
+  ctx->h_asm_flag = nullptr;
   wbem_device_precond_free(ctx);
   wbem_spai_free(ctx);
   wbem_constraints_free(ctx);
@@ -398,6 +404,7 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   if ((rc = dev_upload(ctx, &ctx->d_slot_col, pl.slot_col))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_cta_desc, cta_desc))) return rc;
   if ((rc = dev_upload(ctx, &ctx->d_cell_slots, pl.cell_slots))) return rc;
+  if ((rc = wbem_upload_stream_tables(ctx, sing_ptr, sing_pos, cluster_of_pos))) return rc;
 
   // storage (BEMProblem::reinit, :55-71)
   const size_t ld = ctx->ld, nloc = ctx->nloc;
@@ -405,6 +412,12 @@ int wbem_set_topology(wbem_ctx *ctx, uint32_t N, uint32_t C, const uint32_t *cel
   const int band = std::max(ctx->p.preconditioner_band, 2);
   if ((rc = dev_alloc(ctx, &ctx->d_xyz, 3 * (size_t)N))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_cellgeo, (size_t)C * 8 * ctx->qt.nq + 16))) return rc;
+  if (ctx->qt.n1 == 4)
+    {
+      if ((rc = dev_alloc(ctx, &ctx->d_cellgeo2, (size_t)C * wbem_line_record_doubles() + 64))) return rc;
+    }
+  else
+    FREE_DEV(ctx->d_cellgeo2);
   if ((rc = dev_alloc(ctx, &ctx->d_Nm, nloc * ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_Dm, nloc * ld))) return rc;
   if ((rc = dev_alloc(ctx, &ctx->d_alpha, ld))) return rc;
@@ -512,6 +525,8 @@ static int assemble_timings(wbem_ctx *ctx)
 {
   CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
   CUDA_OK(ctx, cudaGetLastError());
+  if (ctx->h_asm_flag && *ctx->h_asm_flag)
+    WBEM_FAIL(ctx, -7, "assembly: a work item gave up waiting for the clusters it shares columns with (k_assemble_rows)");
   float a = 0, b = 0, c = 0, d = 0, e = 0;
   cudaEventElapsedTime(&a, ctx->ev[6], ctx->ev[0]);
   if (ctx->nloc && ctx->C)

@@ -13,7 +13,9 @@
 //   k_assemble_singular  pairs whose cell holds a dof of double_nodes_set[i] (:223-230,
 //                        261-525): QGaussOneOverR rule, one warp per row, shuffle reduction
 //   k_alpha_rowsum       alpha = -row sums of the Neumann matrix (:594-618)
+#include <algorithm>
 #include <cstdio>
+#include <cstdlib>
 #include <cstring>
 #include <vector>
 
@@ -22,13 +24,22 @@
 
 #define FOUR_PI 12.566370614359172953850573533118
 #define GEO_REC 8 // doubles per (cell, q): y[3], n JxW/(-4 pi)[3], JxW/(4 pi), JxW u_q/(4 pi)
+// Line records of the 4 x 4 rule on a bilinear (Q1) cell, for the stream kernel.  Along a Gauss
+// line v = v_j the panel point is y(u) = A + u B and d_u y x d_v y = P + u Q, with B . P = B . Q = 0, so
+// for a collocation point x and D = A - x
+//     r^2(u)             = D.D + u (2 B.D) + u^2 B.B          (quadratic in u)
+//     (y - x) . n JxW(u) = w_u (D.P' + u D.Q')                 (linear in u; P', Q' carry w_v / (-4 pi) and the orientation)
+// -- 15 FP64 operations per row and line instead of 9 per row and Gauss point.
+// Layout per cell: 4 lines x [A(3), 2B(3), B.B, P'(3), Q'(3), pad] then 16 x (JxW/(4 pi), JxW u/(4 pi)).
+#define LINE_REC 14
+#define GEO2_REC (4 * LINE_REC + 32)
 
 struct DevTables
 {
   int nq, ns, n1, pad;
   double g_u[WBEM_MAX_NQ], g_v[WBEM_MAX_NQ], g_w[WBEM_MAX_NQ];
   double g_shape[4][WBEM_MAX_NQ];
-  double g1_x[8];
+  double g1_x[8], g1_w[8];
   double s_u[4][WBEM_MAX_NS], s_v[4][WBEM_MAX_NS], s_w[4][WBEM_MAX_NS];
 };
 // The tables live in global memory, one copy per context (two contexts with different
@@ -48,6 +59,7 @@ int wbem_upload_tables(wbem_ctx *ctx)
   memcpy(t.g_w, q.g_w, sizeof(t.g_w));
   memcpy(t.g_shape, q.g_shape, sizeof(t.g_shape));
   memcpy(t.g1_x, q.g1_x, sizeof(t.g1_x));
+  memcpy(t.g1_w, q.g1_w, sizeof(t.g1_w));
   memcpy(t.s_u, q.s_u, sizeof(t.s_u));
   memcpy(t.s_v, q.s_v, sizeof(t.s_v));
   memcpy(t.s_w, q.s_w, sizeof(t.s_w));
@@ -62,7 +74,7 @@ int wbem_upload_tables(wbem_ctx *ctx)
 // n JxW = +-(d_u x d_v) w_q exactly (no normalisation needed).
 __global__ void k_cell_geometry(const DevTables *__restrict__ qt, uint32_t C, int nq, const double *__restrict__ xyz,
                                 const uint32_t *__restrict__ cell_dofs,
-                                const uint8_t *__restrict__ dir, double *__restrict__ geo)
+                                const uint8_t *__restrict__ dir, double *__restrict__ geo, double *__restrict__ geo2)
 {
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t c = t / nq;
@@ -85,6 +97,38 @@ __global__ void k_cell_geometry(const DevTables *__restrict__ qt, uint32_t C, in
   g[5 * nq + q] = cr[2] * f;
   g[6 * nq + q] = cn * w * (1.0 / FOUR_PI);
   g[7 * nq + q] = (cn * w * (1.0 / FOUR_PI)) * qt->g_u[q];
+  if (geo2 && nq == 16)
+    {
+      double *h = geo2 + (size_t)c * GEO2_REC;
+      h[4 * LINE_REC + 2 * q] = cn * w * (1.0 / FOUR_PI);
+      h[4 * LINE_REC + 2 * q + 1] = (cn * w * (1.0 / FOUR_PI)) * qt->g_u[q];
+      if ((q & 3) == 0)
+        { // first point of Gauss line j: the line's constants
+          const int j = q >> 2;
+          const double v = qt->g_v[q];
+          const double fl = sgn * qt->g1_w[j] * (-1.0 / FOUR_PI);
+          double A[3], B[3], cc[3], dd[3];
+#pragma unroll
+          for (int d = 0; d < 3; ++d)
+            {
+              cc[d] = X.x[2][d] - X.x[0][d];
+              dd[d] = (X.x[3][d] - X.x[2][d]) - (X.x[1][d] - X.x[0][d]);
+              A[d] = X.x[0][d] + v * cc[d];
+              B[d] = (X.x[1][d] - X.x[0][d]) + v * dd[d];
+            }
+          double *l = h + j * LINE_REC;
+          l[0] = A[0], l[1] = A[1], l[2] = A[2];
+          l[3] = 2.0 * B[0], l[4] = 2.0 * B[1], l[5] = 2.0 * B[2];
+          l[6] = B[0] * B[0] + B[1] * B[1] + B[2] * B[2];
+          l[7] = (B[1] * cc[2] - B[2] * cc[1]) * fl;
+          l[8] = (B[2] * cc[0] - B[0] * cc[2]) * fl;
+          l[9] = (B[0] * cc[1] - B[1] * cc[0]) * fl;
+          l[10] = (B[1] * dd[2] - B[2] * dd[1]) * fl;
+          l[11] = (B[2] * dd[0] - B[0] * dd[2]) * fl;
+          l[12] = (B[0] * dd[1] - B[1] * dd[0]) * fl;
+          l[13] = 0.0;
+        }
+    }
 }
 
 // The literal FEValues of the regular rule handed over by the caller (reference :192-196:
@@ -140,7 +184,7 @@ int wbem_launch_geometry(wbem_ctx *ctx)
   if (total == 0) return 0;
   k_cell_geometry<<<(total + 255) / 256, 256, 0, ctx->stream>>>((const DevTables *)ctx->d_tables, ctx->C, nq, ctx->d_xyz,
                                                                ctx->d_cell_dofs, ctx->d_dir,
-                                                               ctx->d_cellgeo);
+                                                               ctx->d_cellgeo, ctx->d_cellgeo2);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   return 0;
@@ -287,13 +331,336 @@ __device__ __forceinline__ void flush_value(double *p, double v, uint32_t is_add
 #define T1_STRIDE (T1_ROWS + 1) // double2 units between consecutive slots
 #define T1_REC (GEO_REC * 16)   // doubles per cell record
 
+// Moments of one cell for the T1_RPT rows of a thread.  g = the cell's panel record in shared memory
+// ([GEO_REC][16], warp-uniform addresses: broadcast loads); u = the 1-D Gauss nodes.  The tensor
+// structure of the 4 x 4 rule turns the four shape-function sums into the moments
+// S = sum a, Su = sum a u, Sv = sum a v, Suv = sum a u v  (a = kernel value x weight):
+// 2.75 instead of 4 FMAs per evaluation and matrix.
+struct CellMoments
+{
+  double SN[T1_RPT], SuN[T1_RPT], SvN[T1_RPT], SuvN[T1_RPT], SD[T1_RPT], SuD[T1_RPT], SvD[T1_RPT], SuvD[T1_RPT];
+};
+
+__device__ __forceinline__ void integrate_cell(const double *__restrict__ g, const double (&xi0)[T1_RPT],
+                                               const double (&xi1)[T1_RPT], const double (&xi2)[T1_RPT], const double u0,
+                                               const double u1, const double u2, const double u3, CellMoments &m)
+{
+  double(&SN)[T1_RPT] = m.SN, (&SuN)[T1_RPT] = m.SuN, (&SvN)[T1_RPT] = m.SvN, (&SuvN)[T1_RPT] = m.SuvN;
+  double(&SD)[T1_RPT] = m.SD, (&SuD)[T1_RPT] = m.SuD, (&SvD)[T1_RPT] = m.SvD, (&SuvD)[T1_RPT] = m.SuvD;
+#pragma unroll
+  for (int j = 0; j < 4; ++j)
+    {
+      const double vq = j == 0 ? u0 : j == 1 ? u1 : j == 2 ? u2 : u3;
+      double t0n[T1_RPT], t1n[T1_RPT], t0d[T1_RPT], t1d[T1_RPT];
+#pragma unroll
+      for (int qx = 0; qx < 4; ++qx)
+        {
+          const int q = j * 4 + qx;
+          const double uq = qx == 0 ? u0 : qx == 1 ? u1 : qx == 2 ? u2 : u3;
+          const double y0 = g[q], y1 = g[16 + q], y2 = g[32 + q];
+          const double n0 = g[48 + q], n1 = g[64 + q], n2 = g[80 + q], wj = g[96 + q], wju = g[112 + q];
+#pragma unroll
+          for (int r = 0; r < T1_RPT; ++r)
+            {
+              const double Rx = y0 - xi0[r], Ry = y1 - xi1[r], Rz = y2 - xi2[r];
+              const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
+              const double ri = rsqrt_h3(r2);
+              const double ri2 = ri * ri;
+              const double ri3 = ri2 * ri;
+              const double Rn = fma(Rz, n2, fma(Ry, n1, Rx * n0));
+              const double av = Rn * ri3; // (D . n) JxW; the single-layer d JxW = wj ri goes
+              if (qx == 0)                // straight into its two line moments (wju = wj u_q)
+                {
+                  t0n[r] = av;
+                  t1n[r] = av * uq;
+                  t0d[r] = wj * ri;
+                  t1d[r] = wju * ri;
+                }
+              else
+                {
+                  t0n[r] += av;
+                  t1n[r] = fma(av, uq, t1n[r]);
+                  t0d[r] = fma(wj, ri, t0d[r]);
+                  t1d[r] = fma(wju, ri, t1d[r]);
+                }
+            }
+        }
+#pragma unroll
+      for (int r = 0; r < T1_RPT; ++r)
+        if (j == 0)
+          {
+            SN[r] = t0n[r];
+            SuN[r] = t1n[r];
+            SvN[r] = vq * t0n[r];
+            SuvN[r] = vq * t1n[r];
+            SD[r] = t0d[r];
+            SuD[r] = t1d[r];
+            SvD[r] = vq * t0d[r];
+            SuvD[r] = vq * t1d[r];
+          }
+        else
+          {
+            SN[r] += t0n[r];
+            SuN[r] += t1n[r];
+            SvN[r] = fma(vq, t0n[r], SvN[r]);
+            SuvN[r] = fma(vq, t1n[r], SuvN[r]);
+            SD[r] += t0d[r];
+            SuD[r] += t1d[r];
+            SvD[r] = fma(vq, t0d[r], SvD[r]);
+            SuvD[r] = fma(vq, t1d[r], SuvD[r]);
+          }
+    }
+}
+
+// The same moments from the line records (GEO2_REC doubles per cell, see the top of the file), one
+// Gauss line (v = un[J]) at a time.  wq / wuq: the 1-D Gauss weights and weights x nodes (kernel
+// parameters: constant-bank operands).
+template <int J>
+__device__ __forceinline__ void line_moments(const double *__restrict__ g, const double (&xi0)[T1_RPT],
+                                             const double (&xi1)[T1_RPT], const double (&xi2)[T1_RPT], const double (&un)[4],
+                                             const double (&wq)[4], const double (&wuq)[4], CellMoments &m)
+{
+  const double2 *wj2 = reinterpret_cast<const double2 *>(g + 4 * LINE_REC) + J * 4;
+  const double2 *L = reinterpret_cast<const double2 *>(g + J * LINE_REC);
+  const double2 l0 = L[0], l1 = L[1], l2 = L[2], l3 = L[3], l4 = L[4], l5 = L[5], l6 = L[6];
+  const double vq = un[J], bb = l3.x;
+  double c0[T1_RPT], c1[T1_RPT], e0[T1_RPT], e1[T1_RPT];
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    {
+      const double Dx = l0.x - xi0[r], Dy = l0.y - xi1[r], Dz = l1.x - xi2[r];
+      c0[r] = fma(Dz, Dz, fma(Dy, Dy, Dx * Dx));
+      c1[r] = fma(Dz, l2.y, fma(Dy, l2.x, Dx * l1.y));
+      e0[r] = fma(Dz, l4.y, fma(Dy, l4.x, Dx * l3.y));
+      e1[r] = fma(Dz, l6.x, fma(Dy, l5.y, Dx * l5.x));
+    }
+  double t0n[T1_RPT], t1n[T1_RPT], t0d[T1_RPT], t1d[T1_RPT];
+#pragma unroll
+  for (int qx = 0; qx < 4; ++qx)
+    {
+      const double u = un[qx];
+      const double2 wj = wj2[qx];
+#pragma unroll
+      for (int r = 0; r < T1_RPT; ++r)
+        {
+          const double r2 = fma(fma(bb, u, c1[r]), u, c0[r]);
+          const double ri = rsqrt_h3(r2);
+          const double ri2 = ri * ri;
+          const double ri3 = ri2 * ri;
+          const double Rn = fma(e1[r], u, e0[r]);
+          const double av = Rn * ri3;
+          if (qx == 0)
+            {
+              t0n[r] = wq[0] * av;
+              t1n[r] = wuq[0] * av;
+              t0d[r] = wj.x * ri;
+              t1d[r] = wj.y * ri;
+            }
+          else
+            {
+              t0n[r] = fma(wq[qx], av, t0n[r]);
+              t1n[r] = fma(wuq[qx], av, t1n[r]);
+              t0d[r] = fma(wj.x, ri, t0d[r]);
+              t1d[r] = fma(wj.y, ri, t1d[r]);
+            }
+        }
+    }
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    if (J == 0)
+      {
+        m.SN[r] = t0n[r];
+        m.SuN[r] = t1n[r];
+        m.SvN[r] = vq * t0n[r];
+        m.SuvN[r] = vq * t1n[r];
+        m.SD[r] = t0d[r];
+        m.SuD[r] = t1d[r];
+        m.SvD[r] = vq * t0d[r];
+        m.SuvD[r] = vq * t1d[r];
+      }
+    else
+      {
+        m.SN[r] += t0n[r];
+        m.SuN[r] += t1n[r];
+        m.SvN[r] = fma(vq, t0n[r], m.SvN[r]);
+        m.SuvN[r] = fma(vq, t1n[r], m.SuvN[r]);
+        m.SD[r] += t0d[r];
+        m.SuD[r] += t1d[r];
+        m.SvD[r] = fma(vq, t0d[r], m.SvD[r]);
+        m.SuvD[r] = fma(vq, t1d[r], m.SuvD[r]);
+      }
+}
+
+// moments -> the four Q1 shape-function sums, added to the cell's four column slots of the thread's
+// rows.  The four slots of a cell are distinct (cells with a repeated dof take the simple kernel),
+// so the four accumulator loads go out together: one shared-memory round trip per cell, not four.
+__device__ __forceinline__ void scatter_cell_distinct(double2 *accT, const uint32_t sl, const CellMoments &cm,
+                                                      const unsigned long long (&smask)[T1_RPT], const int k,
+                                                      double (&row_sum)[T1_RPT])
+{
+  double2 *const pa = accT + (sl & 0xff) * T1_STRIDE, *const pb = accT + ((sl >> 8) & 0xff) * T1_STRIDE,
+                *const pc = accT + ((sl >> 16) & 0xff) * T1_STRIDE, *const pd = accT + (sl >> 24) * T1_STRIDE;
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    {
+      if ((smask[r] >> k) & 1ull) continue; // singular pair: k_assemble_singular integrates it
+      double2 va = pa[r * T1_THREADS], vb = pb[r * T1_THREADS], vc = pc[r * T1_THREADS], vd = pd[r * T1_THREADS];
+      const double n3 = cm.SuvN[r], n1 = cm.SuN[r] - n3, n2 = cm.SvN[r] - n3, n0 = (cm.SN[r] - cm.SuN[r]) - n2;
+      const double d3 = cm.SuvD[r], d1 = cm.SuD[r] - d3, d2 = cm.SvD[r] - d3, d0 = (cm.SD[r] - cm.SuD[r]) - d2;
+      row_sum[r] += cm.SN[r];
+      va.x += n0, va.y += d0;
+      vb.x += n1, vb.y += d1;
+      vc.x += n2, vc.y += d2;
+      vd.x += n3, vd.y += d3;
+      pa[r * T1_THREADS] = va;
+      pb[r * T1_THREADS] = vb;
+      pc[r * T1_THREADS] = vc;
+      pd[r * T1_THREADS] = vd;
+    }
+}
+
+// moments -> the four Q1 shape-function sums, added to the cell's four column slots of the thread's
+// rows (accT = the thread's first accumulator; sl = the cell's four slot numbers, one byte each)
+__device__ __forceinline__ void scatter_cell(double2 *accT, const uint32_t sl, const CellMoments &cm,
+                                             const unsigned long long (&smask)[T1_RPT], const int k, double (&row_sum)[T1_RPT])
+{
+  double2 *const pa = accT + (sl & 0xff) * T1_STRIDE, *const pb = accT + ((sl >> 8) & 0xff) * T1_STRIDE,
+                *const pc = accT + ((sl >> 16) & 0xff) * T1_STRIDE, *const pd = accT + (sl >> 24) * T1_STRIDE;
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    {
+      if ((smask[r] >> k) & 1ull) continue; // singular pair: k_assemble_singular integrates it
+      const double n3 = cm.SuvN[r], n1 = cm.SuN[r] - n3, n2 = cm.SvN[r] - n3, n0 = (cm.SN[r] - cm.SuN[r]) - n2;
+      const double d3 = cm.SuvD[r], d1 = cm.SuD[r] - d3, d2 = cm.SvD[r] - d3, d0 = (cm.SD[r] - cm.SuD[r]) - d2;
+      row_sum[r] += cm.SN[r];
+      double2 v;
+      v = pa[r * T1_THREADS];
+      v.x += n0;
+      v.y += d0;
+      pa[r * T1_THREADS] = v;
+      v = pb[r * T1_THREADS];
+      v.x += n1;
+      v.y += d1;
+      pb[r * T1_THREADS] = v;
+      v = pc[r * T1_THREADS];
+      v.x += n2;
+      v.y += d2;
+      pc[r * T1_THREADS] = v;
+      v = pd[r * T1_THREADS];
+      v.x += n3;
+      v.y += d3;
+      pd[r * T1_THREADS] = v;
+    }
+}
+
+// flush: warp w owns rows r * T1_THREADS + [32 w, 32 w + 32) of the tile; lanes run over the
+// cluster's column slots (STORE slots first: one coalesced row segment per row)
+__device__ __forceinline__ void flush_rows(const double2 *acc, const uint32_t *s_col, const int nslot, const uint32_t lrow_base,
+                                           const uint32_t nloc, const uint32_t ld, double *Nm, double *Dm, const int warp,
+                                           const int lane)
+{
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    {
+      const uint32_t row_w = lrow_base + r * T1_THREADS + warp * 32;
+      if (row_w >= nloc) continue;
+      const int nrw = min(32, (int)(nloc - row_w));
+      for (int s = lane; s < nslot; s += 32)
+        {
+          const uint32_t cc = s_col[s];
+          const uint32_t is_add = cc >> 31, is_store = is_add ^ 1u;
+          double *gN = Nm + (size_t)row_w * ld + (cc & 0x7fffffffu);
+          double *gD = Dm + (size_t)row_w * ld + (cc & 0x7fffffffu);
+          const double2 *an = acc + s * T1_STRIDE + r * T1_THREADS + warp * 32;
+          if (nrw == 32)
+            {
+#pragma unroll
+              for (int rb = 0; rb < 32; rb += 8)
+                {
+                  double2 v[8];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) v[i] = an[rb + i];
+#pragma unroll
+                  for (int i = 0; i < 8; ++i)
+                    {
+                      flush_value(gN, v[i].x, is_add, is_store);
+                      flush_value(gD, v[i].y, is_add, is_store);
+                      gN += ld;
+                      gD += ld;
+                    }
+                }
+            }
+          else
+            for (int i = 0; i < nrw; ++i)
+              {
+                const double2 v = an[i];
+                flush_value(gN, v.x, is_add, is_store);
+                flush_value(gD, v.y, is_add, is_store);
+                gN += ld;
+                gD += ld;
+              }
+        }
+    }
+}
+
+// One pass of the stream kernel's flush over n consecutive slots [s_begin, s_begin + n) of the cluster,
+// ADD = false: first writers (plain stores, one contiguous row segment per row), ADD = true: RED.ADD.F64.
+// Lanes = slots; when n <= 16 the spare lanes take further rows (P rows per step).
+template <bool ADD>
+__device__ __forceinline__ void flush_pass(const double2 *acc, const uint32_t *s_col, const int s_begin, const int n,
+                                           const uint32_t lrow_base, const uint32_t nloc, const uint32_t ld, double *Nm, double *Dm,
+                                           const int warp, const int lane)
+{
+  if (n <= 0) return;
+#pragma unroll
+  for (int r = 0; r < T1_RPT; ++r)
+    {
+      const uint32_t row_w = lrow_base + r * T1_THREADS + warp * 32;
+      if (row_w >= nloc) continue;
+      const int nrw = min(32, (int)(nloc - row_w));
+      for (int sb = 0; sb < n; sb += 32)
+        {
+          const int nn = min(32, n - sb);
+          const int P = 32 / nn; // rows per step
+          const int part = lane / nn, j = lane - part * nn;
+          if (part < P)
+            {
+              const int s = s_begin + sb + j;
+              const uint32_t cc = s_col[s] & 0x7fffffffu;
+              double *gN = Nm + (size_t)(row_w + part) * ld + cc;
+              double *gD = Dm + (size_t)(row_w + part) * ld + cc;
+              const double2 *an = acc + s * T1_STRIDE + r * T1_THREADS + warp * 32 + part;
+              const size_t step = (size_t)P * ld;
+#pragma unroll 4
+              for (int i = part; i < nrw; i += P)
+                {
+                  const double2 v = *an;
+                  if (ADD)
+                    {
+                      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(gN), "d"(v.x) : "memory");
+                      asm volatile("red.global.add.f64 [%0], %1;" ::"l"(gD), "d"(v.y) : "memory");
+                    }
+                  else
+                    {
+                      *gN = v.x;
+                      *gD = v.y;
+                    }
+                  an += P;
+                  gN += step;
+                  gD += step;
+                }
+            }
+        }
+    }
+}
+
 constexpr size_t rows_smem_bytes()
 {
   return sizeof(double) * (2 * (size_t)T1_W * T1_STRIDE + 2 * T1_CHUNK * T1_REC) + 40 + TILE_MAX_CELLS * 4 +
          ((T1_W + 3) / 4) * 16;
 }
 
-__global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(const TiledArgs a)
+__global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_colours(const TiledArgs a)
 {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double2 *acc = reinterpret_cast<double2 *>(smem_raw);                    // [W][T1_STRIDE] (N, D)
@@ -371,98 +738,9 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
           const int k = c * T1_CHUNK + kk;
           const double *g = gc + kk * T1_REC;
           const uint32_t sl = s_slots[k];
-          double SN[T1_RPT], SuN[T1_RPT], SvN[T1_RPT], SuvN[T1_RPT], SD[T1_RPT], SuD[T1_RPT], SvD[T1_RPT], SuvD[T1_RPT];
-#pragma unroll
-          for (int j = 0; j < 4; ++j)
-            {
-              const double vq = j == 0 ? u0 : j == 1 ? u1 : j == 2 ? u2 : u3;
-              double t0n[T1_RPT], t1n[T1_RPT], t0d[T1_RPT], t1d[T1_RPT];
-#pragma unroll
-              for (int qx = 0; qx < 4; ++qx)
-                {
-                  const int q = j * 4 + qx;
-                  const double uq = qx == 0 ? u0 : qx == 1 ? u1 : qx == 2 ? u2 : u3;
-                  const double y0 = g[q], y1 = g[16 + q], y2 = g[32 + q];
-                  const double n0 = g[48 + q], n1 = g[64 + q], n2 = g[80 + q], wj = g[96 + q], wju = g[112 + q];
-#pragma unroll
-                  for (int r = 0; r < T1_RPT; ++r)
-                    {
-                      const double Rx = y0 - xi0[r], Ry = y1 - xi1[r], Rz = y2 - xi2[r];
-                      const double r2 = fma(Rz, Rz, fma(Ry, Ry, Rx * Rx));
-                      const double ri = rsqrt_h3(r2);
-                      const double ri2 = ri * ri;
-                      const double ri3 = ri2 * ri;
-                      const double Rn = fma(Rz, n2, fma(Ry, n1, Rx * n0));
-                      const double av = Rn * ri3; // (D . n) JxW; the single-layer d JxW = wj ri goes
-                      if (qx == 0)                // straight into its two line moments (wju = wj u_q)
-                        {
-                          t0n[r] = av;
-                          t1n[r] = av * uq;
-                          t0d[r] = wj * ri;
-                          t1d[r] = wju * ri;
-                        }
-                      else
-                        {
-                          t0n[r] += av;
-                          t1n[r] = fma(av, uq, t1n[r]);
-                          t0d[r] = fma(wj, ri, t0d[r]);
-                          t1d[r] = fma(wju, ri, t1d[r]);
-                        }
-                    }
-                }
-#pragma unroll
-              for (int r = 0; r < T1_RPT; ++r)
-                if (j == 0)
-                  {
-                    SN[r] = t0n[r];
-                    SuN[r] = t1n[r];
-                    SvN[r] = vq * t0n[r];
-                    SuvN[r] = vq * t1n[r];
-                    SD[r] = t0d[r];
-                    SuD[r] = t1d[r];
-                    SvD[r] = vq * t0d[r];
-                    SuvD[r] = vq * t1d[r];
-                  }
-                else
-                  {
-                    SN[r] += t0n[r];
-                    SuN[r] += t1n[r];
-                    SvN[r] = fma(vq, t0n[r], SvN[r]);
-                    SuvN[r] = fma(vq, t1n[r], SuvN[r]);
-                    SD[r] += t0d[r];
-                    SuD[r] += t1d[r];
-                    SvD[r] = fma(vq, t0d[r], SvD[r]);
-                    SuvD[r] = fma(vq, t1d[r], SuvD[r]);
-                  }
-            }
-          // moments -> the four Q1 shape-function sums, added to the cell's four column slots
-          double2 *const pa = accT + (sl & 0xff) * T1_STRIDE, *const pb = accT + ((sl >> 8) & 0xff) * T1_STRIDE,
-                        *const pc = accT + ((sl >> 16) & 0xff) * T1_STRIDE, *const pd = accT + (sl >> 24) * T1_STRIDE;
-#pragma unroll
-          for (int r = 0; r < T1_RPT; ++r)
-            {
-              if ((smask[r] >> k) & 1ull) continue; // singular pair: k_assemble_singular integrates it
-              const double n3 = SuvN[r], n1 = SuN[r] - n3, n2 = SvN[r] - n3, n0 = (SN[r] - SuN[r]) - n2;
-              const double d3 = SuvD[r], d1 = SuD[r] - d3, d2 = SvD[r] - d3, d0 = (SD[r] - SuD[r]) - d2;
-              row_sum[r] += SN[r];
-              double2 v;
-              v = pa[r * T1_THREADS];
-              v.x += n0;
-              v.y += d0;
-              pa[r * T1_THREADS] = v;
-              v = pb[r * T1_THREADS];
-              v.x += n1;
-              v.y += d1;
-              pb[r * T1_THREADS] = v;
-              v = pc[r * T1_THREADS];
-              v.x += n2;
-              v.y += d2;
-              pc[r * T1_THREADS] = v;
-              v = pd[r * T1_THREADS];
-              v.x += n3;
-              v.y += d3;
-              pd[r * T1_THREADS] = v;
-            }
+          CellMoments cm;
+          integrate_cell(g, xi0, xi1, xi2, u0, u1, u2, u3, cm);
+          scatter_cell(accT, sl, cm, smask, k, row_sum);
         }
       if (c + 2 < nchunk)
         {
@@ -488,50 +766,381 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
     }
   __syncwarp(); // a warp flushes exactly the rows its own lanes accumulated
 
-  // flush: warp w owns rows r * T1_THREADS + [32 w, 32 w + 32) of the tile; lanes run over the
-  // cluster's column slots (STORE slots first: one coalesced row segment per row)
-  const int warp = tid >> 5, lane = tid & 31;
-#pragma unroll
-  for (int r = 0; r < T1_RPT; ++r)
+  flush_rows(acc, s_col, nslot, lrow_base, a.nloc, a.ld, a.Nm, a.Dm, tid >> 5, tid & 31);
+}
+
+// ---------------------------------------------------------------------------------------
+// Stream kernel: ONE launch for the whole assembly.  Persistent CTAs (3 per SM) draw (row tile, cluster)
+// work items from a ticket counter.  Item order: groups of G consecutive 128-row tiles; inside a
+// group colour after colour, inside a colour tile after tile, cluster after cluster.  So
+//   * the STORE of a column, the ADDs of its other clusters and the neighbouring columns of the same
+//     32-byte sector land within tens of microseconds: they meet in L2 and (almost) every sector
+//     of the two matrices goes to HBM once.  The colour-per-launch order re-read and re-wrote the ADD
+//     columns milliseconds later: 3.7 x the matrix bytes of DRAM traffic; here 1.19 x at G = 1,
+//     1.65 x at G = 2 (N = 20 k; DESIGN.md has the table);
+//   * there is no CTA launch / prologue bubble: the panel-chunk pipeline (TMA bulk copies,
+//     full/empty mbarriers) runs on across work items, the next item's record arrives with its
+//     first chunk, and the rows' coordinates of the next tile are fetched behind the last chunk.
+// Order of the flushes: an item first stores the columns it is the first writer of, then waits until
+// the lower-colour clusters it shares a column with have flushed the same row tile (done flags,
+// release / acquire at gpu scope), then adds -- STORE before ADD and ADDs in colour order for any
+// item order and CTA scheduling, so the matrices are bitwise reproducible.  G tiles per group put
+// G x (clusters of a colour) tickets between an item and the ones it waits for; with fewer tickets
+// than CTAs in flight (G = 1) some items do wait.  The next item's ticket is drawn as late as the
+// chunk pipeline allows (NBUF + 2 chunks before the current item ends; thread 0, one chunk of
+// integration between the dependent steps ticket -> descriptor -> hand-over, so it never waits for
+// an answer): a CTA that falls behind holds back one drawn ticket for a fraction of an item, not
+// two tickets for two items (which made lateness spread to every item waiting on them).
+// Tickets are handed out in item order and an item only waits for lower tickets, which running
+// CTAs own: no deadlock for any CTA scheduling; the wait is bounded anyway (error flag).
+// No CTA-wide barrier in steady state: a warp accumulates and flushes its own 32 rows; the last
+// warp to finish publishes the item's flag (the others order their stores at CTA scope only).
+// ---------------------------------------------------------------------------------------
+#define META_PRED 16  // longest predecessor list the record holds (else: colour-per-launch kernel)
+#define META_TILES 12 // row tiles with singular pairs listed per cluster (more: "look it up")
+#define STREAM_MAX_COLORS 16
+
+struct ItemMeta
+{ // per cluster, launch order; one bulk copy brings it into shared memory
+  uint32_t p0;     // first cell (processing position)
+  uint32_t counts; // cells | slots << 8 | predecessors << 16 | listed row tiles << 24 (0xff: not listed)
+  uint32_t cluster;
+  uint32_t pad;
+  uint32_t pred[META_PRED];
+  uint32_t sing_tiles[META_TILES];
+  uint32_t cell_slots[TILE_MAX_CELLS];
+  uint32_t slot_col[T1_W];
+};
+static_assert(sizeof(ItemMeta) % 16 == 0, "bulk copies move multiples of 16 bytes");
+
+struct StreamArgs
+{
+  const double *xyz;
+  const double *geo; // line records [C][GEO2_REC], processing order
+  const ItemMeta *meta;                    // [clusters] launch order
+  const uint2 *desc;                       // [clusters] launch order: first cell, cells
+  const uint32_t *sing_ptr, *sing_cellpos; // CSR by local row
+  double *Nm, *Dm, *alpha_part;
+  unsigned int *ticket;     // zeroed before the launch
+  unsigned int *done;       // [row tiles][clusters]: epoch of the last assembly that flushed the item
+  unsigned int *error_flag; // set when a dependency wait gave up
+  uint32_t epoch, n_items, n_clusters, ld, row0, nloc;
+  uint32_t row_tiles, group_tiles, n_colors;
+  uint32_t color_ptr[STREAM_MAX_COLORS + 1];
+  double g1_x[4], g1_w[4], g1_wx[4]; // 1-D Gauss nodes, weights, weights x nodes
+};
+
+#ifndef WBEM_T1_NBUF
+#define WBEM_T1_NBUF 2
+#endif
+#define T1_NBUF WBEM_T1_NBUF // panel-chunk buffers of the stream kernel (every item has at least this many chunks, possibly empty)
+
+constexpr size_t stream_smem_bytes()
+{
+  return sizeof(double2) * (size_t)T1_W * T1_STRIDE + sizeof(double) * T1_NBUF * T1_CHUNK * GEO2_REC + 2 * sizeof(ItemMeta) +
+         (2 * T1_NBUF + 2) * sizeof(uint64_t) + (T1_NBUF + 2 + (T1_NBUF & 1)) * sizeof(uint32_t) + 2 * sizeof(uint2) + 2 * sizeof(uint2);
+}
+
+__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+__device__ __forceinline__ void st_relaxed_gpu(unsigned int *p, unsigned int v)
+{
+  asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
+}
+__device__ __forceinline__ void fence_acq_rel_gpu() { asm volatile("fence.acq_rel.gpu;" ::: "memory"); }
+__device__ __forceinline__ unsigned int ld_acquire_gpu(const unsigned int *p)
+{
+  unsigned int v;
+  asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+  return v;
+}
+// A warp (its lane 0) reports that its rows of an item are flushed; the last of the CTA's warps
+// publishes the item's flag.  The others only order their stores at CTA scope (cheap); the gpu-scope
+// fence of the last one is cumulative over what it has observed through the counter.
+__device__ __forceinline__ void signal_flushed(unsigned int *flag, uint32_t *counter, const unsigned int epoch)
+{
+  asm volatile("fence.acq_rel.cta;" ::: "memory");
+  if (atomicAdd(counter, 1u) == T1_WARPS - 1)
     {
-      const uint32_t row_w = lrow_base + r * T1_THREADS + warp * 32;
-      if (row_w >= a.nloc) continue;
-      const int nrw = min(32, (int)(a.nloc - row_w));
-      for (int s = lane; s < nslot; s += 32)
+      *counter = 0;
+      fence_acq_rel_gpu();
+      st_relaxed_gpu(flag, epoch);
+    }
+}
+
+// ticket -> (row tile, launch position); tile = 0xffffffff past the end
+__device__ __forceinline__ uint2 decode_ticket(const uint32_t t, const StreamArgs &a)
+{
+  if (t >= a.n_items) return make_uint2(0xffffffffu, 0u);
+  const uint32_t per_group = a.group_tiles * a.n_clusters;
+  const uint32_t g = t / per_group;
+  uint32_t r = t - g * per_group;
+  const uint32_t G = min(a.group_tiles, a.row_tiles - g * a.group_tiles);
+  uint32_t c = 0;
+  while (c + 1 < a.n_colors && r >= G * a.color_ptr[c + 1]) ++c;
+  r -= G * a.color_ptr[c];
+  const uint32_t nc = a.color_ptr[c + 1] - a.color_ptr[c];
+  const uint32_t tg = r / nc;
+  return make_uint2(g * a.group_tiles + tg, a.color_ptr[c] + (r - tg * nc));
+}
+
+__global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(const StreamArgs a)
+{
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double2 *acc = reinterpret_cast<double2 *>(smem_raw);                              // [W][T1_STRIDE] (N, D)
+  double *geo = reinterpret_cast<double *>(acc + (size_t)T1_W * T1_STRIDE);          // [NBUF][CHUNK][GEO2_REC]
+  ItemMeta *meta = reinterpret_cast<ItemMeta *>(geo + T1_NBUF * T1_CHUNK * GEO2_REC); // [2] by item parity
+  uint64_t *bar = reinterpret_cast<uint64_t *>(meta + 2);                            // [NBUF] full, [NBUF] empty, [2] next item known
+  uint32_t *s_cnt = reinterpret_cast<uint32_t *>(bar + 2 * T1_NBUF + 2);             // [NBUF] refill counters
+  uint32_t *s_fin = s_cnt + T1_NBUF;                                                 // [2] warps that reported an item flushed
+  volatile uint2 *s_item = reinterpret_cast<volatile uint2 *>(s_fin + 2 + (T1_NBUF & 1)); // [2] by item parity: tile, launch position
+  volatile uint2 *s_desc = s_item + 2;                                               // [2] by item parity: first cell, cells
+  uint64_t *const bar_full = bar, *const bar_empty = bar + T1_NBUF, *const bar_next = bar + 2 * T1_NBUF;
+
+  const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+  const uint32_t ncl = a.n_clusters;
+
+  // stream chunk -> buffer / barrier; msrc: the item's record rides on its first chunk
+  auto issue = [&](uint32_t p0, int ncell, int cidx, int buf, const ItemMeta *msrc, ItemMeta *mdst) {
+    int nc = ncell - cidx * T1_CHUNK;
+    nc = nc < 0 ? 0 : (nc > T1_CHUNK ? T1_CHUNK : nc);
+    const uint32_t gbytes = (uint32_t)nc * GEO2_REC * sizeof(double);
+    mbar_expect_tx(&bar_full[buf], gbytes + (msrc ? (uint32_t)sizeof(ItemMeta) : 0u));
+    if (gbytes)
+      bulk_copy_g2s(geo + buf * T1_CHUNK * GEO2_REC, a.geo + ((size_t)p0 + (size_t)cidx * T1_CHUNK) * GEO2_REC, gbytes,
+                    &bar_full[buf]);
+    if (msrc) bulk_copy_g2s(mdst, msrc, (uint32_t)sizeof(ItemMeta), &bar_full[buf]);
+  };
+
+  if (tid == 0)
+    {
+      for (int b = 0; b < T1_NBUF; ++b)
         {
-          const uint32_t cc = s_col[s];
-          const uint32_t is_add = cc >> 31, is_store = is_add ^ 1u;
-          double *gN = a.Nm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
-          double *gD = a.Dm + (size_t)row_w * a.ld + (cc & 0x7fffffffu);
-          const double2 *an = acc + s * T1_STRIDE + r * T1_THREADS + warp * 32;
-          if (nrw == 32)
+          mbar_init(&bar_full[b], 1);
+          mbar_init(&bar_empty[b], T1_THREADS);
+          s_cnt[b] = 0;
+        }
+      mbar_init(&bar_next[0], 1);
+      mbar_init(&bar_next[1], 1);
+      mbar_arrive(&bar_next[0]); // item 0 is handed over right here: use number n of barrier b announces item 2 n + b
+      s_fin[0] = s_fin[1] = 0;
+      const uint2 i0 = decode_ticket(atomicAdd(a.ticket, 1u), a);
+      s_item[0].x = i0.x;
+      s_item[0].y = i0.y;
+      if (i0.x != 0xffffffffu)
+        {
+          const uint2 d0 = a.desc[i0.y];
+          s_desc[0].x = d0.x;
+          s_desc[0].y = d0.y;
+          for (int b = 0; b < T1_NBUF; ++b) issue(d0.x, (int)d0.y, b, b, b == 0 ? a.meta + i0.y : nullptr, meta);
+        }
+    }
+  __syncthreads();
+
+  const double un[4] = {a.g1_x[0], a.g1_x[1], a.g1_x[2], a.g1_x[3]};
+  const double wq[4] = {a.g1_w[0], a.g1_w[1], a.g1_w[2], a.g1_w[3]};
+  const double wuq[4] = {a.g1_wx[0], a.g1_wx[1], a.g1_wx[2], a.g1_wx[3]};
+  double xi0[T1_RPT], xi1[T1_RPT], xi2[T1_RPT]; // this item's rows
+  double xn0[T1_RPT], xn1[T1_RPT], xn2[T1_RPT]; // prefetched for the next row tile
+  uint32_t cur_tile = 0xffffffffu;
+  uint32_t gbuf = 0, gph = 0; // buffer and phase of the next chunk of this CTA's stream
+  double2 *accT = acc + tid;
+
+  auto load_rows = [&](uint32_t tile, double(&o0)[T1_RPT], double(&o1)[T1_RPT], double(&o2)[T1_RPT]) {
+#pragma unroll
+    for (int r = 0; r < T1_RPT; ++r)
+      {
+        const uint32_t lrow = tile * T1_ROWS + r * T1_THREADS + tid;
+        const uint32_t lrow_c = lrow < a.nloc ? lrow : a.nloc - 1;
+        const double *px = a.xyz + 3 * (size_t)(a.row0 + lrow_c);
+        o0[r] = px[0];
+        o1[r] = px[1];
+        o2[r] = px[2];
+      }
+  };
+
+  for (uint32_t it = 0;; ++it)
+    {
+      const uint32_t tile = s_item[it & 1].x, kpos = s_item[it & 1].y;
+      if (tile == 0xffffffffu) break;
+      if (tile != cur_tile)
+        {
+          if (it == 0)
+            load_rows(tile, xi0, xi1, xi2);
+          else
             {
 #pragma unroll
-              for (int rb = 0; rb < 32; rb += 8)
+              for (int r = 0; r < T1_RPT; ++r) xi0[r] = xn0[r], xi1[r] = xn1[r], xi2[r] = xn2[r];
+            }
+          cur_tile = tile;
+        }
+      // the item's record arrives with its first chunk
+      mbar_wait(&bar_full[gbuf], gph);
+      const ItemMeta *mt = meta + (it & 1);
+      const uint32_t p0 = mt->p0, counts = mt->counts, cluster = mt->cluster;
+      const int ncell = (int)(counts & 0xffu), nslot = (int)((counts >> 8) & 0xffu);
+      const int npred = (int)((counts >> 16) & 0xffu), ntl = (int)(counts >> 24);
+      // every item has at least NBUF + 2 chunks (possibly empty ones): the next item is drawn as late
+      // as the pipeline allows -- NBUF + 2 chunks before this one ends
+      const int nchunk = max(T1_NBUF + 2, (ncell + T1_CHUNK - 1) / T1_CHUNK);
+      const int c_draw = nchunk - T1_NBUF - 2;
+      const uint32_t lrow_base = tile * T1_ROWS;
+
+      bool any_sing = ntl == 0xff;
+      for (int i = 0; i < ntl && i < META_TILES; ++i) any_sing |= (mt->sing_tiles[i] == tile);
+      unsigned long long smask[T1_RPT];
+      double row_sum[T1_RPT];
+#pragma unroll
+      for (int r = 0; r < T1_RPT; ++r)
+        {
+          smask[r] = 0ull;
+          row_sum[r] = 0.0;
+          if (any_sing)
+            {
+              const uint32_t lrow = lrow_base + r * T1_THREADS + tid;
+              const uint32_t lrow_c = lrow < a.nloc ? lrow : a.nloc - 1;
+              for (uint32_t k = a.sing_ptr[lrow_c]; k < a.sing_ptr[lrow_c + 1]; ++k)
                 {
-                  double2 v[8];
+                  const uint32_t pos = a.sing_cellpos[k];
+                  if (pos >= p0 && pos < p0 + ncell) smask[r] |= 1ull << (pos - p0);
+                }
+            }
+        }
+      for (int s = 0; s < nslot; ++s)
 #pragma unroll
-                  for (int i = 0; i < 8; ++i) v[i] = an[rb + i];
-#pragma unroll
-                  for (int i = 0; i < 8; ++i)
-                    {
-                      flush_value(gN, v[i].x, is_add, is_store);
-                      flush_value(gD, v[i].y, is_add, is_store);
-                      gN += a.ld;
-                      gD += a.ld;
+        for (int r = 0; r < T1_RPT; ++r) accT[s * T1_STRIDE + r * T1_THREADS] = make_double2(0.0, 0.0);
+
+      unsigned int *const done_tile = a.done + (size_t)tile * ncl;
+      uint32_t tkn = 0xffffffffu;          // thread 0: the next item's ticket ...
+      uint2 itn = make_uint2(0xffffffffu, 0u), dn = make_uint2(0u, 0u); // ... decoded, and its descriptor
+      for (int c = 0; c < nchunk; ++c)
+        {
+          const int buf = gbuf;
+          const uint32_t ph = gph;
+          if (++gbuf == T1_NBUF) gbuf = 0, gph ^= 1u;
+          mbar_wait(&bar_full[buf], ph);
+          // thread 0 draws the next item: ticket, decode + descriptor, hand-over -- one chunk of
+          // integration between the steps, so that it never waits for the answers
+          if (tid == 0)
+            {
+              if (c == c_draw) asm volatile("atom.global.add.u32 %0, [%1], 1;" : "=r"(tkn) : "l"(a.ticket) : "memory");
+              if (c == c_draw + 1)
+                {
+                  itn = decode_ticket(tkn, a);
+                  if (itn.x != 0xffffffffu)
+                    asm volatile("ld.global.v2.u32 {%0, %1}, [%2];" : "=r"(dn.x), "=r"(dn.y) : "l"(a.desc + itn.y));
+                }
+              if (c == c_draw + 2)
+                {
+                  s_item[(it + 1) & 1].x = itn.x;
+                  s_item[(it + 1) & 1].y = itn.y;
+                  s_desc[(it + 1) & 1].x = dn.x;
+                  s_desc[(it + 1) & 1].y = dn.y;
+                  mbar_arrive(&bar_next[(it + 1) & 1]);
+                }
+            }
+          if (c == nchunk - 1)
+            { // everybody: the next item is known by now; its rows' coordinates are fetched behind this chunk
+              mbar_wait(&bar_next[(it + 1) & 1], ((it + 1) >> 1) & 1);
+              const uint32_t tile_next = s_item[(it + 1) & 1].x;
+              if (tile_next != 0xffffffffu && tile_next != tile) load_rows(tile_next, xn0, xn1, xn2);
+            }
+          const double *gc = geo + buf * T1_CHUNK * GEO2_REC;
+          const int kend = min(T1_CHUNK, ncell - c * T1_CHUNK);
+          for (int kk = 0; kk < kend; ++kk)
+            {
+              const int k = c * T1_CHUNK + kk;
+              const double *g = gc + kk * GEO2_REC;
+              const uint32_t sl = mt->cell_slots[k];
+              CellMoments cm;
+              line_moments<0>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              line_moments<1>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              line_moments<2>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              line_moments<3>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              scatter_cell_distinct(accT, sl, cm, smask, k, row_sum);
+            }
+          // buffer consumed: the warp that arrives last refills it with stream chunk + NBUF
+          mbar_arrive(&bar_empty[buf]);
+          __syncwarp();
+          if (lane == 0)
+            {
+              if (atomicAdd(&s_cnt[buf], 1u) == T1_WARPS - 1)
+                {
+                  s_cnt[buf] = 0;
+                  mbar_wait(&bar_empty[buf], ph);
+                  asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+                  const int target = c + T1_NBUF;
+                  if (target < nchunk)
+                    issue(p0, ncell, target, buf, nullptr, nullptr);
+                  else
+                    { // the next item's first chunks (thread 0 has handed it over before its own arrival)
+                      const uint32_t kn = s_item[(it + 1) & 1].y;
+                      if (s_item[(it + 1) & 1].x != 0xffffffffu)
+                        issue(s_desc[(it + 1) & 1].x, (int)s_desc[(it + 1) & 1].y, target - nchunk, buf,
+                              target == nchunk ? a.meta + kn : nullptr, meta + ((it + 1) & 1));
                     }
                 }
             }
-          else
-            for (int i = 0; i < nrw; ++i)
-              {
-                const double2 v = an[i];
-                flush_value(gN, v.x, is_add, is_store);
-                flush_value(gD, v.y, is_add, is_store);
-                gN += a.ld;
-                gD += a.ld;
-              }
         }
+      __syncwarp(); // a warp flushes exactly the rows its own lanes accumulated
+      // first writers first (nobody to wait for), then the columns other clusters have written before
+      int nstore = 0;
+      for (int sb = 0; sb < nslot; sb += 32)
+        nstore += __popc(__ballot_sync(0xffffffffu, sb + lane < nslot && (mt->slot_col[sb + lane] >> 31) == 0u));
+#ifndef WBEM_DBG_NOFLUSH
+      flush_pass<false>(acc, mt->slot_col, 0, nstore, lrow_base, a.nloc, a.ld, a.Nm, a.Dm, warp, lane);
+#endif
+      // the lower-colour clusters sharing a column must have flushed this row tile (acquire loads of their flags)
+#ifndef WBEM_DBG_NOWAIT
+      if (npred)
+        {
+          bool ok = true;
+#ifdef WBEM_DBG_WAITLOG
+          unsigned int dbg_spins = 0;
+#endif
+          if (lane < npred)
+            {
+              const unsigned int *f = done_tile + mt->pred[lane];
+              uint32_t spins = 0;
+              while (ld_acquire_gpu(f) != a.epoch)
+                {
+                  __nanosleep(200);
+                  if (++spins > (1u << 22))
+                    {
+                      ok = false;
+                      break;
+                    }
+                }
+#ifdef WBEM_DBG_WAITLOG
+              dbg_spins = spins;
+#endif
+            }
+          if (!__all_sync(0xffffffffu, ok) && lane == 0) atomicExch(a.error_flag, 1u);
+#ifdef WBEM_DBG_WAITLOG
+          {
+            unsigned int sp = 0;
+            if (lane < npred) sp = dbg_spins;
+            for (int off = 16; off > 0; off >>= 1) sp = max(sp, __shfl_xor_sync(0xffffffffu, sp, off));
+            if (lane == 0 && warp == 0) a.done[(size_t)a.row_tiles * ncl + (size_t)tile * ncl + kpos] = sp | (blockIdx.x << 20);
+          }
+#endif
+        }
+#endif
+#ifndef WBEM_DBG_NOFLUSH
+      flush_pass<true>(acc, mt->slot_col, nstore, nslot - nstore, lrow_base, a.nloc, a.ld, a.Nm, a.Dm, warp, lane);
+#endif
+#pragma unroll
+      for (int r = 0; r < T1_RPT; ++r)
+        {
+          const uint32_t lrow = lrow_base + r * T1_THREADS + tid;
+          if (lrow < a.nloc) a.alpha_part[(size_t)cluster * a.nloc + lrow] = row_sum[r];
+        }
+      __syncwarp();
+      if (lane == 0) signal_flushed(done_tile + kpos, &s_fin[it & 1], a.epoch);
     }
 }
 
@@ -737,6 +1346,63 @@ __global__ void __launch_bounds__(256)
   if (lane == 0) out[lrow] = -s;
 }
 
+// Per-cluster records of the stream kernel (launch order) and its synchronisation words.
+int wbem_upload_stream_tables(wbem_ctx *ctx, const std::vector<uint32_t> &sing_ptr, const std::vector<uint32_t> &sing_pos,
+                              const std::vector<uint32_t> &cluster_of_pos)
+{
+  const AssemblyPlan &pl = ctx->plan;
+  const uint32_t ncl = pl.n_clusters;
+  const uint32_t row_tiles = (ctx->nloc + T1_ROWS - 1) / T1_ROWS;
+  ctx->stream_ok = ncl > 0 && pl.max_pred <= META_PRED && pl.max_cells <= TILE_MAX_CELLS && pl.W <= T1_W &&
+                   pl.n_colors <= STREAM_MAX_COLORS && (uint64_t)row_tiles * ncl < 0xfffffff0ull;
+  if (!ctx->stream_ok) return 0;
+  // row tiles in which a cluster has singular pairs
+  std::vector<std::vector<uint32_t>> tiles_of(ncl);
+  for (uint32_t r = 0; r < ctx->nloc; ++r)
+    for (uint32_t k = sing_ptr[r]; k < sing_ptr[r + 1]; ++k)
+      {
+        std::vector<uint32_t> &t = tiles_of[cluster_of_pos[sing_pos[k]]];
+        if (t.empty() || t.back() != r / T1_ROWS) t.push_back(r / T1_ROWS); // rows ascend
+      }
+  std::vector<ItemMeta> meta(ncl);
+  std::vector<uint2> desc(ncl);
+  for (uint32_t k = 0; k < ncl; ++k)
+    {
+      const uint32_t cl = pl.color_clusters[k];
+      ItemMeta &m = meta[k];
+      memset(&m, 0, sizeof(m));
+      const uint32_t nc = pl.cl_cell_ptr[cl + 1] - pl.cl_cell_ptr[cl], nsl = pl.cl_slot_ptr[cl + 1] - pl.cl_slot_ptr[cl];
+      const uint32_t npred = pl.pred_ptr[k + 1] - pl.pred_ptr[k];
+      const std::vector<uint32_t> &tl = tiles_of[cl];
+      const uint32_t ntl = tl.size() <= META_TILES ? (uint32_t)tl.size() : 0xffu;
+      m.p0 = pl.cl_cell_ptr[cl];
+      m.counts = nc | (nsl << 8) | (npred << 16) | (ntl << 24);
+      m.cluster = cl;
+      for (uint32_t i = 0; i < npred; ++i) m.pred[i] = pl.pred[pl.pred_ptr[k] + i];
+      if (ntl != 0xffu)
+        for (uint32_t i = 0; i < ntl; ++i) m.sing_tiles[i] = tl[i];
+      for (uint32_t i = 0; i < nc; ++i)
+        memcpy(&m.cell_slots[i], &pl.cell_slots[4 * (size_t)(m.p0 + i)], 4);
+      for (uint32_t i = 0; i < nsl; ++i) m.slot_col[i] = pl.slot_col[pl.cl_slot_ptr[cl] + i];
+      desc[k] = make_uint2(m.p0, nc);
+    }
+  if (ctx->d_item_meta) cudaFree(ctx->d_item_meta);
+  if (ctx->d_item_desc) cudaFree(ctx->d_item_desc);
+  if (ctx->d_asm_sync) cudaFree(ctx->d_asm_sync);
+  ctx->d_item_meta = ctx->d_item_desc = nullptr;
+  ctx->d_asm_sync = nullptr;
+  const size_t nsync = 4 + 2 * (size_t)std::max(1u, row_tiles) * ncl; // (second half: wait log of debug builds)
+  CUDA_OK(ctx, cudaMalloc(&ctx->d_item_meta, sizeof(ItemMeta) * ncl));
+  CUDA_OK(ctx, cudaMalloc(&ctx->d_item_desc, sizeof(uint2) * ncl));
+  CUDA_OK(ctx, cudaMalloc((void **)&ctx->d_asm_sync, sizeof(unsigned int) * nsync));
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_item_meta, meta.data(), sizeof(ItemMeta) * ncl, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(ctx, cudaMemcpyAsync(ctx->d_item_desc, desc.data(), sizeof(uint2) * ncl, cudaMemcpyHostToDevice, ctx->stream));
+  CUDA_OK(ctx, cudaMemsetAsync(ctx->d_asm_sync, 0, sizeof(unsigned int) * nsync, ctx->stream));
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream)); // the host vectors go out of scope
+  ctx->asm_epoch = 0;
+  return 0;
+}
+
 // ---------------------------------------------------------------------------------------
 // host launchers
 // ---------------------------------------------------------------------------------------
@@ -745,15 +1411,23 @@ int wbem_launch_assemble(wbem_ctx *ctx)
   cudaStream_t st = ctx->stream;
   const int nq = ctx->qt.nq;
   if (ctx->nloc == 0 || ctx->C == 0) return 0;
-  const bool tiled = (ctx->p.assemble_variant == 0) && (ctx->qt.n1 == 4) && !ctx->has_degenerate_cells;
+  const bool tiled = (ctx->p.assemble_variant == 0 || ctx->p.assemble_variant == 2) && (ctx->qt.n1 == 4) && !ctx->has_degenerate_cells;
+  // the line records need the cells' vertices: caller-supplied FEValues (any mapping) take the per-point kernel
+  const bool stream = tiled && ctx->p.assemble_variant == 0 && ctx->stream_ok && !ctx->fevalues_given && ctx->d_cellgeo2;
   CUDA_OK(ctx, cudaEventRecord(ctx->ev[0], st));
   if (tiled)
     {
       const AssemblyPlan &pl = ctx->plan;
       if (!ctx->tiled_attr_set)
         { // per device: a second context on another GPU needs its own opt-in
-          CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+          CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_colours, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                             (int)rows_smem_bytes()));
+          CUDA_OK(ctx, cudaFuncSetAttribute(k_assemble_rows, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                            (int)stream_smem_bytes()));
+          CUDA_OK(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&ctx->stream_ctas_per_sm, k_assemble_rows, T1_THREADS,
+                                                                     stream_smem_bytes()));
+          if (ctx->n_sm == 0) CUDA_OK(ctx, cudaDeviceGetAttribute(&ctx->n_sm, cudaDevAttrMultiProcessorCount, ctx->dev));
+          if (const char *e = getenv("WBEM_ASM_GROUP")) ctx->asm_group_tiles = atoi(e); // tuning experiments
           ctx->tiled_attr_set = true;
         }
       // columns no cell touches (none on deal.II meshes) stay zero
@@ -765,6 +1439,57 @@ int wbem_launch_assemble(wbem_ctx *ctx)
           CUDA_OK(ctx, cudaMemset2DAsync(ctx->d_Dm + pl.n_cols_written, ctx->ld * sizeof(double), 0,
                                          w, ctx->nloc, st));
         }
+    }
+  if (stream && ctx->stream_ctas_per_sm > 0)
+    {
+      const AssemblyPlan &pl = ctx->plan;
+      const uint32_t row_tiles = (ctx->nloc + T1_ROWS - 1) / T1_ROWS;
+      StreamArgs a;
+      a.xyz = ctx->d_xyz;
+      a.geo = ctx->d_cellgeo2;
+      a.meta = (const ItemMeta *)ctx->d_item_meta;
+      a.desc = (const uint2 *)ctx->d_item_desc;
+      a.sing_ptr = ctx->d_sing_ptr;
+      a.sing_cellpos = ctx->d_sing_cellpos;
+      a.Nm = ctx->d_Nm;
+      a.Dm = ctx->d_Dm;
+      a.alpha_part = ctx->d_alpha_part;
+      a.ticket = ctx->d_asm_sync;
+      a.error_flag = ctx->d_asm_sync + 1;
+      a.done = ctx->d_asm_sync + 4;
+      if (++ctx->asm_epoch == 0)
+        { // the flags hold epochs: start over after a wrap
+          CUDA_OK(ctx, cudaMemsetAsync(ctx->d_asm_sync, 0, sizeof(unsigned int) * (4 + (size_t)row_tiles * pl.n_clusters), st));
+          ctx->asm_epoch = 1;
+        }
+      a.epoch = ctx->asm_epoch;
+      a.n_items = row_tiles * pl.n_clusters;
+      a.n_clusters = pl.n_clusters;
+      a.ld = ctx->ld;
+      a.row0 = ctx->row0;
+      a.nloc = ctx->nloc;
+      a.row_tiles = row_tiles;
+      a.group_tiles = std::max(1, std::min(ctx->asm_group_tiles, (int)row_tiles));
+      a.n_colors = pl.n_colors;
+      for (uint32_t c = 0; c <= pl.n_colors; ++c) a.color_ptr[c] = pl.color_ptr[c];
+      for (int i = 0; i < 4; ++i)
+        {
+          a.g1_x[i] = ctx->qt.g1_x[i];
+          a.g1_w[i] = ctx->qt.g1_w[i];
+          a.g1_wx[i] = ctx->qt.g1_w[i] * ctx->qt.g1_x[i];
+        }
+      CUDA_OK(ctx, cudaMemsetAsync(ctx->d_asm_sync, 0, sizeof(unsigned int), st)); // ticket
+      const uint32_t want = (uint32_t)(ctx->n_sm * ctx->stream_ctas_per_sm);
+      const uint32_t grid = std::min(want, a.n_items);
+      k_assemble_rows<<<std::max(1u, grid), T1_THREADS, stream_smem_bytes(), st>>>(a);
+      ctx->launches++;
+      CUDA_OK(ctx, cudaGetLastError());
+      if (!ctx->h_asm_flag) CUDA_OK(ctx, cudaMallocHost((void **)&ctx->h_asm_flag, sizeof(unsigned int)));
+      CUDA_OK(ctx, cudaMemcpyAsync(ctx->h_asm_flag, ctx->d_asm_sync + 1, sizeof(unsigned int), cudaMemcpyDeviceToHost, st));
+    }
+  else if (tiled)
+    {
+      const AssemblyPlan &pl = ctx->plan;
       TiledArgs a;
       a.xyz = ctx->d_xyz;
       a.geo = ctx->d_cellgeo;
@@ -790,7 +1515,7 @@ int wbem_launch_assemble(wbem_ctx *ctx)
           if (nclu == 0) continue;
           a.cluster_base = pl.color_ptr[c];
           dim3 grid(nclu, row_tiles);
-          k_assemble_rows<<<grid, T1_THREADS, rows_smem_bytes(), st>>>(a);
+          k_assemble_colours<<<grid, T1_THREADS, rows_smem_bytes(), st>>>(a);
           ctx->launches++;
         }
       CUDA_OK(ctx, cudaGetLastError());
@@ -876,6 +1601,16 @@ extern "C" int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out,
   return 0;
 }
 
+// development: raw copy of the stream kernel's synchronisation words (ticket, error flag, done flags, wait log)
+extern "C" int wbem_debug_read_asm_sync(wbem_ctx *ctx, size_t offset, size_t n, unsigned int *out)
+{
+  if (!ctx || !ctx->d_asm_sync) return -1;
+  CUDA_OK(ctx, cudaStreamSynchronize(ctx->stream));
+  CUDA_OK(ctx, cudaMemcpy(out, ctx->d_asm_sync + offset, n * sizeof(unsigned int), cudaMemcpyDeviceToHost));
+  return 0;
+}
+
 // tile geometry of the regular-pair kernel, for the host-side maps built in wbem_set_topology
 uint32_t wbem_tile_rows(void) { return T1_ROWS; }
 uint32_t wbem_tile_width(void) { return T1_W; }
+uint32_t wbem_line_record_doubles(void) { return GEO2_REC; }

@@ -44,6 +44,12 @@ struct AssemblyPlan
   std::vector<uint32_t> color_clusters;  // cluster ids grouped by color
   std::vector<uint32_t> colpos;          // [N] global dof -> storage column
   std::vector<uint32_t> colperm;         // [N] storage column -> global dof
+  // dependencies of the single-launch kernel: for the cluster at launch position k, the launch
+  // positions (< k, lower colours) of the clusters it shares a dof with -- the ones whose flush
+  // has to land before this cluster's (STORE before ADD, ADDs in colour order)
+  std::vector<uint32_t> pred_ptr;        // [ncl+1] by launch position
+  std::vector<uint32_t> pred;
+  uint32_t max_pred = 0;
 };
 int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t W_max,
                     uint32_t max_cells_per_cluster, AssemblyPlan *plan);
@@ -148,10 +154,20 @@ struct wbem_ctx
   uint32_t *d_slot_col = nullptr;
   uint32_t *d_cta_desc = nullptr; // [clusters][4] in launch order: first cell, first slot, counts, cluster id
   uint8_t *d_cell_slots = nullptr;
+  // single-launch (stream) kernel: per-cluster records, look-ahead descriptors, ticket + error flag + done flags
+  void *d_item_meta = nullptr;
+  void *d_item_desc = nullptr;
+  unsigned int *d_asm_sync = nullptr; // [0] ticket, [1] error flag, [4...] done[row tiles][clusters]
+  bool stream_ok = false;             // the plan fits the records (predecessor lists, cluster sizes)
+  unsigned int asm_epoch = 0;
+  unsigned int *h_asm_flag = nullptr; // pinned copy of the error flag, read after the next synchronisation
+  int stream_ctas_per_sm = 0;
+  int asm_group_tiles = 2; // G: row tiles interleaved colour by colour (environment WBEM_ASM_GROUP overrides)
 
   // geometry
   double *d_xyz = nullptr;     // [N][3]
-  double *d_cellgeo = nullptr; // [C][7][nq] in processing order
+  double *d_cellgeo = nullptr; // [C][8][nq] in processing order
+  double *d_cellgeo2 = nullptr; // [C][GEO2_REC] line records of the stream kernel (4 x 4 rule only)
   bool have_geometry = false, assembled = false, have_alpha = false;
   bool fevalues_given = false; // cellgeo was filled by wbem_set_fevalues, not from the support points
   bool has_degenerate_cells = false; // a cell lists the same dof twice -> simple kernel
@@ -248,9 +264,12 @@ int wbem_upload_tables(wbem_ctx *ctx);
 int wbem_launch_geometry(wbem_ctx *ctx);
 int wbem_upload_fevalues(wbem_ctx *ctx, const double *q_points, const double *normals, const double *JxW);
 int wbem_launch_assemble(wbem_ctx *ctx);
+int wbem_upload_stream_tables(wbem_ctx *ctx, const std::vector<uint32_t> &sing_ptr, const std::vector<uint32_t> &sing_pos,
+                              const std::vector<uint32_t> &cluster_of_pos);
 int wbem_launch_alpha(wbem_ctx *ctx, bool from_matrix = false);
 uint32_t wbem_tile_rows(void);
 uint32_t wbem_tile_width(void);
+uint32_t wbem_line_record_doubles(void);
 // operator.cu
 int wbem_apply_operator(wbem_ctx *ctx, int mode /*0 vmult, 1 rhs*/, const double *d_src,
                         double *d_dst, bool constrained);

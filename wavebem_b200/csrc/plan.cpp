@@ -189,6 +189,29 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
     std::vector<uint32_t> fill(pl->color_ptr.begin(), pl->color_ptr.end() - 1);
     for (uint32_t k = 0; k < ncl; ++k) pl->color_clusters[fill[color[k]]++] = k;
   }
+  // predecessors in launch order (see AssemblyPlan::pred)
+  {
+    std::vector<uint32_t> launch_pos(ncl);
+    for (uint32_t idx = 0; idx < ncl; ++idx) launch_pos[pl->color_clusters[idx]] = idx;
+    pl->pred_ptr.assign(ncl + 1, 0);
+    std::vector<uint32_t> tmp;
+    for (uint32_t idx = 0; idx < ncl; ++idx)
+      {
+        const uint32_t k = pl->color_clusters[idx];
+        tmp.clear();
+        for (uint32_t s = pl->cl_slot_ptr[k]; s < pl->cl_slot_ptr[k + 1]; ++s)
+          {
+            const uint32_t d = cl_nodes_all[s];
+            for (uint32_t a = dptr[d]; a < dptr[d + 1]; ++a)
+              if (dcl[a] != k && launch_pos[dcl[a]] < idx) tmp.push_back(launch_pos[dcl[a]]);
+          }
+        std::sort(tmp.begin(), tmp.end());
+        tmp.erase(std::unique(tmp.begin(), tmp.end()), tmp.end());
+        pl->pred.insert(pl->pred.end(), tmp.begin(), tmp.end());
+        pl->pred_ptr[idx + 1] = (uint32_t)pl->pred.size();
+        pl->max_pred = std::max(pl->max_pred, (uint32_t)tmp.size());
+      }
+  }
   // storage columns in first-writer order; later writers get the ADD flag.  Inside a cluster
   // the slots are reordered so that the STORE slots come first (in column order) and the ADD
   // slots last: the flush of one CTA then writes one contiguous row segment per row with
@@ -260,8 +283,9 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
 }
 
 // Host-only self check of the plan (no GPU needed; used by tests/test_plan.py).
-// stats[0..7] = n_clusters, n_colors, max cells/cluster, max slots/cluster, total slots,
-//               slots flagged ADD, columns written, 32-byte sectors under the ADD slots
+// stats[0..8] = n_clusters, n_colors, max cells/cluster, max slots/cluster, total slots,
+//               slots flagged ADD, columns written, 32-byte sectors under the ADD slots,
+//               longest predecessor list
 // Returns 0 when every invariant holds, a positive code naming the first violated one.
 extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t W_max,
                                uint32_t max_cells, double *stats)
@@ -318,6 +342,26 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
             n_add += add;
           }
       }
+  // 5. predecessor lists: exactly the earlier (lower-colour) clusters sharing a column
+  {
+    std::vector<std::vector<uint32_t>> col_users(N);
+    for (uint32_t idx = 0; idx < ncl; ++idx)
+      {
+        const uint32_t k = pl.color_clusters[idx];
+        std::vector<uint32_t> want;
+        for (uint32_t s = pl.cl_slot_ptr[k]; s < pl.cl_slot_ptr[k + 1]; ++s)
+          {
+            const uint32_t col = pl.slot_col[s] & 0x7fffffffu;
+            want.insert(want.end(), col_users[col].begin(), col_users[col].end());
+            col_users[col].push_back(idx);
+          }
+        std::sort(want.begin(), want.end());
+        want.erase(std::unique(want.begin(), want.end()), want.end());
+        if (pl.pred_ptr[idx + 1] - pl.pred_ptr[idx] != want.size()) return 8;
+        if (!std::equal(want.begin(), want.end(), pl.pred.begin() + pl.pred_ptr[idx])) return 8;
+        if (want.size() > pl.max_pred) return 8;
+      }
+  }
   uint32_t nw = 0;
   for (uint32_t col = 0; col < N; ++col)
     {
@@ -348,6 +392,7 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
               }
         }
       stats[7] = (double)sectors;
+      stats[8] = pl.max_pred;
     }
   return 0;
 }
