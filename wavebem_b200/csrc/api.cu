@@ -208,6 +208,9 @@ static void free_topology(wbem_ctx *ctx)
   FREE_DEV(ctx->d_sol);
   FREE_DEV(ctx->d_V);
   FREE_DEV(ctx->d_h);
+  FREE_DEV(ctx->d_gm);
+  FREE_DEV(ctx->d_gm_ctl);
+  ctx->gm_doubles = 0;
   FREE_DEV(ctx->d_band);
   if (ctx->h_pinned) cudaFreeHost(ctx->h_pinned);
   if (ctx->h_asm_flag) cudaFreeHost(ctx->h_asm_flag);

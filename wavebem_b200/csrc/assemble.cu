@@ -446,9 +446,8 @@ __device__ __forceinline__ void line_moments(const double *__restrict__ g, const
           const double r2 = fma(fma(bb, u, c1[r]), u, c0[r]);
           const double ri = rsqrt_h3(r2);
           const double ri2 = ri * ri;
-          const double ri3 = ri2 * ri;
           const double Rn = fma(e1[r], u, e0[r]);
-          const double av = Rn * ri3;
+          const double av = (Rn * ri) * ri2; // (two products side by side: one level less than r^-3 first)
           if (qx == 0)
             {
               t0n[r] = wq[0] * av;
@@ -489,6 +488,74 @@ __device__ __forceinline__ void line_moments(const double *__restrict__ g, const
         m.SvD[r] = fma(vq, t0d[r], m.SvD[r]);
         m.SuvD[r] = fma(vq, t1d[r], m.SuvD[r]);
       }
+}
+
+// Two Gauss lines at once, written stage by stage over their 8 points: more independent dependency
+// chains in flight per warp (the per-point chain r^2 -> rsqrt -> r^-3 -> moments is ~12 FP64 latencies deep).
+template <int J>
+__device__ __forceinline__ void line_pair_moments(const double *__restrict__ g, const double (&xi0)[T1_RPT],
+                                                  const double (&xi1)[T1_RPT], const double (&xi2)[T1_RPT], const double (&un)[4],
+                                                  const double (&wq)[4], const double (&wuq)[4], CellMoments &m)
+{
+  static_assert(T1_RPT == 1, "written for one row per thread");
+  double c0[2], c1[2], e0[2], e1[2], bb[2];
+#pragma unroll
+  for (int l = 0; l < 2; ++l)
+    {
+      const double2 *L = reinterpret_cast<const double2 *>(g + (J + l) * LINE_REC);
+      const double2 l0 = L[0], l1 = L[1], l2 = L[2], l3 = L[3], l4 = L[4], l5 = L[5], l6 = L[6];
+      bb[l] = l3.x;
+      const double Dx = l0.x - xi0[0], Dy = l0.y - xi1[0], Dz = l1.x - xi2[0];
+      c0[l] = fma(Dz, Dz, fma(Dy, Dy, Dx * Dx));
+      c1[l] = fma(Dz, l2.y, fma(Dy, l2.x, Dx * l1.y));
+      e0[l] = fma(Dz, l4.y, fma(Dy, l4.x, Dx * l3.y));
+      e1[l] = fma(Dz, l6.x, fma(Dy, l5.y, Dx * l5.x));
+    }
+  double r2[8], y[8], t[8], e[8], p[8], ye[8], ri[8], ri3[8], av[8];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) r2[i] = fma(fma(bb[i >> 2], un[i & 3], c1[i >> 2]), un[i & 3], c0[i >> 2]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(r2[i]));
+#pragma unroll
+  for (int i = 0; i < 8; ++i) t[i] = r2[i] * y[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) e[i] = fma(-t[i], y[i], 1.0);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) p[i] = fma(0.375, e[i], 0.5), ye[i] = y[i] * e[i];
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ri[i] = fma(p[i], ye[i], y[i]);
+#pragma unroll
+  for (int i = 0; i < 8; ++i) ri3[i] = ri[i] * ri[i]; // r^-2
+#pragma unroll
+  for (int i = 0; i < 8; ++i) av[i] = (fma(e1[i >> 2], un[i & 3], e0[i >> 2]) * ri[i]) * ri3[i];
+  const double2 *wj2 = reinterpret_cast<const double2 *>(g + 4 * LINE_REC) + J * 4;
+#pragma unroll
+  for (int l = 0; l < 2; ++l)
+    {
+      double t0n = wq[0] * av[4 * l], t1n = wuq[0] * av[4 * l];
+      const double2 w0 = wj2[4 * l];
+      double t0d = w0.x * ri[4 * l], t1d = w0.y * ri[4 * l];
+#pragma unroll
+      for (int qx = 1; qx < 4; ++qx)
+        {
+          const double2 wj = wj2[4 * l + qx];
+          t0n = fma(wq[qx], av[4 * l + qx], t0n);
+          t1n = fma(wuq[qx], av[4 * l + qx], t1n);
+          t0d = fma(wj.x, ri[4 * l + qx], t0d);
+          t1d = fma(wj.y, ri[4 * l + qx], t1d);
+        }
+      const double vq = un[J + l];
+      if (J + l == 0)
+        {
+          m.SN[0] = t0n, m.SuN[0] = t1n, m.SvN[0] = vq * t0n, m.SuvN[0] = vq * t1n;
+          m.SD[0] = t0d, m.SuD[0] = t1d, m.SvD[0] = vq * t0d, m.SuvD[0] = vq * t1d;
+        }
+      else
+        {
+          m.SN[0] += t0n, m.SuN[0] += t1n, m.SvN[0] = fma(vq, t0n, m.SvN[0]), m.SuvN[0] = fma(vq, t1n, m.SuvN[0]);
+          m.SD[0] += t0d, m.SuD[0] += t1d, m.SvD[0] = fma(vq, t0d, m.SvD[0]), m.SuvD[0] = fma(vq, t1d, m.SuvD[0]);
+        }
+    }
 }
 
 // moments -> the four Q1 shape-function sums, added to the cell's four column slots of the thread's
@@ -569,8 +636,8 @@ __device__ __forceinline__ void flush_rows(const double2 *acc, const uint32_t *s
         {
           const uint32_t cc = s_col[s];
           const uint32_t is_add = cc >> 31, is_store = is_add ^ 1u;
-          double *gN = Nm + (size_t)row_w * ld + (cc & 0x7fffffffu);
-          double *gD = Dm + (size_t)row_w * ld + (cc & 0x7fffffffu);
+          double *gN = Nm + (size_t)row_w * ld + (cc & WBEM_SLOT_COL_MASK);
+          double *gD = Dm + (size_t)row_w * ld + (cc & WBEM_SLOT_COL_MASK);
           const double2 *an = acc + s * T1_STRIDE + r * T1_THREADS + warp * 32;
           if (nrw == 32)
             {
@@ -626,7 +693,7 @@ __device__ __forceinline__ void flush_pass(const double2 *acc, const uint32_t *s
           if (part < P)
             {
               const int s = s_begin + sb + j;
-              const uint32_t cc = s_col[s] & 0x7fffffffu;
+              const uint32_t cc = s_col[s] & WBEM_SLOT_COL_MASK;
               double *gN = Nm + (size_t)(row_w + part) * ld + cc;
               double *gD = Dm + (size_t)(row_w + part) * ld + cc;
               const double2 *an = acc + s * T1_STRIDE + r * T1_THREADS + warp * 32 + part;
@@ -1057,10 +1124,15 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
               const double *g = gc + kk * GEO2_REC;
               const uint32_t sl = mt->cell_slots[k];
               CellMoments cm;
+#if !defined(WBEM_NO_LINE_PAIRS) && WBEM_T1_RPT == 1
+              line_pair_moments<0>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              line_pair_moments<2>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+#else
               line_moments<0>(g, xi0, xi1, xi2, un, wq, wuq, cm);
               line_moments<1>(g, xi0, xi1, xi2, un, wq, wuq, cm);
               line_moments<2>(g, xi0, xi1, xi2, un, wq, wuq, cm);
               line_moments<3>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+#endif
               scatter_cell_distinct(accT, sl, cm, smask, k, row_sum);
             }
           // buffer consumed: the warp that arrives last refills it with stream chunk + NBUF
@@ -1090,7 +1162,7 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
       // first writers first (nobody to wait for), then the columns other clusters have written before
       int nstore = 0;
       for (int sb = 0; sb < nslot; sb += 32)
-        nstore += __popc(__ballot_sync(0xffffffffu, sb + lane < nslot && (mt->slot_col[sb + lane] >> 31) == 0u));
+        nstore += __popc(__ballot_sync(0xffffffffu, sb + lane < nslot && (mt->slot_col[sb + lane] & WBEM_SLOT_ADD) == 0u));
 #ifndef WBEM_DBG_NOFLUSH
       flush_pass<false>(acc, mt->slot_col, 0, nstore, lrow_base, a.nloc, a.ld, a.Nm, a.Dm, warp, lane);
 #endif

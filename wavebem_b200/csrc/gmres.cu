@@ -24,9 +24,10 @@
 // fixed reduction order inside a CTA, the segments are summed in order by the consumer)
 __global__ void __launch_bounds__(256)
   k_dots(uint32_t N, const double *__restrict__ V, size_t ldv, const double *__restrict__ w,
-         double *__restrict__ partial)
+         double *__restrict__ partial, const int *stop = nullptr)
 {
   __shared__ double red[8];
+  if (stop && *stop != 0) return; // iteration enqueued ahead of a finished solve
   const double *v = V + (size_t)blockIdx.x * ldv;
   const uint32_t seg = blockIdx.y;
   const uint32_t len = (N + DOT_SEGS - 1) / DOT_SEGS;
@@ -62,10 +63,11 @@ __global__ void __launch_bounds__(256)
 __global__ void __launch_bounds__(128)
   k_project_out(uint32_t N, int k, const double *__restrict__ V, size_t ldv,
                 const double *__restrict__ partial, double *__restrict__ w, double *__restrict__ hacc,
-                int accumulate, double *__restrict__ nrm2)
+                int accumulate, double *__restrict__ nrm2, const int *stop = nullptr)
 {
   extern __shared__ double sh[];
   __shared__ double red[4];
+  if (stop && *stop != 0) return;
   for (int i = threadIdx.x; i < k; i += blockDim.x)
     {
       double t = 0;
@@ -117,7 +119,7 @@ __global__ void __launch_bounds__(128)
 }
 
 // out[0] = ||v||_2   (single CTA, fixed order)
-__global__ void __launch_bounds__(1024) k_norm2(uint32_t N, const double *__restrict__ v, double *out)
+__global__ void __launch_bounds__(1024) k_norm2(uint32_t N, const double *__restrict__ v, double *out, double *out_inv = nullptr)
 {
   __shared__ double red[32];
   double s = 0;
@@ -131,8 +133,72 @@ __global__ void __launch_bounds__(1024) k_norm2(uint32_t N, const double *__rest
       s = red[threadIdx.x];
 #pragma unroll
       for (int off = 16; off > 0; off >>= 1) s += __shfl_xor_sync(0xffffffffu, s, off);
-      if (threadIdx.x == 0) out[0] = sqrt(s);
+      if (threadIdx.x == 0)
+        {
+          out[0] = sqrt(s);
+          if (out_inv) out_inv[0] = 1.0 / sqrt(s);
+        }
     }
+}
+
+// One Arnoldi step's small algebra on the device (one thread): the new Hessenberg column from the
+// accumulated projections hacc[0..dim) and the per-CTA sums of squares of the orthogonalised vector,
+// the Givens rotations (deal.II SolverGMRES::givens_rotation, as restated for the host below -- same
+// operations in the same order, no contraction, so both give the same bits), the residual estimate
+// and the stop decision.  With it the host can enqueue several iterations before it looks.
+//   gm: [0] 1/h[dim] for the mat-vec that consumes the new vector, [1] rho; then gamma[kmax+2],
+//   ci[kmax+2], si[kmax+2], Hs[kmax][ntmp] (rotated columns)
+__global__ void __launch_bounds__(32)
+  k_hessenberg(int inner, int ntmp, unsigned nparts, const double *__restrict__ nrm2, const double *__restrict__ hacc,
+               double *__restrict__ gm, int *__restrict__ ctl, double tol, int accumulated, int max_steps)
+{
+  // one warp: the lanes fetch (coalesced), lane 0 does the arithmetic in the fixed order of the host code
+  __shared__ double s_part[256], s_h[GM_KMAX + 8], s_c[GM_KMAX + 8], s_s[GM_KMAX + 8];
+  if (ctl[0] != 0) return;
+  const int lane = threadIdx.x, dim = inner + 1;
+  double *gamma = gm + 2, *ci = gamma + (ntmp + 2), *si = ci + (ntmp + 2), *H = si + (ntmp + 2) + (size_t)inner * ntmp;
+  for (int i = lane; i < dim; i += 32)
+    {
+      s_h[i] = hacc[i];
+      s_c[i] = ci[i];
+      s_s[i] = si[i];
+    }
+  double ss = 0;
+  for (unsigned base = 0; base < nparts; base += 256)
+    {
+      __syncwarp();
+      for (unsigned i = lane; i < 256 && base + i < nparts; i += 32) s_part[i] = nrm2[base + i];
+      __syncwarp();
+      if (lane == 0)
+        for (unsigned i = 0; i < 256 && base + i < nparts; ++i) ss = __dadd_rn(ss, s_part[i]);
+    }
+  __syncwarp();
+  if (lane != 0) return;
+  const double hd = sqrt(ss);
+  gm[0] = 1.0 / hd;
+  // rotations of the previous columns
+  double lo = s_h[0];
+  for (int i = 0; i < inner; ++i)
+    {
+      const double s = s_s[i], c = s_c[i], t = lo, nx = s_h[i + 1];
+      H[i] = __dadd_rn(__dmul_rn(c, t), __dmul_rn(s, nx));
+      lo = __dadd_rn(__dmul_rn(-s, t), __dmul_rn(c, nx));
+    }
+  // the new rotation
+  const double r = 1.0 / sqrt(__dadd_rn(__dmul_rn(lo, lo), __dmul_rn(hd, hd)));
+  const double sn = __dmul_rn(hd, r), cs = __dmul_rn(lo, r);
+  si[inner] = sn;
+  ci[inner] = cs;
+  H[inner] = __dadd_rn(__dmul_rn(cs, lo), __dmul_rn(sn, hd));
+  const double g_in = gamma[inner];
+  gamma[dim] = __dmul_rn(-sn, g_in);
+  gamma[inner] = __dmul_rn(g_in, cs);
+  const double rho = fabs(__dmul_rn(-sn, g_in));
+  gm[1] = rho;
+  int state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
+  if (!(rho == rho)) state = 2;
+  ctl[1] = dim;
+  ctl[0] = state;
 }
 
 __global__ void k_scale(uint32_t N, double *__restrict__ v, double a)
@@ -482,9 +548,26 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   double *d_nrm = d_part + DOT_SEGS * GM_KMAX;  // [0,nb128) per-CTA |w|^2, directly followed by
   double *d_hacc = d_nrm + nb128;               // [0,KMAX) the accumulated Hessenberg column
   double *hp = ctx->h_pinned;
+  // device-side Arnoldi state (k_hessenberg): the host enqueues `ahead` iterations at a time and only
+  // then reads the stop state back; kernels of iterations past the stop return at once.  The sparse
+  // approximate inverse path is all early-exit kernels; the band / host preconditioners keep one
+  // synchronisation per iteration.
+  const size_t gm_need = 2 + 3 * (size_t)(ntmp + 2) + (size_t)ntmp * ntmp;
+  if (ctx->gm_doubles < gm_need)
+    {
+      if (ctx->d_gm) cudaFree(ctx->d_gm);
+      ctx->d_gm = nullptr;
+      CUDA_OK(ctx, cudaMalloc((void **)&ctx->d_gm, sizeof(double) * gm_need));
+      ctx->gm_doubles = gm_need;
+    }
+  if (!ctx->d_gm_ctl) CUDA_OK(ctx, cudaMalloc((void **)&ctx->d_gm_ctl, sizeof(int) * 8));
+  double *gm = ctx->d_gm;
+  int *ctl = ctx->d_gm_ctl;
+  double *gm_gamma = gm + 2, *gm_H = gm + 2 + 3 * (size_t)(ntmp + 2);
+  const bool spai_path = ctx->p.precond_kind == 1 && ctx->p.preconditioner_band > 0 && !ctx->precond_host_active;
+  const int ahead = spai_path ? 8 : 1;
   CUDA_OK(ctx, cudaMemsetAsync(x, 0, sizeof(double) * N, st));
-  std::vector<double> H((size_t)ntmp * ntmp, 0.0), gamma(ntmp + 1), ci(ntmp + 1), si(ntmp + 1),
-    h(ntmp + 1), y(ntmp + 1);
+  std::vector<double> H((size_t)ntmp * ntmp, 0.0), gamma(ntmp + 1), y(ntmp + 1);
   int accumulated = 0, state = 0;
   double rho = 0;
   bool x_is_zero = true;
@@ -507,51 +590,83 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
       rc = wbem_apply_preconditioner(ctx, p, v0);
       g_timer.end();
       if (rc) return rc;
-      k_norm2<<<1, 1024, 0, st>>>(N, v0, ctx->d_h + 256);
+      // rho = |v0|; its inverse (the normalisation folded into the first mat-vec) stays on the device
+      CUDA_OK(ctx, cudaMemsetAsync(ctl, 0, sizeof(int) * 8, st));
+      k_norm2<<<1, 1024, 0, st>>>(N, v0, ctx->d_h + 256, gm);
       ctx->launches++;
+      CUDA_OK(ctx, cudaMemcpyAsync(gm_gamma, ctx->d_h + 256, sizeof(double), cudaMemcpyDeviceToDevice, st)); // gamma[0] = rho
       CUDA_OK(ctx, cudaMemcpyAsync(hp, ctx->d_h + 256, sizeof(double), cudaMemcpyDeviceToHost, st));
       CUDA_OK(ctx, cudaStreamSynchronize(st));
       rho = hp[0];
       state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
       if (!(rho == rho)) state = 2;
       if (state != 0) break;
-      gamma[0] = rho;
-      // the normalisation of the newest Krylov vector is folded into the mat-vec that consumes it
-      // (k_prep_multipliers scales it in place); the last vector of a cycle is never used again
-      double pending_scale = 1.0 / rho;
       int dim = 0;
-      for (int inner = 0; inner < m && state == 0; ++inner)
+      ctx->op_scale_ptr = gm;
+      ctx->op_stop_ptr = ctl;
+      while (dim < m && state == 0)
         {
-          ++accumulated;
-          double *vv = V + (size_t)(inner + 1) * ldv;
-          // vv = M^-1 (A V[inner]): operator, its epilogue and the preconditioner
-          rc = wbem_apply_operator_ex(ctx, 0, V + (size_t)inner * ldv, vv, true, pending_scale, V + (size_t)inner * ldv, true);
-          ++n_gemv;
-          if (rc) return rc;
-          dim = inner + 1;
-          // CGS2
-          for (int pass = 0; pass < 2; ++pass)
+          int batch = std::min(ahead, m - dim);
+          batch = std::min(batch, std::max(1, max_steps - accumulated));
+          for (int j = 0; j < batch; ++j)
             {
-              k_dots<<<dim3(dim, DOT_SEGS), 256, 0, st>>>(N, V, ldv, vv, d_part);
-              k_project_out<<<nb128, 128, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_part, vv, d_hacc, pass,
-                                                                     d_nrm);
-              ctx->launches += 2;
+              const int inner = dim + j;
+              double *vv = V + (size_t)(inner + 1) * ldv;
+              // vv = M^-1 (A V[inner]): operator, its epilogue and the preconditioner; V[inner] is
+              // normalised in place by the mat-vec's prologue (factor gm[0], left by the step before)
+              rc = wbem_apply_operator_ex(ctx, 0, V + (size_t)inner * ldv, vv, true, 1.0, V + (size_t)inner * ldv, true);
+              ++n_gemv;
+              if (rc)
+                {
+                  ctx->op_scale_ptr = nullptr;
+                  ctx->op_stop_ptr = nullptr;
+                  return rc;
+                }
+              // CGS2
+              for (int pass = 0; pass < 2; ++pass)
+                {
+                  k_dots<<<dim3(inner + 1, DOT_SEGS), 256, 0, st>>>(N, V, ldv, vv, d_part, ctl);
+                  k_project_out<<<nb128, 128, sizeof(double) * (inner + 1), st>>>(N, inner + 1, V, ldv, d_part, vv, d_hacc, pass,
+                                                                                 d_nrm, ctl);
+                  ctx->launches += 2;
+                }
+              k_hessenberg<<<1, 32, 0, st>>>(inner, ntmp, nb128, d_nrm, d_hacc, gm, ctl, tol, accumulated + j + 1, max_steps);
+              ctx->launches++;
             }
-          // one D2H: accumulated h[0..dim) and the per-CTA sums of squares of the new vector
-          CUDA_OK(ctx, cudaMemcpyAsync(hp, d_nrm, sizeof(double) * (nb128 + dim), cudaMemcpyDeviceToHost, st));
+          // one look per batch: stop state, iterations done in this cycle, residual estimate
+          CUDA_OK(ctx, cudaMemcpyAsync(hp, gm + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
+          CUDA_OK(ctx, cudaMemcpyAsync(hp + 8, ctl, sizeof(int) * 2, cudaMemcpyDeviceToHost, st));
           CUDA_OK(ctx, cudaStreamSynchronize(st));
-          for (int i = 0; i < dim; ++i) h[i] = hp[nb128 + i];
-          double ss = 0;
-          for (unsigned i = 0; i < nb128; ++i) ss += hp[i];
-          h[dim] = std::sqrt(ss);
-          pending_scale = 1.0 / h[dim];
-          givens(h, gamma, ci, si, inner);
-          for (int i = 0; i < dim; ++i) H[(size_t)i * ntmp + inner] = h[i];
-          rho = std::fabs(gamma[dim]);
-          state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
-          if (!(rho == rho)) state = 2;
+          const int *hctl = reinterpret_cast<const int *>(hp + 8);
+          const int done = hctl[1] - dim;
+          if (done <= 0 || done > batch)
+            {
+              ctx->op_scale_ptr = nullptr;
+              ctx->op_stop_ptr = nullptr;
+              WBEM_FAIL(ctx, -2, "GMRES: inconsistent device iteration count (%d after %d)", hctl[1], dim);
+            }
+          accumulated += done;
+          dim = hctl[1];
+          state = hctl[0];
+          rho = hp[0];
         }
-      // H y = gamma, x += V y
+      ctx->op_scale_ptr = nullptr;
+      ctx->op_stop_ptr = nullptr;
+      // H y = gamma (rotated columns and right-hand side from the device), x += V y
+      const size_t hneed = (size_t)(ntmp + 2) + (size_t)dim * ntmp;
+      std::vector<double> hbig;
+      double *hb = hp;
+      if (hneed > ctx->pinned_doubles)
+        { // long restart lengths on small problems: pageable staging
+          hbig.resize(hneed);
+          hb = hbig.data();
+        }
+      CUDA_OK(ctx, cudaMemcpyAsync(hb, gm_gamma, sizeof(double) * (dim + 1), cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaMemcpyAsync(hb + ntmp + 2, gm_H, sizeof(double) * (size_t)dim * ntmp, cudaMemcpyDeviceToHost, st));
+      CUDA_OK(ctx, cudaStreamSynchronize(st));
+      for (int i = 0; i <= dim; ++i) gamma[i] = hb[i];
+      for (int c = 0; c < dim; ++c)
+        for (int i = 0; i <= c; ++i) H[(size_t)i * ntmp + c] = hb[ntmp + 2 + (size_t)c * ntmp + i];
       for (int i = dim - 1; i >= 0; --i)
         {
           double s = gamma[i];
@@ -560,6 +675,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
         }
       for (int i = 0; i < dim; ++i) hp[i] = y[i];
       CUDA_OK(ctx, cudaMemcpyAsync(d_h, hp, sizeof(double) * dim, cudaMemcpyHostToDevice, st));
+      // the last Krylov vector of the cycle was never normalised, nor is it used
       k_update_solution<<<nb, 256, sizeof(double) * dim, st>>>(N, dim, V, ldv, d_h, x);
       ctx->launches++;
       CUDA_OK(ctx, cudaStreamSynchronize(st)); // hp is reused next cycle

@@ -27,6 +27,10 @@ int wbem_build_quadrature(int quad_order, int sing_order, QuadTables *qt);
 struct NcclApi; // comm.cpp
 struct WbemGroup; // group.cpp: one context driving several row blocks (GPUs) from one host thread
 
+// slot_col entries: storage column | flags
+#define WBEM_SLOT_ADD 0x80000000u  // an earlier cluster has written the column: add
+#define WBEM_SLOT_COL_MASK 0x7fffffffu
+
 // Tiling plan of the regular-pair kernel, built once per topology (plan.cpp).
 struct AssemblyPlan
 {
@@ -233,6 +237,13 @@ struct wbem_ctx
   unsigned long long p2p_epoch = 0, gemv_done_total = 0;
   unsigned long long *d_done_counter = nullptr;
 
+  // GMRES iterations enqueued ahead of the host (gmres.cu): device-side Hessenberg / Givens state, the
+  // normalisation factor of the newest Krylov vector and the stop flag the iteration kernels look at
+  double *d_gm = nullptr;     // [0] 1/h[dim] (scale of the newest vector), [1] rho; then gamma, ci, si, Hs columns
+  int *d_gm_ctl = nullptr;    // [0] stop state (0 run, 1 converged, 2 failed), [1] inner iterations done in this cycle
+  size_t gm_doubles = 0;
+  const double *op_scale_ptr = nullptr; // set around wbem_apply_operator_ex by the GMRES loop
+  const int *op_stop_ptr = nullptr;
   void *multi = nullptr; // gmres.cu: work vectors of wbem_solve_system_multi (allocated at first use)
   double *d_ymulti = nullptr; // [WBEM_MULTI_MAX][chunk*world] gather buffers of the block mat-vec (no peer stores)
   wbem_timings tm = {};
@@ -285,6 +296,7 @@ struct EpilogueArgs
   int n_peers;
   unsigned long long epoch;
   unsigned int *timeout_flag;
+  const int *stop; // device flag of the GMRES loop: non-zero = this iteration was enqueued ahead of a finished solve, do nothing
 };
 int wbem_spai_apply_fused(wbem_ctx *ctx, const EpilogueArgs &ea, double *d_out);
 int wbem_apply_operator_multi(wbem_ctx *ctx, int mode, int nb, const double *const *d_src, double *const *d_dst,

@@ -76,6 +76,7 @@ __device__ __forceinline__ void gemv_pass(const double *__restrict__ M, const do
 
 struct GemvArgs
 {
+  const int *stop; // GMRES iterations enqueued ahead: non-zero = skip the streaming (the completion protocol still runs)
   const double *M1, *x1, *M2, *x2, *alpha, *xdiag;
   const uint32_t *list1, *list2;
   int n1, n2;
@@ -170,7 +171,8 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t G = gridDim.x, c = blockIdx.x;
   const uint32_t Wt = G * GEMV_WARPS;
-  const uint32_t q = a.n_rows / Wt, rem = a.n_rows - q * Wt;
+  const bool idle = a.stop && *a.stop != 0;
+  const uint32_t q = idle ? 0u : a.n_rows / Wt, rem = idle ? 0u : a.n_rows - q * Wt;
   uint32_t r0 = (c * GEMV_WARPS + warp) * q;
   const uint32_t r1 = r0 + q;
   while (r0 < r1)
@@ -218,10 +220,12 @@ __global__ void k_prep_multipliers(uint32_t N, const double *__restrict__ src,
                                    const double *__restrict__ m1, const double *__restrict__ m2,
                                    const uint32_t *__restrict__ colpos, double *__restrict__ x1p,
                                    double *__restrict__ x2p, double *__restrict__ xdiag, double scale = 1.0,
-                                   double *src_rw = nullptr)
+                                   double *src_rw = nullptr, const double *scale_ptr = nullptr, const int *stop = nullptr)
 {
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (stop && *stop != 0) return;
+  if (scale_ptr) scale = *scale_ptr;
   double s;
   if (src_rw)
     {
@@ -242,7 +246,7 @@ __global__ void k_epilogue(uint32_t N, const double *y, const double *__restrict
                            const int32_t *__restrict__ line_of, const uint32_t *__restrict__ cptr,
                            const uint32_t *__restrict__ ccol, const double *__restrict__ cval,
                            double shift, double *__restrict__ dst, const unsigned long long *flags, int n_peers,
-                           unsigned long long epoch, unsigned int *timeout_flag)
+                           unsigned long long epoch, unsigned int *timeout_flag, const int *stop = nullptr)
 {
   if (flags)
     { // fused gather: wait until every rank has raised its flag for this epoch.  The wait is
@@ -271,6 +275,7 @@ __global__ void k_epilogue(uint32_t N, const double *y, const double *__restrict
     }
   const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
+  if (stop && *stop != 0) return;
   double v = y[i] + shift;
   if (line_of)
     {
@@ -363,7 +368,8 @@ int wbem_apply_operator_ex(wbem_ctx *ctx, int mode, const double *d_src, double 
   const double *m1 = mode == 0 ? ctx->d_other : ctx->d_surf; // multiplier mask of N
   const double *m2 = mode == 0 ? ctx->d_surf : ctx->d_other; // multiplier mask of D
   k_prep_multipliers<<<(N + 255) / 256, 256, 0, st>>>(N, d_src, m1, m2, ctx->d_colpos, ctx->d_xn,
-                                                     ctx->d_xd, ctx->d_xdiag, src_scale, src_scale_rw);
+                                                     ctx->d_xd, ctx->d_xdiag, src_scale, src_scale_rw,
+                                                     src_scale_rw ? ctx->op_scale_ptr : nullptr, ctx->op_stop_ptr);
   ctx->launches++;
   double *yloc = ctx->d_yloc + (size_t)ctx->p.rank * ctx->chunk;
   const int P = ctx->p.world_size;
@@ -382,6 +388,7 @@ int wbem_apply_operator_ex(wbem_ctx *ctx, int mode, const double *d_src, double 
           if (ctas_per_sm < 1) ctas_per_sm = 1;
         }
       GemvArgs ga;
+      ga.stop = ctx->op_stop_ptr;
       ga.M1 = ctx->d_Nm;
       ga.x1 = ctx->d_xn;
       ga.M2 = ctx->d_Dm;
@@ -472,12 +479,13 @@ int wbem_apply_operator_ex(wbem_ctx *ctx, int mode, const double *d_src, double 
       ea.n_peers = P;
       ea.epoch = ctx->p2p_epoch;
       ea.timeout_flag = ctx->d_gather_timeout;
+      ea.stop = ctx->op_stop_ptr;
       return wbem_spai_apply_fused(ctx, ea, d_dst);
     }
   double *d_mid = with_precond ? ctx->d_tmp[0] : d_dst;
   k_epilogue<<<(N + 255) / 256, 256, 0, st>>>(N, ygather, d_src, con ? ctx->d_con_line_of : nullptr, ctx->d_con_ptr,
                                              ctx->d_con_col, ctx->d_con_val, 0.0, d_mid, flags, P, ctx->p2p_epoch,
-                                             ctx->d_gather_timeout);
+                                             ctx->d_gather_timeout, ctx->op_stop_ptr);
   ctx->launches++;
   CUDA_OK(ctx, cudaGetLastError());
   if (with_precond) return wbem_apply_preconditioner(ctx, d_mid, d_dst);
@@ -605,7 +613,8 @@ __global__ void __launch_bounds__(GEMV_WARPS * 32, 2) k_bem_gemv_multi(const Gem
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
   const uint32_t G = gridDim.x, c = blockIdx.x;
   const uint32_t Wt = G * GEMV_WARPS;
-  const uint32_t q = a.n_rows / Wt, rem = a.n_rows - q * Wt;
+  const bool idle = a.stop && *a.stop != 0;
+  const uint32_t q = idle ? 0u : a.n_rows / Wt, rem = idle ? 0u : a.n_rows - q * Wt;
   uint32_t r0 = (c * GEMV_WARPS + warp) * q;
   const uint32_t r1 = r0 + q;
   while (r0 < r1)
@@ -741,6 +750,7 @@ int wbem_apply_operator_multi(wbem_ctx *ctx, int mode, int nb, const double *con
       }
     GemvMultiArgs ma;
     GemvArgs &ga = ma.g;
+    ga.stop = nullptr;
     ga.M1 = ctx->d_Nm;
     ga.x1 = mw->d_xn;
     ga.M2 = ctx->d_Dm;

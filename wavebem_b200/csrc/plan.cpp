@@ -252,7 +252,7 @@ int wbem_build_plan(uint32_t N, uint32_t C, const uint32_t *cell_dofs, uint32_t 
               ++next_col;
             }
           else
-            pl->slot_col[s] = pl->colpos[d] | 0x80000000u;
+            pl->slot_col[s] = pl->colpos[d] | WBEM_SLOT_ADD;
         }
     }
   // slot index of each cell's local dofs (after the reordering above)
@@ -316,7 +316,7 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
           {
             const uint32_t s = pl.cell_slots[4 * (size_t)p + j];
             if (s >= nsl) return 3;
-            const uint32_t col = pl.slot_col[pl.cl_slot_ptr[k] + s] & 0x7fffffffu;
+            const uint32_t col = pl.slot_col[pl.cl_slot_ptr[k] + s] & WBEM_SLOT_COL_MASK;
             if (col >= N || pl.colperm[col] != cell_dofs[4 * (size_t)pl.cell_order[p] + j]) return 3;
           }
     }
@@ -333,7 +333,7 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
         const uint32_t k = pl.color_clusters[idx];
         for (uint32_t s = pl.cl_slot_ptr[k]; s < pl.cl_slot_ptr[k + 1]; ++s)
           {
-            const uint32_t col = pl.slot_col[s] & 0x7fffffffu;
+            const uint32_t col = pl.slot_col[s] & WBEM_SLOT_COL_MASK;
             const bool add = pl.slot_col[s] >> 31;
             if (last_color[col] == c) return 5;
             last_color[col] = c;
@@ -351,7 +351,7 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
         std::vector<uint32_t> want;
         for (uint32_t s = pl.cl_slot_ptr[k]; s < pl.cl_slot_ptr[k + 1]; ++s)
           {
-            const uint32_t col = pl.slot_col[s] & 0x7fffffffu;
+            const uint32_t col = pl.slot_col[s] & WBEM_SLOT_COL_MASK;
             want.insert(want.end(), col_users[col].begin(), col_users[col].end());
             col_users[col].push_back(idx);
           }
@@ -386,7 +386,7 @@ extern "C" int wbem_plan_check(uint32_t N, uint32_t C, const uint32_t *cell_dofs
           for (uint32_t s = pl.cl_slot_ptr[k]; s < pl.cl_slot_ptr[k + 1]; ++s)
             if (pl.slot_col[s] >> 31)
               {
-                const uint32_t sec = (pl.slot_col[s] & 0x7fffffffu) / 4;
+                const uint32_t sec = (pl.slot_col[s] & WBEM_SLOT_COL_MASK) / 4;
                 if (sec != last) ++sectors; // ADD slots are sorted by column
                 last = sec;
               }

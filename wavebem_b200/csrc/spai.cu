@@ -413,6 +413,7 @@ __global__ void __launch_bounds__(256)
         }
       __syncthreads();
     }
+  if (e.stop && *e.stop != 0) return; // enqueued ahead of a finished solve (uniform over the grid)
   const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
   const uint32_t i = t >> 3, part = t & 7;
   double s = 0.0;
