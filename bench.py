@@ -512,7 +512,7 @@ def run_ours(args):
                               "share_of_step": acc["gemv"] / (ms_total)},
             # the path's second bound is the FP64 pipe, not the tensor cores: "fp64" says so; peak is
             # the DFMA rate measured in this run (MEASURED_PEAKS.json has no FP64 entry)
-            "roofline_assembly": {"bound": "fp64", "kernel": "k_assemble_rows (one launch per colour)",
+            "roofline_assembly": {"bound": "fp64", "kernel": "k_assemble_rows (one persistent launch per assembly)",
                                   "achieved": asm_tflops, "peak": fp64_peak, "unit": "TFLOP/s",
                                   "frac": asm_tflops / fp64_peak if fp64_peak else None, "traffic": asm_traffic,
                                   "flop_per_eval": FLOP_PER_EVAL, "evals_per_step": evals,

@@ -29,7 +29,7 @@ if [ "$MODE" != "quick" ]; then
   timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file $OUT/launches.csv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_list.log 2>&1; echo "ncu list rc=$?" | tee -a $OUT/summary.log
   echo "== ncu full: assembly + gemv" | tee -a $OUT/summary.log
-  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_assemble_rows -s 5 -c 5 -f -o $OUT/prof_assemble \
+  timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_assemble_rows -s 2 -c 1 -f -o $OUT/prof_assemble \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_asm.log 2>&1; echo "ncu asm rc=$?" | tee -a $OUT/summary.log
   timeout 900 ncu --set full --clock-control none --import-source on -k regex:k_bem_gemv -s 4 -c 2 -f -o $OUT/prof_gemv \
       python bench.py --steps 1 --warmup 1 --no-cpu-baseline > $OUT/ncu_gemv.log 2>&1; echo "ncu gemv rc=$?" | tee -a $OUT/summary.log
@@ -41,8 +41,7 @@ if [ "$MODE" != "quick" ]; then
   timeout 600 python bench.py --config 5 --nodes 20000 --steps 3 --warmup 1 --jv-batched 2>/dev/null | tail -1 > $OUT/bench_cfg5_20k_batched.json
   timeout 600 python bench.py --config 5 --steps 10 --warmup 2 2>/dev/null | tail -1 > $OUT/bench_cfg5_4k.json
   timeout 300 python bench.py --impl reference --steps 2 --warmup 1 2>/dev/null | tail -1 > $OUT/bench_reference.json
-  echo "== SASS of the two hot kernels" | tee -a $OUT/summary.log
-  cuobjdump -sass wavebem_b200/lib/assemble.o | awk '/Function : .*k_assemble_rows/{f=1} /Function : /{if(!/k_assemble_rows/)f=0} f' > $OUT/sass_k_assemble_rows.txt
-  cuobjdump -sass wavebem_b200/lib/operator.o | awk '/Function : .*k_bem_gemv9GemvArgs/{f=1} /Function : /{if(!/k_bem_gemv9GemvArgs/)f=0} f' > $OUT/sass_k_bem_gemv.txt
+  echo "== DRAM bytes of one assembly against the row-tile group size G (WBEM_ASM_GROUP)" | tee -a $OUT/summary.log
+  GROUPS_TO_TRY="1 2 3 4" bash scripts/asm_dram.sh 20000 2>&1 | tee $OUT/assemble_dram_vs_group.txt | tee -a $OUT/summary.log
 fi
 echo "== done" | tee -a $OUT/summary.log

@@ -101,14 +101,15 @@ if t:
               open(os.path.join(PROF, "gemv_dram_bytes_per_launch.json"), "w"))
 t = summarize(os.path.join(OUT, "prof_assemble.ncu-rep"), "assemble")
 if t:
-    # the capture holds the launches (one per colour) of ONE assembly: the step's traffic is their sum
+    # the capture holds the launch(es) of ONE assembly (the stream kernel: one): the step's traffic is their sum
     json.dump({"bytes_per_step": sum(t), "launches_captured": len(t),
                "kernel_source_sha1_16": kernel_source_hash(),
                "source": "sum over the k_assemble_rows launches of one assembly of dram__bytes_read.sum + "
                          "dram__bytes_write.sum, ncu --set full"},
               open(os.path.join(PROF, "assemble_dram_bytes_per_step.json"), "w"))
-for f in ("bench.json", "gpu_info.csv"):
+for f in ("bench.json", "gpu_info.csv", "assemble_dram_vs_group.txt", "bench_cfg3_g1.json", "bench_cfg5_20k.json", "bench_cfg5_20k_batched.json", "bench_cfg5_4k.json", "bench_reference.json"):
     src = os.path.join(OUT, f)
     if os.path.exists(src):
         open(os.path.join(PROF, f"{tag}_{f}"), "w").write(open(src).read())
+subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "sass_excerpts.py"), tag])
 print("profiles written to", PROF)

@@ -58,15 +58,87 @@ __global__ void __launch_bounds__(256)
     }
 }
 
+// One Arnoldi step's small algebra on the device (one warp; lane 0 does the arithmetic): the new
+// Hessenberg column from the accumulated projections hacc[0..dim) and the per-CTA sums of squares of the
+// orthogonalised vector, the Givens rotations (deal.II SolverGMRES::givens_rotation, as restated for the
+// host below -- same operations in the same order, no contraction, so both give the same bits), the
+// residual estimate and the stop decision.  With it the host can enqueue several iterations before it looks.
+//   gm: [0] 1/h[dim] for the mat-vec that consumes the new vector, [1] rho; then gamma[ntmp+2],
+//   ci[ntmp+2], si[ntmp+2], Hs[..][ntmp] (rotated columns)
+struct HessArgs
+{
+  double *gm;            // null: no Hessenberg step behind this launch
+  int *ctl;              // [0] stop state, [1] inner iterations done in this cycle
+  unsigned int *counter; // CTAs of the launch that have finished (the last one runs the step)
+  const double *hacc;
+  int inner, ntmp, accumulated, max_steps;
+  double tol;
+};
+
+struct HessShared
+{
+  double part[128], h[GM_KMAX + 8], c[GM_KMAX + 8], s[GM_KMAX + 8];
+};
+
+__device__ __forceinline__ void hessenberg_step(const HessArgs &a, const double *nrm2, unsigned nparts, HessShared &sh, int lane)
+{
+  const int inner = a.inner, ntmp = a.ntmp, dim = inner + 1;
+  double *gm = a.gm;
+  double *gamma = gm + 2, *ci = gamma + (ntmp + 2), *si = ci + (ntmp + 2), *H = si + (ntmp + 2) + (size_t)inner * ntmp;
+  for (int i = lane; i < dim; i += 32)
+    {
+      sh.h[i] = __ldcg(a.hacc + i); // (written by other CTAs of this launch: L2, not a stale L1 line)
+      sh.c[i] = __ldcg(ci + i);
+      sh.s[i] = __ldcg(si + i);
+    }
+  const double g_in = __ldcg(gamma + inner);
+  double ss = 0;
+  for (unsigned base = 0; base < nparts; base += 128)
+    {
+      __syncwarp();
+      for (unsigned i = lane; i < 128 && base + i < nparts; i += 32) sh.part[i] = __ldcg(nrm2 + base + i);
+      __syncwarp();
+      if (lane == 0)
+        for (unsigned i = 0; i < 128 && base + i < nparts; ++i) ss = __dadd_rn(ss, sh.part[i]);
+    }
+  __syncwarp();
+  if (lane != 0) return;
+  const double hd = sqrt(ss);
+  gm[0] = 1.0 / hd;
+  double lo = sh.h[0];
+  for (int i = 0; i < inner; ++i)
+    { // rotations of the previous columns
+      const double s = sh.s[i], c = sh.c[i], t = lo, nx = sh.h[i + 1];
+      H[i] = __dadd_rn(__dmul_rn(c, t), __dmul_rn(s, nx));
+      lo = __dadd_rn(__dmul_rn(-s, t), __dmul_rn(c, nx));
+    }
+  const double r = 1.0 / sqrt(__dadd_rn(__dmul_rn(lo, lo), __dmul_rn(hd, hd))); // the new rotation
+  const double sn = __dmul_rn(hd, r), cs = __dmul_rn(lo, r);
+  si[inner] = sn;
+  ci[inner] = cs;
+  H[inner] = __dadd_rn(__dmul_rn(cs, lo), __dmul_rn(sn, hd));
+  gamma[dim] = __dmul_rn(-sn, g_in);
+  gamma[inner] = __dmul_rn(g_in, cs);
+  const double rho = fabs(__dmul_rn(-sn, g_in));
+  gm[1] = rho;
+  int state = (rho <= a.tol) ? 1 : ((a.accumulated >= a.max_steps) ? 2 : 0);
+  if (!(rho == rho)) state = 2;
+  a.ctl[1] = dim;
+  __threadfence();
+  a.ctl[0] = state;
+}
+
 // h[i] = sum_seg partial ; w -= sum_i h[i] V[i] ; hacc[i] (+)= h[i] (block 0) ;
 // nrm2[blockIdx.x] = sum over this CTA's entries of w_j^2 (after the update)
 __global__ void __launch_bounds__(128)
   k_project_out(uint32_t N, int k, const double *__restrict__ V, size_t ldv,
                 const double *__restrict__ partial, double *__restrict__ w, double *__restrict__ hacc,
-                int accumulate, double *__restrict__ nrm2, const int *stop = nullptr)
+                int accumulate, double *__restrict__ nrm2, const int *stop = nullptr, const HessArgs hs = HessArgs{})
 {
   extern __shared__ double sh[];
   __shared__ double red[4];
+  __shared__ bool s_last;
+  __shared__ HessShared s_hess;
   if (stop && *stop != 0) return;
   for (int i = threadIdx.x; i < k; i += blockDim.x)
     {
@@ -116,6 +188,22 @@ __global__ void __launch_bounds__(128)
       for (int kk = 0; kk < 4; ++kk) t += red[kk];
       nrm2[blockIdx.x] = t;
     }
+  if (hs.gm)
+    { // second pass: the CTA that finishes last does the Arnoldi step's small algebra (no extra launch)
+      __syncthreads();
+      if (threadIdx.x == 0)
+        {
+          __threadfence();
+          s_last = (atomicAdd(hs.counter, 1u) == gridDim.x - 1);
+        }
+      __syncthreads();
+      if (s_last && threadIdx.x < 32)
+        {
+          __threadfence();
+          if (threadIdx.x == 0) *hs.counter = 0;
+          hessenberg_step(hs, nrm2, gridDim.x, s_hess, threadIdx.x);
+        }
+    }
 }
 
 // out[0] = ||v||_2   (single CTA, fixed order)
@@ -139,66 +227,6 @@ __global__ void __launch_bounds__(1024) k_norm2(uint32_t N, const double *__rest
           if (out_inv) out_inv[0] = 1.0 / sqrt(s);
         }
     }
-}
-
-// One Arnoldi step's small algebra on the device (one thread): the new Hessenberg column from the
-// accumulated projections hacc[0..dim) and the per-CTA sums of squares of the orthogonalised vector,
-// the Givens rotations (deal.II SolverGMRES::givens_rotation, as restated for the host below -- same
-// operations in the same order, no contraction, so both give the same bits), the residual estimate
-// and the stop decision.  With it the host can enqueue several iterations before it looks.
-//   gm: [0] 1/h[dim] for the mat-vec that consumes the new vector, [1] rho; then gamma[kmax+2],
-//   ci[kmax+2], si[kmax+2], Hs[kmax][ntmp] (rotated columns)
-__global__ void __launch_bounds__(32)
-  k_hessenberg(int inner, int ntmp, unsigned nparts, const double *__restrict__ nrm2, const double *__restrict__ hacc,
-               double *__restrict__ gm, int *__restrict__ ctl, double tol, int accumulated, int max_steps)
-{
-  // one warp: the lanes fetch (coalesced), lane 0 does the arithmetic in the fixed order of the host code
-  __shared__ double s_part[256], s_h[GM_KMAX + 8], s_c[GM_KMAX + 8], s_s[GM_KMAX + 8];
-  if (ctl[0] != 0) return;
-  const int lane = threadIdx.x, dim = inner + 1;
-  double *gamma = gm + 2, *ci = gamma + (ntmp + 2), *si = ci + (ntmp + 2), *H = si + (ntmp + 2) + (size_t)inner * ntmp;
-  for (int i = lane; i < dim; i += 32)
-    {
-      s_h[i] = hacc[i];
-      s_c[i] = ci[i];
-      s_s[i] = si[i];
-    }
-  double ss = 0;
-  for (unsigned base = 0; base < nparts; base += 256)
-    {
-      __syncwarp();
-      for (unsigned i = lane; i < 256 && base + i < nparts; i += 32) s_part[i] = nrm2[base + i];
-      __syncwarp();
-      if (lane == 0)
-        for (unsigned i = 0; i < 256 && base + i < nparts; ++i) ss = __dadd_rn(ss, s_part[i]);
-    }
-  __syncwarp();
-  if (lane != 0) return;
-  const double hd = sqrt(ss);
-  gm[0] = 1.0 / hd;
-  // rotations of the previous columns
-  double lo = s_h[0];
-  for (int i = 0; i < inner; ++i)
-    {
-      const double s = s_s[i], c = s_c[i], t = lo, nx = s_h[i + 1];
-      H[i] = __dadd_rn(__dmul_rn(c, t), __dmul_rn(s, nx));
-      lo = __dadd_rn(__dmul_rn(-s, t), __dmul_rn(c, nx));
-    }
-  // the new rotation
-  const double r = 1.0 / sqrt(__dadd_rn(__dmul_rn(lo, lo), __dmul_rn(hd, hd)));
-  const double sn = __dmul_rn(hd, r), cs = __dmul_rn(lo, r);
-  si[inner] = sn;
-  ci[inner] = cs;
-  H[inner] = __dadd_rn(__dmul_rn(cs, lo), __dmul_rn(sn, hd));
-  const double g_in = gamma[inner];
-  gamma[dim] = __dmul_rn(-sn, g_in);
-  gamma[inner] = __dmul_rn(g_in, cs);
-  const double rho = fabs(__dmul_rn(-sn, g_in));
-  gm[1] = rho;
-  int state = (rho <= tol) ? 1 : ((accumulated >= max_steps) ? 2 : 0);
-  if (!(rho == rho)) state = 2;
-  ctl[1] = dim;
-  ctl[0] = state;
 }
 
 __global__ void k_scale(uint32_t N, double *__restrict__ v, double a)
@@ -548,7 +576,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   double *d_nrm = d_part + DOT_SEGS * GM_KMAX;  // [0,nb128) per-CTA |w|^2, directly followed by
   double *d_hacc = d_nrm + nb128;               // [0,KMAX) the accumulated Hessenberg column
   double *hp = ctx->h_pinned;
-  // device-side Arnoldi state (k_hessenberg): the host enqueues `ahead` iterations at a time and only
+  // device-side Arnoldi state (k_hessenberg): the host enqueues `ahead` (4) iterations at a time and only
   // then reads the stop state back; kernels of iterations past the stop return at once.  The sparse
   // approximate inverse path is all early-exit kernels; the band / host preconditioners keep one
   // synchronisation per iteration.
@@ -565,14 +593,14 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   int *ctl = ctx->d_gm_ctl;
   double *gm_gamma = gm + 2, *gm_H = gm + 2 + 3 * (size_t)(ntmp + 2);
   const bool spai_path = ctx->p.precond_kind == 1 && ctx->p.preconditioner_band > 0 && !ctx->precond_host_active;
-  const int ahead = spai_path ? 8 : 1;
+  const int ahead = spai_path ? 4 : 1;
   CUDA_OK(ctx, cudaMemsetAsync(x, 0, sizeof(double) * N, st));
   std::vector<double> H((size_t)ntmp * ntmp, 0.0), gamma(ntmp + 1), y(ntmp + 1);
   int accumulated = 0, state = 0;
   double rho = 0;
   bool x_is_zero = true;
   g_timer.begin(T_GMRES);
-  int n_gemv = 0;
+  int n_gemv = 0, n_idle = 0; // n_idle: iterations enqueued past the stop (their kernels return at once)
   do
     {
       double *v0 = V;
@@ -625,13 +653,24 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
               // CGS2
               for (int pass = 0; pass < 2; ++pass)
                 {
+                  HessArgs hs{};
+                  if (pass == 1)
+                    { // the Arnoldi step's small algebra rides on the last CTA of the second projection
+                      hs.gm = gm;
+                      hs.ctl = ctl;
+                      hs.counter = reinterpret_cast<unsigned int *>(ctl + 4);
+                      hs.hacc = d_hacc;
+                      hs.inner = inner;
+                      hs.ntmp = ntmp;
+                      hs.accumulated = accumulated + j + 1;
+                      hs.max_steps = max_steps;
+                      hs.tol = tol;
+                    }
                   k_dots<<<dim3(inner + 1, DOT_SEGS), 256, 0, st>>>(N, V, ldv, vv, d_part, ctl);
                   k_project_out<<<nb128, 128, sizeof(double) * (inner + 1), st>>>(N, inner + 1, V, ldv, d_part, vv, d_hacc, pass,
-                                                                                 d_nrm, ctl);
+                                                                                 d_nrm, ctl, hs);
                   ctx->launches += 2;
                 }
-              k_hessenberg<<<1, 32, 0, st>>>(inner, ntmp, nb128, d_nrm, d_hacc, gm, ctl, tol, accumulated + j + 1, max_steps);
-              ctx->launches++;
             }
           // one look per batch: stop state, iterations done in this cycle, residual estimate
           CUDA_OK(ctx, cudaMemcpyAsync(hp, gm + 1, sizeof(double), cudaMemcpyDeviceToHost, st));
@@ -646,6 +685,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
               WBEM_FAIL(ctx, -2, "GMRES: inconsistent device iteration count (%d after %d)", hctl[1], dim);
             }
           accumulated += done;
+          n_idle += batch - done;
           dim = hctl[1];
           state = hctl[0];
           rho = hp[0];
@@ -709,7 +749,7 @@ int wbem_solve_system_device(wbem_ctx *ctx, double *d_phi, double *d_dphi_dn, co
   ctx->tm.constraints_ms = sums[T_CONSTRAINTS];
   ctx->tm.solve_system_total_ms = ms;
   ctx->tm.gmres_iters = accumulated;
-  ctx->tm.gemv_calls = counts[T_GEMV];
+  ctx->tm.gemv_calls = counts[T_GEMV] - n_idle; // mat-vecs that streamed the matrices
   (void)n_gemv;
   if (iters_out) *iters_out = accumulated;
   if (last_res_out) *last_res_out = rho;

@@ -165,7 +165,7 @@ __device__ __forceinline__ void gemv_row_split(const GemvArgs &a, uint32_t idx, 
 // whole rows; the n_rows - q*warps remainder rows are split column-wise over the 8 warps of a
 // CTA, so all warps finish together whatever the row count (no tail wave, no 3-rows-vs-2 skew
 // on row-sharded runs).
-__global__ void __launch_bounds__(GEMV_WARPS * 32) k_bem_gemv(const GemvArgs a)
+__global__ void __launch_bounds__(GEMV_WARPS * 32, 3) k_bem_gemv(const GemvArgs a)
 {
   __shared__ double red[GEMV_WARPS];
   const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
