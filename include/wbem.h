@@ -278,6 +278,12 @@ int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out, int n);
 int wbem_plan_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *cell_dofs, uint32_t w_max,
                     uint32_t max_cells, double *stats9);
 
+/* host-only check of the item order of the single-launch assembly kernel (no GPU): every (row tile, cluster)
+ * is drawn exactly once and after the clusters it has to wait for; stats4 = items, smallest / mean ticket
+ * distance to a predecessor, row tiles.  0 = holds; 101 = this mesh takes the colour-per-launch kernel */
+int wbem_stream_order_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *cell_dofs, uint32_t n_rows,
+                            uint32_t group_tiles, double *stats4);
+
 #ifdef __cplusplus
 }
 #endif

@@ -29,6 +29,31 @@ def test_plan_invariants(wb, make):
     assert st[2] <= 64 and st[3] <= 48 and st[6] == m.n_nodes
 
 
+def test_stream_kernel_item_order(wb):
+    """Ticket order of the single-launch assembly kernel (assemble.cu, decode_ticket_order): a bijection onto
+    (row tile, cluster), predecessors always drawn earlier, for every group size and ragged row counts; with
+    G tiles per group an item and its predecessors are ~G x (clusters of a colour) tickets apart."""
+    m = meshgen.wigley_tank_for_nodes(6000)
+    cells = np.ascontiguousarray(m.cells, dtype=np.uint32)
+    f = wb.lib().wbem_stream_order_check
+    mean = {}
+    for n_rows in (m.n_nodes, m.n_nodes // 3 + 5, 1, 129):
+        for g in (1, 2, 3, 7, 1000):
+            st = np.zeros(4)
+            rc = f(C.c_uint32(m.n_nodes), C.c_uint32(m.n_cells), cells.ctypes.data_as(C.c_void_p), C.c_uint32(n_rows),
+                   C.c_uint32(g), st.ctypes.data_as(C.c_void_p))
+            assert rc == 0, (n_rows, g, rc)
+            assert st[3] == (n_rows + 127) // 128 and st[1] >= 1
+            if n_rows == m.n_nodes:
+                mean[g] = st[2]
+    assert mean[2] > 1.8 * mean[1] and mean[3] > 2.7 * mean[1]
+    m2 = meshgen.cube(4, renumber="random", seed=3)
+    st = np.zeros(4)
+    rc = f(C.c_uint32(m2.n_nodes), C.c_uint32(m2.n_cells), np.ascontiguousarray(m2.cells, dtype=np.uint32).ctypes.data_as(C.c_void_p),
+           C.c_uint32(m2.n_nodes), C.c_uint32(2), st.ctypes.data_as(C.c_void_p))
+    assert rc in (0, 101)
+
+
 def test_plan_small_tiles_and_degenerate_cells(wb):
     m = meshgen.cube(4)
     for w, mc in ((4, 1), (6, 2), (9, 4), (16, 64)):

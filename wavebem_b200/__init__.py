@@ -77,7 +77,7 @@ ABI_SYMBOLS = [
     "wbem_solve_system", "wbem_solve", "wbem_solve_dev", "wbem_solve_system_dev", "wbem_residual",
     "wbem_get_system_rhs", "wbem_get_sol", "wbem_get_timings", "wbem_reset_counters",
     "wbem_comm_unique_id", "wbem_comm_init", "wbem_measure_fp64_peak", "wbem_measure_copy_bw",
-    "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check",
+    "wbem_time_operator", "wbem_time_assemble", "wbem_selftest_rsqrt", "wbem_plan_check", "wbem_stream_order_check",
     "wbem_timer_start", "wbem_timer_stop", "wbem_comm_ipc_export", "wbem_comm_ipc_import",
     "wbem_comm_ipc_close", "wbem_get_spai", "wbem_spai_pattern_check", "wbem_set_precond_kind",
     "wbem_compute_normals", "wbem_compute_surface_gradients", "wbem_set_hanging_constraints",

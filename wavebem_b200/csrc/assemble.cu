@@ -490,17 +490,18 @@ __device__ __forceinline__ void line_moments(const double *__restrict__ g, const
       }
 }
 
-// Two Gauss lines at once, written stage by stage over their 8 points: more independent dependency
+// NL Gauss lines at once, written stage by stage over their 4 NL points: more independent dependency
 // chains in flight per warp (the per-point chain r^2 -> rsqrt -> r^-3 -> moments is ~12 FP64 latencies deep).
-template <int J>
-__device__ __forceinline__ void line_pair_moments(const double *__restrict__ g, const double (&xi0)[T1_RPT],
-                                                  const double (&xi1)[T1_RPT], const double (&xi2)[T1_RPT], const double (&un)[4],
-                                                  const double (&wq)[4], const double (&wuq)[4], CellMoments &m)
+template <int J, int NL>
+__device__ __forceinline__ void line_group_moments(const double *__restrict__ g, const double (&xi0)[T1_RPT],
+                                                   const double (&xi1)[T1_RPT], const double (&xi2)[T1_RPT], const double (&un)[4],
+                                                   const double (&wq)[4], const double (&wuq)[4], CellMoments &m)
 {
   static_assert(T1_RPT == 1, "written for one row per thread");
-  double c0[2], c1[2], e0[2], e1[2], bb[2];
+  constexpr int NP = 4 * NL;
+  double c0[NL], c1[NL], e0[NL], e1[NL], bb[NL];
 #pragma unroll
-  for (int l = 0; l < 2; ++l)
+  for (int l = 0; l < NL; ++l)
     {
       const double2 *L = reinterpret_cast<const double2 *>(g + (J + l) * LINE_REC);
       const double2 l0 = L[0], l1 = L[1], l2 = L[2], l3 = L[3], l4 = L[4], l5 = L[5], l6 = L[6];
@@ -511,26 +512,26 @@ __device__ __forceinline__ void line_pair_moments(const double *__restrict__ g, 
       e0[l] = fma(Dz, l4.y, fma(Dy, l4.x, Dx * l3.y));
       e1[l] = fma(Dz, l6.x, fma(Dy, l5.y, Dx * l5.x));
     }
-  double r2[8], y[8], t[8], e[8], p[8], ye[8], ri[8], ri3[8], av[8];
+  double r2[NP], y[NP], t[NP], e[NP], p[NP], ye[NP], ri[NP], rr[NP], av[NP];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) r2[i] = fma(fma(bb[i >> 2], un[i & 3], c1[i >> 2]), un[i & 3], c0[i >> 2]);
+  for (int i = 0; i < NP; ++i) r2[i] = fma(fma(bb[i >> 2], un[i & 3], c1[i >> 2]), un[i & 3], c0[i >> 2]);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(r2[i]));
+  for (int i = 0; i < NP; ++i) asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y[i]) : "d"(r2[i]));
 #pragma unroll
-  for (int i = 0; i < 8; ++i) t[i] = r2[i] * y[i];
+  for (int i = 0; i < NP; ++i) t[i] = r2[i] * y[i];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) e[i] = fma(-t[i], y[i], 1.0);
+  for (int i = 0; i < NP; ++i) e[i] = fma(-t[i], y[i], 1.0);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) p[i] = fma(0.375, e[i], 0.5), ye[i] = y[i] * e[i];
+  for (int i = 0; i < NP; ++i) p[i] = fma(0.375, e[i], 0.5), ye[i] = y[i] * e[i];
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ri[i] = fma(p[i], ye[i], y[i]);
+  for (int i = 0; i < NP; ++i) ri[i] = fma(p[i], ye[i], y[i]);
 #pragma unroll
-  for (int i = 0; i < 8; ++i) ri3[i] = ri[i] * ri[i]; // r^-2
+  for (int i = 0; i < NP; ++i) rr[i] = ri[i] * ri[i]; // r^-2
 #pragma unroll
-  for (int i = 0; i < 8; ++i) av[i] = (fma(e1[i >> 2], un[i & 3], e0[i >> 2]) * ri[i]) * ri3[i];
+  for (int i = 0; i < NP; ++i) av[i] = (fma(e1[i >> 2], un[i & 3], e0[i >> 2]) * ri[i]) * rr[i];
   const double2 *wj2 = reinterpret_cast<const double2 *>(g + 4 * LINE_REC) + J * 4;
 #pragma unroll
-  for (int l = 0; l < 2; ++l)
+  for (int l = 0; l < NL; ++l)
     {
       double t0n = wq[0] * av[4 * l], t1n = wuq[0] * av[4 * l];
       const double2 w0 = wj2[4 * l];
@@ -939,20 +940,28 @@ __device__ __forceinline__ void signal_flushed(unsigned int *flag, uint32_t *cou
     }
 }
 
-// ticket -> (row tile, launch position); tile = 0xffffffff past the end
-__device__ __forceinline__ uint2 decode_ticket(const uint32_t t, const StreamArgs &a)
+// ticket -> (row tile, launch position); tile = 0xffffffff past the end.  Order: groups of group_tiles
+// row tiles; inside a group colour after colour, inside a colour tile after tile, cluster after cluster.
+__host__ __device__ __forceinline__ uint2 decode_ticket_order(const uint32_t t, const uint32_t n_items, const uint32_t n_clusters,
+                                                              const uint32_t row_tiles, const uint32_t group_tiles,
+                                                              const uint32_t n_colors, const uint32_t *color_ptr)
 {
-  if (t >= a.n_items) return make_uint2(0xffffffffu, 0u);
-  const uint32_t per_group = a.group_tiles * a.n_clusters;
+  if (t >= n_items) return make_uint2(0xffffffffu, 0u);
+  const uint32_t per_group = group_tiles * n_clusters;
   const uint32_t g = t / per_group;
   uint32_t r = t - g * per_group;
-  const uint32_t G = min(a.group_tiles, a.row_tiles - g * a.group_tiles);
+  const uint32_t left = row_tiles - g * group_tiles;
+  const uint32_t G = group_tiles < left ? group_tiles : left;
   uint32_t c = 0;
-  while (c + 1 < a.n_colors && r >= G * a.color_ptr[c + 1]) ++c;
-  r -= G * a.color_ptr[c];
-  const uint32_t nc = a.color_ptr[c + 1] - a.color_ptr[c];
+  while (c + 1 < n_colors && r >= G * color_ptr[c + 1]) ++c;
+  r -= G * color_ptr[c];
+  const uint32_t nc = color_ptr[c + 1] - color_ptr[c];
   const uint32_t tg = r / nc;
-  return make_uint2(g * a.group_tiles + tg, a.color_ptr[c] + (r - tg * nc));
+  return make_uint2(g * group_tiles + tg, color_ptr[c] + (r - tg * nc));
+}
+__device__ __forceinline__ uint2 decode_ticket(const uint32_t t, const StreamArgs &a)
+{
+  return decode_ticket_order(t, a.n_items, a.n_clusters, a.row_tiles, a.group_tiles, a.n_colors, a.color_ptr);
 }
 
 __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(const StreamArgs a)
@@ -1125,8 +1134,9 @@ __global__ void __launch_bounds__(T1_THREADS, WBEM_T1_MINCTAS) k_assemble_rows(c
               const uint32_t sl = mt->cell_slots[k];
               CellMoments cm;
 #if !defined(WBEM_NO_LINE_PAIRS) && WBEM_T1_RPT == 1
-              line_pair_moments<0>(g, xi0, xi1, xi2, un, wq, wuq, cm);
-              line_pair_moments<2>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              // (8 points in flight; all 16 at once, 156 registers, measured 1 % slower)
+              line_group_moments<0, 2>(g, xi0, xi1, xi2, un, wq, wuq, cm);
+              line_group_moments<2, 2>(g, xi0, xi1, xi2, un, wq, wuq, cm);
 #else
               line_moments<0>(g, xi0, xi1, xi2, un, wq, wuq, cm);
               line_moments<1>(g, xi0, xi1, xi2, un, wq, wuq, cm);
@@ -1670,6 +1680,49 @@ extern "C" int wbem_selftest_rsqrt(wbem_ctx *ctx, const double *in, double *out,
   CUDA_OK(ctx, cudaMemcpy(out, d_out, sizeof(double) * n, cudaMemcpyDeviceToHost));
   cudaFree(d_in);
   cudaFree(d_out);
+  return 0;
+}
+
+// Host-only check of the stream kernel's item order (no GPU; tests/test_plan_and_host.py): every (row tile,
+// cluster) gets exactly one ticket and every cluster's predecessors on the same tile hold lower tickets.
+// stats[0..3] = items, smallest / mean ticket distance between an item and a predecessor, row tiles.
+extern "C" int wbem_stream_order_check(uint32_t n_dofs, uint32_t n_cells, const uint32_t *cell_dofs, uint32_t n_rows,
+                                       uint32_t group_tiles, double *stats4)
+{
+  AssemblyPlan pl;
+  if (wbem_build_plan(n_dofs, n_cells, cell_dofs, T1_W, TILE_MAX_CELLS, &pl)) return 100;
+  if (pl.n_colors > STREAM_MAX_COLORS || pl.max_pred > META_PRED) return 101; // the colour kernel's case
+  const uint32_t ncl = pl.n_clusters, row_tiles = (n_rows + T1_ROWS - 1) / T1_ROWS;
+  const uint32_t n_items = row_tiles * ncl;
+  group_tiles = std::max(1u, std::min(group_tiles, row_tiles));
+  std::vector<uint32_t> ticket_of((size_t)n_items, 0xffffffffu);
+  for (uint32_t t = 0; t < n_items; ++t)
+    {
+      const uint2 it = decode_ticket_order(t, n_items, ncl, row_tiles, group_tiles, pl.n_colors, pl.color_ptr.data());
+      if (it.x >= row_tiles || it.y >= ncl) return 1;
+      uint32_t &slot = ticket_of[(size_t)it.x * ncl + it.y];
+      if (slot != 0xffffffffu) return 2; // drawn twice
+      slot = t;
+    }
+  if (decode_ticket_order(n_items, n_items, ncl, row_tiles, group_tiles, pl.n_colors, pl.color_ptr.data()).x != 0xffffffffu) return 3;
+  double dmin = 1e300, dsum = 0, dn = 0;
+  for (uint32_t tile = 0; tile < row_tiles; ++tile)
+    for (uint32_t k = 0; k < ncl; ++k)
+      for (uint32_t q = pl.pred_ptr[k]; q < pl.pred_ptr[k + 1]; ++q)
+        {
+          const uint32_t a = ticket_of[(size_t)tile * ncl + k], b = ticket_of[(size_t)tile * ncl + pl.pred[q]];
+          if (b >= a) return 4; // an item would wait for a ticket nobody has drawn yet
+          dmin = std::min(dmin, (double)(a - b));
+          dsum += a - b;
+          dn += 1;
+        }
+  if (stats4)
+    {
+      stats4[0] = n_items;
+      stats4[1] = dn ? dmin : 0;
+      stats4[2] = dn ? dsum / dn : 0;
+      stats4[3] = row_tiles;
+    }
   return 0;
 }
 
