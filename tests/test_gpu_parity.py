@@ -555,6 +555,43 @@ def test_spai_preconditioner_rows_and_solve(wb, orc, tank_case):
     ctx.close()
 
 
+def test_spai_gmres_batches_restarts_and_step_limit(wb, orc, tank_case):
+    """With the sparse approximate inverse the host enqueues 4 iterations ahead and the Arnoldi step's small
+    algebra runs on the device: restart cycles shorter than, equal to and not a multiple of the batch, a step
+    limit that falls inside a batch (NoConvergence with exactly max_steps iterations), and the same solution as
+    one long cycle."""
+    t = tank_case
+    m = t["m"]
+    n = m.n_nodes
+    z = np.zeros(n)
+    tol = 1e-10
+
+    def run(n_tmp, steps):
+        ctx = _ctx(wb, m, precond_kind=1, gmres_tol=tol, gmres_max_steps=steps, gmres_n_tmp_vectors=n_tmp)
+        ctx.assemble()
+        ctx.set_masks(m.surface_nodes, m.other_nodes)
+        ctx.set_constraints(t["cl"])
+        try:
+            _, _, it, res = ctx.solve_system(z, z, t["bc"])
+            out = (True, it, res, ctx.get_sol())
+        except wb.NoConvergence:
+            out = (False, int(ctx.timings()["gmres_iters"]), None, ctx.get_sol())
+        ctx.close()
+        return out
+
+    ok, it_long, res, x_long = run(100, 400)
+    assert ok and res <= tol and it_long < 40
+    for n_tmp in (5, 6, 9, 12):  # cycles of 3, 4, 7, 10 inner iterations
+        ok, it, res, x = run(n_tmp, 2000)
+        assert ok and res <= tol and it >= it_long
+        assert np.linalg.norm(x - x_long) <= 1e-7 * np.linalg.norm(x_long)
+    for steps in (it_long - 1, it_long - 2, 5, 1):
+        ok, it, _, _ = run(100, steps)
+        assert not ok and it == steps
+    ok, it, _, _ = run(100, it_long)
+    assert ok and it == it_long
+
+
 @pytest.mark.parametrize("mesh", ["cube1", "cube4_random_flipped"])
 def test_spai_on_tiny_and_randomly_numbered_meshes(wb, orc, mesh):
     """Fewer dofs than K (padding slots) and a random numbering (the band preconditioner depends
