@@ -24,6 +24,6 @@ print("items with > 20 spins:", len(t))
 print("by tile % G(=env):", np.bincount(t % int(os.environ.get("WBEM_ASM_GROUP", "3")), minlength=1))
 print("kpos histogram (10 bins):", np.histogram(k, bins=10, range=(0, ncl))[0])
 print("tile histogram (10 bins):", np.histogram(t, bins=10, range=(0, tiles))[0])
-order = np.argsort(-spins.ravel())[:30]
+order = np.argsort(-spins.ravel().astype(np.int64))[:30]
 for o in order:
     print("  tile", o // ncl, "kpos", o % ncl, "spins", spins.ravel()[o], "cta", cta.ravel()[o])

@@ -237,8 +237,8 @@ __device__ __forceinline__ void con_grid_barrier(unsigned int *counter, unsigned
   if (threadIdx.x == 0)
     {
       ++epoch;
-      __threadfence();
-      atomicAdd(counter, 1u);
+      // release (the CTA's writes, ordered before this thread by the barrier above) / acquire: no further fences
+      asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(counter) : "memory");
       const unsigned int target = epoch * gridDim.x;
       unsigned int v;
       do
@@ -246,7 +246,6 @@ __device__ __forceinline__ void con_grid_barrier(unsigned int *counter, unsigned
           asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(counter) : "memory");
         }
       while (v < target);
-      __threadfence();
     }
   __syncthreads();
 }
@@ -330,11 +329,14 @@ __global__ void __launch_bounds__(CG_THREADS, 1)
   double *part0 = part, *part1 = part + (size_t)gridDim.x * 3;
 
   auto total = [&](const double *pp, double out[3]) { // same order in every CTA: identical results
-    if (threadIdx.x < 3)
-      {
+    if (threadIdx.x < 96)
+      { // one warp per component: lanes stride over the CTAs' partials (L2), then a fixed shuffle tree
+        const uint32_t d = threadIdx.x >> 5, lane = threadIdx.x & 31;
         double t = 0;
-        for (uint32_t c = 0; c < gridDim.x; ++c) t += __ldcg(pp + (size_t)c * 3 + threadIdx.x); // other CTAs' data: L2
-        s_tot[threadIdx.x] = t;
+        for (uint32_t c = lane; c < gridDim.x; c += 32) t += __ldcg(pp + (size_t)c * 3 + d);
+#pragma unroll
+        for (int off = 16; off > 0; off >>= 1) t += __shfl_xor_sync(0xffffffffu, t, off);
+        if (lane == 0) s_tot[d] = t;
       }
     __syncthreads();
     for (int d = 0; d < 3; ++d) out[d] = s_tot[d];
