@@ -1,18 +1,24 @@
 // assemble.cu -- sm_100a kernels for BEMProblem<3>::assemble_system
 // (reference source/bem_problem.cc:106-590) and compute_alpha (:594-618).
 //
-//   k_cell_geometry      FEValues of the regular rule for every cell (:133-137, 192-196),
-//                        folded into per-(cell,q) constants:  y_q, n_q JxW_q /(-4 pi), JxW_q/(4 pi),
-//                        JxW_q u_q/(4 pi)
-//   k_assemble_rows      regular (node, cell) pairs (:241-260, 531-537): one CTA per
-//                        (128-row tile, cell cluster), one thread per row; panel data staged in
-//                        shared memory by a TMA bulk copy; per-column accumulators in shared
-//                        memory; deterministic STORE/ADD flush (see plan.cpp)
+//   k_cell_geometry      FEValues of the regular rule for every cell (:133-137, 192-196), folded into
+//                        per-(cell,q) records  y_q, n_q JxW_q /(-4 pi), JxW_q/(4 pi), JxW_q u_q/(4 pi)
+//                        and, for the 4 x 4 rule, into the line records of the stream kernel
+//   k_assemble_rows      regular (node, cell) pairs (:241-260, 531-537), the default: ONE persistent
+//                        launch; work items (128-row tile, cell cluster) drawn from a ticket counter;
+//                        line-wise polynomial arithmetic; panel chunks through a TMA / mbarrier pipeline;
+//                        per-column accumulators in shared memory; STORE / ADD flush ordered by done
+//                        flags between the clusters sharing a column (see plan.cpp): deterministic
+//   k_assemble_colours   the same tiling with per-point arithmetic, one launch per colour
+//                        (assemble_variant = 2; caller-supplied FEValues; plans the stream kernel's
+//                        records cannot hold)
 //   k_assemble_simple    same integrals, literal reference arithmetic, global atomics: the
 //                        independent cross-check and the fallback for quadrature orders != 4
 //   k_assemble_singular  pairs whose cell holds a dof of double_nodes_set[i] (:223-230,
 //                        261-525): QGaussOneOverR rule, one warp per row, shuffle reduction
-//   k_alpha_rowsum       alpha = -row sums of the Neumann matrix (:594-618)
+//   k_alpha_from_parts / k_alpha_rowsum   alpha = -row sums of the Neumann matrix (:594-618)
+// Development switches (never set in the product build): -DWBEM_DBG_NOWAIT / _NOFLUSH / _WAITLOG time the
+// kernel without its dependency waits / without the flush, or log the spins per work item.
 #include <algorithm>
 #include <cstdio>
 #include <cstdlib>
