@@ -915,12 +915,6 @@ constexpr size_t stream_smem_bytes()
          (2 * T1_NBUF + 2) * sizeof(uint64_t) + (T1_NBUF + 2 + (T1_NBUF & 1)) * sizeof(uint32_t) + 2 * sizeof(uint2) + 2 * sizeof(uint2);
 }
 
-__device__ __forceinline__ unsigned int ld_relaxed_gpu(const unsigned int *p)
-{
-  unsigned int v;
-  asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
-  return v;
-}
 __device__ __forceinline__ void st_relaxed_gpu(unsigned int *p, unsigned int v)
 {
   asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
