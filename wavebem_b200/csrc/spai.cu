@@ -24,6 +24,7 @@
 #include <algorithm>
 #include <cmath>
 #include <cstdio>
+#include <thread>
 #include <vector>
 
 #include "internal.h"
@@ -62,57 +63,75 @@ static void spai_build_neighbours(uint32_t N, uint32_t C, const uint32_t *cell_d
       for (int j = 0; j < 4; ++j) nadj[fill[cell_dofs[4 * (size_t)c + j]]++] = c;
   }
   nbr.assign((size_t)N * K, SPAI_NONE);
-  std::vector<uint32_t> mark(N, SPAI_NONE), order, frontier, next;
-  std::vector<std::pair<double, uint32_t>> cand;
-  for (uint32_t i = 0; i < N; ++i)
-    {
-      order.clear();
-      frontier.clear();
-      mark[i] = i;
-      order.push_back(i);
-      frontier.push_back(i);
-      // collect ~3K candidates (whole rings): on stretched cells the K nearest dofs are not the
-      // first rings
-      while (order.size() < 3 * (size_t)K && !frontier.empty())
-        {
-          next.clear();
-          for (uint32_t u : frontier)
-            {
-              for (uint32_t a = nptr[u]; a < nptr[u + 1]; ++a)
-                for (int j = 0; j < 4; ++j)
+  // rows are independent: host threads over row ranges, each with its own scratch (reinit() runs on every remesh)
+  auto rows = [&](uint32_t i0, uint32_t i1) {
+    std::vector<uint32_t> mark(N, SPAI_NONE), order, frontier, next;
+    std::vector<std::pair<double, uint32_t>> cand;
+    for (uint32_t i = i0; i < i1; ++i)
+      {
+        order.clear();
+        frontier.clear();
+        mark[i] = i;
+        order.push_back(i);
+        frontier.push_back(i);
+        // collect ~3K candidates (whole rings): on stretched cells the K nearest dofs are not the
+        // first rings
+        while (order.size() < 3 * (size_t)K && !frontier.empty())
+          {
+            next.clear();
+            for (uint32_t u : frontier)
+              {
+                for (uint32_t a = nptr[u]; a < nptr[u + 1]; ++a)
+                  for (int j = 0; j < 4; ++j)
+                    {
+                      const uint32_t v = cell_dofs[4 * (size_t)nadj[a] + j];
+                      if (mark[v] != i)
+                        {
+                          mark[v] = i;
+                          next.push_back(v);
+                        }
+                    }
+                for (uint32_t a = dn_ptr[u]; a < dn_ptr[u + 1]; ++a)
                   {
-                    const uint32_t v = cell_dofs[4 * (size_t)nadj[a] + j];
+                    const uint32_t v = dn_idx[a];
                     if (mark[v] != i)
                       {
                         mark[v] = i;
                         next.push_back(v);
                       }
                   }
-              for (uint32_t a = dn_ptr[u]; a < dn_ptr[u + 1]; ++a)
-                {
-                  const uint32_t v = dn_idx[a];
-                  if (mark[v] != i)
-                    {
-                      mark[v] = i;
-                      next.push_back(v);
-                    }
-                }
-            }
-          order.insert(order.end(), next.begin(), next.end());
-          frontier.swap(next);
-        }
-      cand.clear();
-      for (uint32_t v : order)
+              }
+            order.insert(order.end(), next.begin(), next.end());
+            frontier.swap(next);
+          }
+        cand.clear();
+        for (uint32_t v : order)
+          {
+            const double dx = xyz[3 * (size_t)v] - xyz[3 * (size_t)i], dy = xyz[3 * (size_t)v + 1] - xyz[3 * (size_t)i + 1],
+                         dz = xyz[3 * (size_t)v + 2] - xyz[3 * (size_t)i + 2];
+            cand.emplace_back(v == i ? -1.0 : dx * dx + dy * dy + dz * dz, v);
+          }
+        const size_t keep = std::min<size_t>(K, cand.size());
+        std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
+        uint32_t *row = nbr.data() + (size_t)i * K;
+        for (size_t k = 0; k < keep; ++k) row[k] = cand[k].second;
+        std::sort(row, row + keep);
+      }
+  };
+  unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (N < 4096) nt = 1;
+  if (nt == 1)
+    rows(0, N);
+  else
+    {
+      std::vector<std::thread> pool;
+      const uint32_t per = (N + nt - 1) / nt;
+      for (unsigned t = 0; t < nt; ++t)
         {
-          const double dx = xyz[3 * (size_t)v] - xyz[3 * (size_t)i], dy = xyz[3 * (size_t)v + 1] - xyz[3 * (size_t)i + 1],
-                       dz = xyz[3 * (size_t)v + 2] - xyz[3 * (size_t)i + 2];
-          cand.emplace_back(v == i ? -1.0 : dx * dx + dy * dy + dz * dz, v);
+          const uint32_t i0 = std::min(N, t * per), i1 = std::min(N, (t + 1) * per);
+          if (i0 < i1) pool.emplace_back(rows, i0, i1);
         }
-      const size_t keep = std::min<size_t>(K, cand.size());
-      std::partial_sort(cand.begin(), cand.begin() + keep, cand.end());
-      uint32_t *row = nbr.data() + (size_t)i * K;
-      for (size_t k = 0; k < keep; ++k) row[k] = cand[k].second;
-      std::sort(row, row + keep);
+      for (auto &th : pool) th.join();
     }
 }
 
@@ -134,30 +153,62 @@ static uint32_t spai_build_nearfield_pattern(uint32_t N, uint32_t K, const std::
           if (r != SPAI_NONE) rev[fill[r]++] = i;
         }
   }
+  // rows are independent: host threads over row ranges, concatenated in row order afterwards
+  unsigned nt = std::min(16u, std::max(1u, std::thread::hardware_concurrency()));
+  if (N < 4096) nt = 1;
+  const uint32_t per = (N + nt - 1) / nt;
+  std::vector<std::vector<uint32_t>> cols(nt), lens(nt);
+  std::vector<uint32_t> widest_t(nt, 0);
+  auto rows = [&](unsigned t) {
+    const uint32_t r0 = std::min(N, t * per), r1 = std::min(N, (t + 1) * per);
+    std::vector<uint32_t> mark(N, SPAI_NONE);
+    std::vector<uint32_t> &ec = cols[t];
+    ec.reserve((size_t)(r1 - r0) * 4 * K);
+    lens[t].reserve(r1 - r0);
+    for (uint32_t r = r0; r < r1; ++r)
+      {
+        const size_t b = ec.size();
+        for (uint32_t a = rptr[r]; a < rptr[r + 1]; ++a)
+          {
+            const uint32_t *row = nbr.data() + (size_t)rev[a] * K;
+            for (uint32_t k = 0; k < K; ++k)
+              {
+                const uint32_t c = row[k];
+                if (c != SPAI_NONE && mark[c] != r)
+                  {
+                    mark[c] = r;
+                    ec.push_back(c);
+                  }
+              }
+          }
+        std::sort(ec.begin() + b, ec.end());
+        lens[t].push_back((uint32_t)(ec.size() - b));
+        widest_t[t] = std::max(widest_t[t], (uint32_t)(ec.size() - b));
+      }
+  };
+  if (nt == 1)
+    rows(0);
+  else
+    {
+      std::vector<std::thread> pool;
+      for (unsigned t = 0; t < nt; ++t) pool.emplace_back(rows, t);
+      for (auto &th : pool) th.join();
+    }
   eptr.assign(N + 1, 0);
   ecol.clear();
-  ecol.reserve((size_t)N * 4 * K);
-  std::vector<uint32_t> mark(N, SPAI_NONE);
-  uint32_t widest = 0;
-  for (uint32_t r = 0; r < N; ++r)
+  uint32_t widest = 0, r = 0;
+  size_t total = 0;
+  for (unsigned t = 0; t < nt; ++t) total += cols[t].size();
+  ecol.reserve(total);
+  for (unsigned t = 0; t < nt; ++t)
     {
-      const size_t b = ecol.size();
-      for (uint32_t a = rptr[r]; a < rptr[r + 1]; ++a)
+      ecol.insert(ecol.end(), cols[t].begin(), cols[t].end());
+      for (uint32_t l : lens[t])
         {
-          const uint32_t *row = nbr.data() + (size_t)rev[a] * K;
-          for (uint32_t k = 0; k < K; ++k)
-            {
-              const uint32_t c = row[k];
-              if (c != SPAI_NONE && mark[c] != r)
-                {
-                  mark[c] = r;
-                  ecol.push_back(c);
-                }
-            }
+          eptr[r + 1] = eptr[r] + l;
+          ++r;
         }
-      std::sort(ecol.begin() + b, ecol.end());
-      eptr[r + 1] = (uint32_t)ecol.size();
-      widest = std::max(widest, (uint32_t)(ecol.size() - b));
+      widest = std::max(widest, widest_t[t]);
     }
   return widest;
 }
