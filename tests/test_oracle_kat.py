@@ -487,3 +487,57 @@ def test_sparse_projection_restatement_matches_the_c_oracle_and_condenses_hangin
     h0, ent = hang2[0]
     assert np.abs(gc[h0] - sum(w * gc[mm] for mm, w in ent)).max() < 1e-12
     assert np.abs(gc - gu).max() > 1e-6
+
+
+def test_line_records_reproduce_the_pointwise_integrand_on_warped_cells(orc):
+    """The identities behind k_assemble_rows' line records (assemble.cu): on a bilinear cell, along a Gauss line
+    v = v_j, y(u) = A + u B and d_u y x d_v y = P + u Q with B.P = B.Q = 0, hence for D = A - x
+        |y - x|^2 = D.D + u (2 B.D) + u^2 B.B        and        (y - x).n JxW = w_u w_v (D.P + u D.Q) sign.
+    A numpy restatement of the records (k_cell_geometry) against the oracle's FEValues (quadrature points,
+    normals, JxW of deal.II's MappingQ1) on warped, non-planar cells of both orientations, for collocation points
+    near and far: integrands and the four shape-function sums of both kernels agree to rounding."""
+    rng = np.random.default_rng(5)
+    x1, w1 = orc.gauss01(4)
+    uv, w = orc.qgauss2(4)            # point q = 4 j + i  <->  (u_i, v_j)
+    assert np.allclose(uv[:, 0], np.tile(x1, 4)) and np.allclose(uv[:, 1], np.repeat(x1, 4))
+    for trial in range(20):
+        X = np.array([[0, 0, 0], [1, 0, 0], [0, 1, 0], [1, 1, 0]], float) * rng.uniform(0.2, 3.0, 3)
+        X += rng.normal(0, 0.15, X.shape) + rng.uniform(-5, 5, 3)   # warped (non-planar), anywhere in space
+        flag = trial % 2
+        sgn = 1.0 if flag else -1.0
+        qp, nr, jw, sh = orc.fe_values(X, flag, uv, w)
+        cc = X[2] - X[0]
+        dd = (X[3] - X[2]) - (X[1] - X[0])
+        for x in (X.mean(0) + rng.normal(0, 0.7, 3), X[0] + rng.normal(0, 30.0, 3), X[3] + 0.3 * (X[3] - X[0])):
+            r_ref = qp - x
+            r2_ref = (r_ref ** 2).sum(1)
+            rn_ref = (r_ref * nr).sum(1) * jw
+            sums_n = np.zeros(4)
+            sums_d = np.zeros(4)
+            for j in range(4):
+                v = x1[j]
+                A = X[0] + v * cc
+                B = (X[1] - X[0]) + v * dd
+                P = np.cross(B, cc) * sgn * w1[j]
+                Q = np.cross(B, dd) * sgn * w1[j]
+                assert abs(B @ np.cross(B, cc)) < 1e-12 and abs(B @ np.cross(B, dd)) < 1e-12
+                D = A - x
+                c0, c1, c2, e0, e1 = D @ D, 2 * (B @ D), B @ B, D @ P, D @ Q
+                for i in range(4):
+                    u = x1[i]
+                    q = 4 * j + i
+                    r2 = (c2 * u + c1) * u + c0
+                    rn = w1[i] * (e1 * u + e0)
+                    assert abs(r2 - r2_ref[q]) <= 1e-13 * max(r2_ref[q], (np.abs(X - x) ** 2).sum(1).max())
+                    assert abs(rn - rn_ref[q]) <= 1e-13 * np.abs(r_ref[q]).max() * jw[q] + 1e-15
+                    ri = 1.0 / np.sqrt(r2)
+                    kn, kd = rn * ri ** 3 / (-4 * np.pi), jw[q] * ri / (4 * np.pi)
+                    phi = np.array([(1 - u) * (1 - v), u * (1 - v), (1 - u) * v, u * v])
+                    sums_n += kn * phi
+                    sums_d += kd * phi
+            # the reference's pointwise sums (bem_problem.cc:241-260 with LaplaceKernel, laplace_kernel.h:47-57)
+            r = np.sqrt(r2_ref)
+            ref_n = ((r_ref * nr).sum(1) / (-4 * np.pi * r ** 3) * jw) @ sh.T
+            ref_d = (1.0 / (4 * np.pi * r) * jw) @ sh.T
+            assert np.abs(sums_n - ref_n).max() <= 1e-13 * max(np.abs(ref_n).max(), 1e-300) + 1e-16
+            assert np.abs(sums_d - ref_d).max() <= 1e-13 * np.abs(ref_d).max()
